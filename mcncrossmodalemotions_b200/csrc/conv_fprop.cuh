@@ -1,0 +1,267 @@
+// conv_fprop.cuh -- implicit-GEMM convolution forward on tcgen05 tensor cores (sm_100a).
+//
+// Replaces (behind the C ABI in include/xemo.h) the arithmetic of MatConvNet's vl_nnconv forward,
+// the operator that dagnn.Conv.forward calls from dag.eval at
+//   /root/reference/emoVoxCeleb/fetch_emovoxceleb_imdb.m:129, external/compute_visual_feats.m:90,
+//   external/compute_audio_feats.m:126 and inside cnn_train_dag (emoVoxCeleb/run_distillation.m:170).
+//
+// GEMM view:  D[M = N*OH*OW, Kout] = sum_{r,s,c} X[n, oh*sy+r-pt, ow*sx+s-pl, c] * F[kout, r, s, c]
+//   A (activations) : NHWC fp16, fetched by TMA in im2col mode -- 128 consecutive output pixels x BK
+//                     channels per (r,s) filter tap, zero-filled outside the image, 128/64/32B-swizzled.
+//   B (filters)     : [Kout][R][S][C] fp16 (K-major), fetched by tiled TMA, same swizzle.
+//   D (accumulator) : fp32 in TMEM, 128 lanes x block_n columns, double-buffered (2 x 256 columns) so
+//                     the epilogue of tile i overlaps the main loop of tile i+1.
+// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0   : TMA producer (one elected lane)
+//   warp 1   : tcgen05.mma issuer (one elected lane)
+//   warps 2-5: epilogue -- tcgen05.ld, per-channel scale/shift (folded test-mode BN or bias), optional
+//              residual add, optional ReLU, fp16 (and/or fp32) store.  Warp 2 also owns TMEM alloc/free.
+#pragma once
+#include "xemo_ptx.cuh"
+
+namespace xemo {
+
+constexpr int kConvBlockM = 128;
+constexpr int kConvThreads = 192;
+constexpr int kConvTmemCols = 512;
+
+struct ConvFpropParams {
+  int M;       // N*OH*OW output pixels
+  int Kout;    // output channels (ldc of the output matrix)
+  int Cin, R, S;
+  int OH, OW;
+  int stride_h, stride_w, pad_t, pad_l;
+  int block_n;      // N tile: multiple of 16, <= 256, divides Kout
+  int num_m_tiles;  // ceil(M / 128)
+  int num_n_tiles;  // Kout / block_n
+  int kc_blocks;    // Cin / BK
+  int num_stages;
+  // epilogue: y = acc * scale[k] + shift[k] (+ residual) ; relu ; store
+  const float* scale;       // [Kout] or nullptr (=1)
+  const float* shift;       // [Kout] or nullptr (=0)
+  const __half* residual;   // [M, Kout] or nullptr
+  int relu;
+  __half* out;              // [M, Kout] fp16 or nullptr
+  float* out_f32;           // [M, Kout] fp32 or nullptr
+};
+
+template <int BK>
+struct ConvSwizzle;
+template <>
+struct ConvSwizzle<64> { static constexpr uint32_t mode = 2; };  // 128B
+template <>
+struct ConvSwizzle<32> { static constexpr uint32_t mode = 4; };  // 64B
+template <>
+struct ConvSwizzle<16> { static constexpr uint32_t mode = 6; };  // 32B
+
+__host__ __device__ inline int conv_stage_bytes(int bk, int block_n) {
+  const int a_bytes = kConvBlockM * bk * 2;
+  const int b_bytes = ((block_n * bk * 2) + 1023) & ~1023;
+  return a_bytes + b_bytes;
+}
+
+template <int BK>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvFpropParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // swizzled TMA/UMMA tiles want 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  constexpr int kABytes = kConvBlockM * BK * 2;
+  const int b_bytes = p.block_n * BK * 2;
+  const int stage_bytes = conv_stage_bytes(BK, p.block_n);
+  const int num_stages = p.num_stages;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(num_stages) * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + num_stages;
+  uint64_t* tmem_full_bar = bars + 2 * num_stages;
+  uint64_t* tmem_empty_bar = bars + 2 * num_stages + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * num_stages + 4);
+
+  const int warp = threadIdx.x >> 5;  // warp-uniform
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    for (int s = 0; s < num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, kConvTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int k_iters = p.R * p.S * p.kc_blocks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int ohw = p.OH * p.OW;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int m0 = m_tile * kConvBlockM;
+        const int n_img = m0 / ohw;
+        const int rem = m0 - n_img * ohw;
+        const int oh = rem / p.OW;
+        const int ow = rem - oh * p.OW;
+        const int w_base = ow * p.stride_w - p.pad_l;
+        const int h_base = oh * p.stride_h - p.pad_t;
+        const int n0 = n_tile * p.block_n;
+        for (int r = 0; r < p.R; ++r) {
+          for (int s = 0; s < p.S; ++s) {
+            const int kbase = (r * p.S + s) * p.Cin;
+            for (int kc = 0; kc < p.kc_blocks; ++kc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + size_t(stage) * stage_bytes;
+              uint8_t* sb = sa + kABytes;
+              mbar_arrive_expect_tx(&full_bar[stage], uint32_t(kABytes + b_bytes));
+              tma_load_im2col_4d(&tmA, &full_bar[stage], sa, kc * BK, w_base, h_base, n_img, uint16_t(s),
+                                 uint16_t(r));
+              tma_load_2d(&tmB, &full_bar[stage], sb, kbase + kc * BK, n0);
+              if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_f16(kConvBlockM, p.block_n, 0, 0);
+      constexpr uint32_t kSbo = 8 * BK * 2;  // 8 rows of BK fp16
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc) * 256u;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + size_t(stage) * stage_bytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t a_desc = make_smem_desc(sa, 16, kSbo, ConvSwizzle<BK>::mode);
+          const uint64_t b_desc = make_smem_desc(sb, 16, kSbo, ConvSwizzle<BK>::mode);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
+            umma_f16_ss(d_tmem, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc,
+                        (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps 2..5
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int row = m_tile * kConvBlockM + row_in_tile;
+      const int n0 = n_tile * p.block_n;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc) * 256u;
+      const bool row_ok = row < p.M;
+      const size_t row_off = size_t(row) * p.Kout + n0;
+      for (int j = 0; j < p.block_n; j += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + uint32_t(j), v);
+        tmem_ld_wait();
+        if (row_ok) {
+          float x[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
+          if (p.scale) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + j + i));
+              x[i] *= sc.x; x[i + 1] *= sc.y; x[i + 2] *= sc.z; x[i + 3] *= sc.w;
+            }
+          }
+          if (p.shift) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + j + i));
+              x[i] += sh.x; x[i + 1] += sh.y; x[i + 2] += sh.z; x[i + 3] += sh.w;
+            }
+          }
+          if (p.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + j);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint4 rv = __ldg(rp + h);
+              const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(r2[i]);
+                x[h * 8 + 2 * i] += f.x;
+                x[h * 8 + 2 * i + 1] += f.y;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
+          }
+          if (p.out) {
+            uint4 o[2];
+            __half2* o2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o2[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+            uint4* op = reinterpret_cast<uint4*>(p.out + row_off + j);
+            op[0] = o[0];
+            op[1] = o[1];
+          }
+          if (p.out_f32) {
+            float4* fp = reinterpret_cast<float4*>(p.out_f32 + row_off + j);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) fp[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kConvTmemCols);
+  }
+}
+
+}  // namespace xemo
