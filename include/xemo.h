@@ -1,0 +1,213 @@
+/* xemo.h -- C ABI of libxemo.so: the B200-native (sm_100a) replacement for the MatConvNet /
+ * mcnExtraLayers operator back-end that albanie/mcnCrossModalEmotions reaches through
+ * dagnn.DagNN.eval and cnn_train_dag.
+ *
+ * The reference repository contains no native code; the interface this ABI replaces is the MEX
+ * gateway of the un-vendored upstream operators (vl_nnconv, vl_nnbnorm, vl_nnpool, vl_nnrelu,
+ * vl_nnsigmoid, vl_nnsoftmaxceloss, ...), reached from the reference at
+ *   emoVoxCeleb/fetch_emovoxceleb_imdb.m:129      dag.eval (teacher forward)
+ *   external/compute_visual_feats.m:90            dag.eval (teacher forward)
+ *   external/compute_audio_feats.m:126            dag.eval (student forward)
+ *   emoVoxCeleb/run_distillation.m:170-182        cnn_train_dag (student forward/backward/update)
+ *   emoVoxCeleb/emoVoxZoo.m:151-157               dagnn.SoftmaxCELoss(T=2, logitTargets)
+ *
+ * Two layers of entry points:
+ *   (A) xemo_vl_*   MatConvNet-boundary operators.  Arrays are `single`, H x W x C x N, column-major
+ *                   (MATLAB layout), in host OR device memory (detected per pointer); outputs are
+ *                   caller-allocated and live where the caller put them.  Forward when `dzdy` is
+ *                   NULL, backward otherwise -- the MATLAB calling convention.  These are what the
+ *                   MEX shims in mex/ forward to.
+ *   (B) xemo_op_*   device-native building blocks on NHWC fp16 activations (fp32 where stated) that
+ *                   the host-side graph compiler (mcncrossmodalemotions_b200/dagnn.py) strings
+ *                   together into fused teacher / student / distillation-step programs, captured
+ *                   as CUDA graphs (xemo_capture_*).
+ *
+ * Conventions: every function returns 0 on success or an xemo_status error code; the message is
+ * available from xemo_last_error().  No exceptions cross the ABI.  A context is bound to one device
+ * and one stream and is not thread-safe; all work is asynchronous on that stream unless the call
+ * returns data to host memory.  The caller owns every buffer it passes in.  There is no CPU
+ * fallback: without an sm_100 device xemo_create fails.
+ */
+#ifndef XEMO_H_
+#define XEMO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xemo_ctx xemo_ctx;
+typedef struct xemo_graph xemo_graph;
+
+typedef enum {
+  XEMO_OK = 0,
+  XEMO_ERR_INVALID = 1,     /* bad argument / unsupported shape */
+  XEMO_ERR_CUDA = 2,        /* CUDA runtime or driver error */
+  XEMO_ERR_NO_DEVICE = 3,   /* no sm_100 device / TMA entry points unavailable */
+  XEMO_ERR_NOMEM = 4
+} xemo_status;
+
+/* single-precision MATLAB array: dims H x W x C x N, column-major (index h + H*(w + W*(c + C*n))) */
+typedef struct {
+  void* data;
+  int64_t h, w, c, n;
+} xemo_array;
+
+/* ------------------------------------------------------------------ context */
+int xemo_version(void);
+/* `cuda_stream` is a cudaStream_t (NULL: the context creates its own non-blocking stream). */
+int xemo_create(int device, void* cuda_stream, xemo_ctx** out);
+void xemo_destroy(xemo_ctx* ctx);
+const char* xemo_last_error(xemo_ctx* ctx);
+int xemo_sync(xemo_ctx* ctx);
+int xemo_num_sms(xemo_ctx* ctx);
+/* number of kernels this context has launched (graph replays count their kernel nodes) */
+uint64_t xemo_launch_count(xemo_ctx* ctx);
+/* async copies on the context stream (host memory should be pinned for true asynchrony) */
+int xemo_h2d(xemo_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int xemo_d2h(xemo_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int xemo_memset(xemo_ctx* ctx, void* dst_dev, int byte, size_t bytes);
+
+/* CUDA-graph capture of a sequence of xemo_op_* calls on the context stream */
+int xemo_capture_begin(xemo_ctx* ctx);
+int xemo_capture_end(xemo_ctx* ctx, xemo_graph** out);
+int xemo_graph_launch(xemo_ctx* ctx, xemo_graph* g);
+int xemo_graph_num_kernels(xemo_graph* g);
+void xemo_graph_destroy(xemo_graph* g);
+
+/* ------------------------------------------------------------------ (A) MatConvNet-boundary operators */
+/* output size rule shared by vl_nnconv / vl_nnpool: floor((H + pt + pb - FH)/sy) + 1 */
+int xemo_out_size(int64_t h, int64_t w, int fh, int fw, const int pad[4], const int stride[2], int64_t* oh,
+                  int64_t* ow);
+
+/* Y = vl_nnconv(X, F, B, 'pad', pad, 'stride', stride)            (dzdy == NULL; y written)
+ * [DX, DF, DB] = vl_nnconv(X, F, B, DZDY, ...)                    (dx / df / db written; each may be NULL)
+ * F is FH x FW x FC x K with FC == C (no groups on this path); B is K x 1 or NULL. */
+int xemo_vl_nnconv(xemo_ctx* ctx, const xemo_array* x, const xemo_array* f, const xemo_array* b,
+                   const xemo_array* dzdy, const int pad[4], const int stride[2], xemo_array* y, xemo_array* dx,
+                   xemo_array* df, xemo_array* db);
+
+/* method: 0 = max (padding = -inf; backward to the first maximum of the memory-order scan), 1 = avg
+ * (divides by the in-bounds window area).  `argmax` (optional, forward max only) receives the
+ * window-local index dw*PH + dh as uint8, OH x OW x C x N column-major, same memory space as y. */
+int xemo_vl_nnpool(xemo_ctx* ctx, const xemo_array* x, const int pool[2], const xemo_array* dzdy, const int pad[4],
+                   const int stride[2], int method, xemo_array* y_or_dx, uint8_t* argmax);
+
+/* [Y, MOMENTS] = vl_nnbnorm(X, G, B, 'epsilon', e [, 'moments', M])  /  [DX, DG, DB, MOMENTS] = ...(.., DZDY, ..)
+ * g, b: C x 1; moments: C x 2 = [mu sigma] (sigma, not variance).  moments_in NULL = batch statistics. */
+int xemo_vl_nnbnorm(xemo_ctx* ctx, const xemo_array* x, const float* g, const float* b, const xemo_array* dzdy,
+                    float epsilon, const float* moments_in, xemo_array* y_or_dx, float* dg, float* db,
+                    float* moments_out);
+
+int xemo_vl_nnrelu(xemo_ctx* ctx, const xemo_array* x, const xemo_array* dzdy, float leak, xemo_array* y_or_dx);
+int xemo_vl_nnsigmoid(xemo_ctx* ctx, const xemo_array* x, const xemo_array* dzdy, xemo_array* y_or_dx);
+/* softmax along dim 3 (channels) of x / temperature */
+int xemo_vl_nnsoftmaxt(xemo_ctx* ctx, const xemo_array* x, float temperature, xemo_array* y);
+/* Y = vl_nnsoftmaxceloss(X, P, 'temperature', T, 'logitTargets', lt, 'instanceWeights', W): scalar *loss;
+ * DX = vl_nnsoftmaxceloss(X, P, DZDY, ...): dx written.  x, p: 1 x 1 x C x N with C <= 16. */
+int xemo_vl_nnsoftmaxceloss(xemo_ctx* ctx, const xemo_array* x, const xemo_array* p, const float* dzdy,
+                            float temperature, int logit_targets, const float* instance_weights, float* loss,
+                            xemo_array* dx);
+/* vl_nnloss(X, c, [], 'loss', 'classerror'): labels are 1-based (float, as MATLAB passes them) */
+int xemo_vl_nnloss_classerror(xemo_ctx* ctx, const xemo_array* x, const float* labels, float* nerr);
+/* mcnExtraLayers global average pooling (SE squeeze): H x W x C x N -> 1 x 1 x C x N */
+int xemo_vl_nnglobalpool(xemo_ctx* ctx, const xemo_array* x, const xemo_array* dzdy, xemo_array* y_or_dx);
+/* mcnExtraLayers Axpy (SE excite + shortcut): out = a (.) x + y, a is 1 x 1 x C x N */
+int xemo_vl_nnaxpy(xemo_ctx* ctx, const xemo_array* a, const xemo_array* x, const xemo_array* y, xemo_array* out);
+
+/* ------------------------------------------------------------------ (B) device-native building blocks
+ * Activations: NHWC fp16, channel count a multiple of 16 for convolution operands, 8 otherwise.
+ * Filters: [Kout][R][S][Cin] fp16 ("KRSC").  All pointers are device pointers. */
+
+/* layout conversion at graph edges */
+int xemo_op_hwcn_to_nhwc(xemo_ctx* ctx, const float* src, int H, int W, int C, int N, void* dst, int Cp, int dst_f32);
+int xemo_op_nhwc_to_hwcn(xemo_ctx* ctx, const void* src, int src_f32, int H, int W, int C, int N, int Cp, float* dst);
+int xemo_op_filters_to_krsc(xemo_ctx* ctx, const float* f, int FH, int FW, int FC, int K, void* dst16, int Kp, int Cp,
+                            int flip_transpose);
+/* teacher stem staging: faces H x W x C x N (fp32 HWCN) -> [N][H][OW][32] fp16 row-im2col (7x7/2 -> 7x1, 32 ch) */
+int xemo_op_face_rows_im2col(xemo_ctx* ctx, const float* faces, int H, int W, int C, int N, int S, int stride_w,
+                             int pad_l, int OW, void* dst16);
+/* student stem staging: spectrograms H x W x 1 x N -> [N][HP][OW][16] fp16 space-to-depth (7x7/2 -> 4x1, 16 ch) */
+int xemo_op_spec_s2d(xemo_ctx* ctx, const float* spec, int H, int W, int N, int pad_t, int pad_l, int HP, int OW,
+                     void* dst16);
+
+/* implicit-GEMM convolution on tcgen05: out = act(scale[k]*conv(x,w) + shift[k] + residual).
+ * out16 (fp16) and/or out32 (fp32) receive [N*OH*OW][ldc]; scale/shift/residual may be NULL. */
+int xemo_op_conv_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int Cin, const void* w16, int Kout, int R,
+                     int S, int sh, int sw, int pt, int pb, int pl, int pr, const float* scale, const float* shift,
+                     const void* residual16, int relu, void* out16, float* out32, int ldc);
+/* data gradient: dx[N][H][W][Cin] from dy[N][OH][OW][Kout] and the packed filters produced by
+ * xemo_op_pack_dgrad_filters (one flipped/transposed sub-filter per output parity class). */
+size_t xemo_dgrad_pack_elems(int Cin, int Kout, int R, int S, int sh, int sw);
+int xemo_op_pack_dgrad_filters(xemo_ctx* ctx, const void* w16_krsc, int Kout, int R, int S, int Cin, int sh, int sw,
+                               int pt, int pl, void* packed16);
+int xemo_op_conv_dgrad(xemo_ctx* ctx, const void* dy16, int N, int H, int W, int Cin, const void* packed16, int Kout,
+                       int R, int S, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16);
+/* filter gradient, accumulated (+=) into dF[Kout][R][S][Cin] fp32, scaled by `scale` */
+int xemo_op_conv_wgrad(xemo_ctx* ctx, const void* x16, int N, int H, int W, int Cin, const void* dy16, int ldy,
+                       int Kout, int R, int S, int sh, int sw, int pt, int pb, int pl, int pr, float* dF, float scale);
+/* bias gradient: out[c] = scale * sum_p dy[p][c] */
+int xemo_op_colsum(xemo_ctx* ctx, const void* dy16, size_t P, int ld, int C, float scale, float* out);
+
+/* pooling (fp16 NHWC).  maxpool_fwd optionally applies z = relu(a[c]*x + b[c]) on the fly (BN+ReLU folded into
+ * the pooling read) and emits the uint8 window-local arg-max dw*PH + dh that maxpool_bwd consumes. */
+int xemo_op_maxpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
+                        int pt, int pb, int pl, int pr, const float* a, const float* b, void* y16, uint8_t* argmax);
+int xemo_op_maxpool_bwd(xemo_ctx* ctx, const void* dy16, const uint8_t* argmax, int N, int H, int W, int C, int PH,
+                        int PW, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16);
+int xemo_op_avgpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
+                        int pt, int pb, int pl, int pr, void* y16);
+int xemo_op_avgpool_bwd(xemo_ctx* ctx, const void* dy16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
+                        int pt, int pb, int pl, int pr, void* dx16);
+
+/* batch normalisation over P = N*H*W rows of C channels.
+ * bn_train: batch statistics -> moments[2C] = [mu | sigma], a = g/sigma, b = beta - a*mu (ws: 2C doubles).
+ * bn_test : a, b from given moments.  affine_act: y = a*x + b (+ReLU).
+ * bn_bwd  : dz = dy*[a*x+b > 0] (relu_mask); dg = sum dz*xhat, db = sum dz (scaled by inv_grad_scale, fp32);
+ *           dx = a*(dz - db/P - xhat*dg/P)  (train)  or  a*dz  (test_mode). */
+int xemo_op_bn_train(xemo_ctx* ctx, const void* x16, size_t P, int C, const float* g, const float* beta, float eps,
+                     double* ws, float* moments, float* a, float* b);
+int xemo_op_bn_test(xemo_ctx* ctx, const float* moments, int C, const float* g, const float* beta, float* a, float* b);
+int xemo_op_affine_act(xemo_ctx* ctx, const void* x16, size_t P, int C, const float* a, const float* b, int relu,
+                       void* y16);
+int xemo_op_bn_bwd(xemo_ctx* ctx, const void* x16, const void* dy16, size_t P, int C, const float* moments,
+                   const float* a, const float* b, int relu_mask, int test_mode, double* ws, void* dx16, float* dg,
+                   float* db, float inv_grad_scale);
+int xemo_op_relu_bwd(xemo_ctx* ctx, const void* y16, const void* dy16, size_t n, void* dx16);
+int xemo_op_add_act(xemo_ctx* ctx, const void* a16, const void* b16, size_t n, int relu, void* y16);
+
+/* squeeze-and-excitation: s = mean_hw(u) ; gate = sigmoid(W2 relu(W1 s + b1) + b2) ; y = relu(gate*u + shortcut) */
+int xemo_op_se_squeeze(xemo_ctx* ctx, const void* u16, int N, int HW, int C, float* s);
+int xemo_op_se_gate(xemo_ctx* ctx, const float* s, int N, int C, int Cr, const float* w1, const float* b1,
+                    const float* w2, const float* b2, float* gate);
+int xemo_op_se_excite(xemo_ctx* ctx, const void* u16, const float* gate, const void* shortcut16, int N, int HW, int C,
+                      int relu, void* y16);
+
+/* teacher -> student coupling (emoVoxCeleb/getBatchEmoVoxCeleb.m:133-159,179-188): per clip n aggregate frame
+ * logits rows [start[n], end[n]) with max (use_mean = 0) or mean into target[N][num_pred] */
+int xemo_op_logit_aggregate(xemo_ctx* ctx, const float* frame_logits, int ldl, const int* start, const int* end, int N,
+                            int num_pred, int use_mean, float* target);
+/* fused T-softmax CE + backward + metric layers.  x16: [N][ldx] fp16 student logits; t: [N][ldt] fp32 teacher
+ * logits (or distributions); dx16 (optional) = grad_scale*dzdy*w_n*(q-p)/T; scalars[0] += loss, scalars[1] +=
+ * classerror; class_stats[0..C) += correct per class, [C..2C) += count per class; max_label[N] (1-based). */
+int xemo_op_softmaxce(xemo_ctx* ctx, const void* x16, int ldx, const float* t, int ldt, const float* w, int N, int C,
+                      float T, int logit_targets, float dzdy, float grad_scale, void* dx16, float* scalars,
+                      float* class_stats, int* max_label);
+/* cnn_train_dag update: m <- mu*m - (wd*w + g*inv_grad_scale/B); w <- w + lr*m; optional fp16 copy refresh.
+ * hyper (device, fp32[4]) = {lr, momentum, weight_decay, 1/B}; lr_mult / wd_mult are per-parameter multipliers */
+int xemo_op_sgd_momentum(xemo_ctx* ctx, float* w, float* m, const float* g, size_t n, const float* hyper, float lr_mult,
+                         float wd_mult, float inv_grad_scale, void* w16);
+/* dagnn.BatchNorm moments parameter: moments <- (1-rate)*moments + rate*batch_moments */
+int xemo_op_moments_average(xemo_ctx* ctx, float* moments, const float* batch_moments, int n, float rate);
+int xemo_op_cast_f32_f16(xemo_ctx* ctx, const float* src, size_t n, void* dst16);
+int xemo_op_cast_f16_f32(xemo_ctx* ctx, const void* src16, size_t n, float scale, float* dst);
+/* dst[o*outer_stride + inner_off + i] = value for o < outer, i < inner (masks structurally-zero filter slots) */
+int xemo_op_fill_strided_f32(xemo_ctx* ctx, float* dst, int outer, size_t outer_stride, size_t inner_off, int inner,
+                             float value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XEMO_H_ */

@@ -4,6 +4,9 @@
 // the operator that dagnn.Conv.forward calls from dag.eval at
 //   /root/reference/emoVoxCeleb/fetch_emovoxceleb_imdb.m:129, external/compute_visual_feats.m:90,
 //   external/compute_audio_feats.m:126 and inside cnn_train_dag (emoVoxCeleb/run_distillation.m:170).
+// The same kernel computes the data gradient (vl_nnconv backward, DX) of stride-1 convolutions by
+// running on dY with flipped/transposed filters, and of strided ones as a sum over output parities
+// written through the strided-output mode.
 //
 // GEMM view:  D[M = N*OH*OW, Kout] = sum_{r,s,c} X[n, oh*sy+r-pt, ow*sx+s-pl, c] * F[kout, r, s, c]
 //   A (activations) : NHWC fp16, fetched by TMA in im2col mode -- 128 consecutive output pixels x BK
@@ -15,7 +18,9 @@
 //   warp 0   : TMA producer (one elected lane)
 //   warp 1   : tcgen05.mma issuer (one elected lane)
 //   warps 2-5: epilogue -- tcgen05.ld, per-channel scale/shift (folded test-mode BN or bias), optional
-//              residual add, optional ReLU, fp16 (and/or fp32) store.  Warp 2 also owns TMEM alloc/free.
+//              residual add, optional ReLU; fp16 tile staged in swizzled smem and written with TMA
+//              stores (residual tiles prefetched with TMA loads), or stored directly (fp32 / strided
+//              outputs).  Warp 2 also owns TMEM alloc/free.
 #pragma once
 #include "xemo_ptx.cuh"
 
@@ -24,10 +29,11 @@ namespace xemo {
 constexpr int kConvBlockM = 128;
 constexpr int kConvThreads = 192;
 constexpr int kConvTmemCols = 512;
+constexpr int kEpiStageBytes = kConvBlockM * 64 * 2;  // one [128 x 64] fp16 staging tile
 
 struct ConvFpropParams {
   int M;       // N*OH*OW output pixels
-  int Kout;    // output channels (ldc of the output matrix)
+  int Kout;    // output channels
   int Cin, R, S;
   int OH, OW;
   int stride_h, stride_w, pad_t, pad_l;
@@ -39,10 +45,18 @@ struct ConvFpropParams {
   // epilogue: y = acc * scale[k] + shift[k] (+ residual) ; relu ; store
   const float* scale;       // [Kout] or nullptr (=1)
   const float* shift;       // [Kout] or nullptr (=0)
-  const __half* residual;   // [M, Kout] or nullptr
+  const __half* residual;   // [M, ldc] or nullptr
   int relu;
-  __half* out;              // [M, Kout] fp16 or nullptr
-  float* out_f32;           // [M, Kout] fp32 or nullptr
+  __half* out;              // fp16 output or nullptr
+  float* out_f32;           // [M, ldc] fp32 or nullptr
+  int ldc;                  // row pitch (elements) of out / out_f32 / residual in dense mode
+  // strided-output mode (dgrad of strided convs): row address = n*out_sn + oh*out_sh + ow*out_sw
+  int strided_out;
+  long long out_sn, out_sh, out_sw;
+  // TMA epilogue
+  int use_tma_store;        // fp16 `out` written through tmOut
+  int use_tma_residual;     // residual read through tmRes
+  int epi_cw;               // staging chunk width in columns: 64 / 32 / 16
 };
 
 template <int BK>
@@ -60,9 +74,19 @@ __host__ __device__ inline int conv_stage_bytes(int bk, int block_n) {
   return a_bytes + b_bytes;
 }
 
+// byte offset of 16-byte chunk `chunk` of row `row` inside a TMA-swizzled staging tile with row pitch
+// `pitch` bytes (128 -> SW128, 64 -> SW64, 32 -> SW32): address bits [4,7) ^= bits [7,10) & mask.
+__device__ __forceinline__ uint32_t swz_off(int row, int chunk, int pitch, uint32_t mask) {
+  uint32_t off = uint32_t(row) * uint32_t(pitch) + uint32_t(chunk) * 16u;
+  return off ^ (((off >> 7) & mask) << 4);
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 template <int BK>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                   const ConvFpropParams p) {
   extern __shared__ uint8_t smem_raw[];
   // swizzled TMA/UMMA tiles want 1024-byte alignment
@@ -73,12 +97,16 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int stage_bytes = conv_stage_bytes(BK, p.block_n);
   const int num_stages = p.num_stages;
 
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(num_stages) * stage_bytes);
+  uint8_t* epi_store_buf = smem + size_t(num_stages) * stage_bytes;                  // 2 x 16 KB (if used)
+  uint8_t* epi_res_buf = epi_store_buf + (p.use_tma_store ? 2 * kEpiStageBytes : 0); // 2 x 16 KB (if used)
+  uint8_t* after = epi_res_buf + (p.use_tma_residual ? 2 * kEpiStageBytes : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + num_stages;
   uint64_t* tmem_full_bar = bars + 2 * num_stages;
   uint64_t* tmem_empty_bar = bars + 2 * num_stages + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * num_stages + 4);
+  uint64_t* res_bar = bars + 2 * num_stages + 4;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * num_stages + 6);
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
   const int lane = threadIdx.x & 31;
@@ -86,6 +114,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
+    if (p.use_tma_store) prefetch_tensormap(&tmOut);
+    if (p.use_tma_residual) prefetch_tensormap(&tmRes);
     for (int s = 0; s < num_stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -93,6 +123,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&res_bar[a], 1);
     }
     fence_barrier_init();
   }
@@ -180,23 +211,75 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------ epilogue warps 2..5
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
+    const bool leader = (threadIdx.x == 64);  // warp 2, lane 0
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;  // staging-chunk counter across tiles (buffer = ctr & 1)
+    const int cw = p.epi_cw;
+    const int chunks_per_tile = p.block_n / cw;
+    const int pitch = cw * 2;
+    const uint32_t swz_mask = (cw == 64) ? 7u : (cw == 32) ? 3u : 1u;
+    const uint32_t chunk_bytes = uint32_t(kConvBlockM) * uint32_t(pitch);
+    const int ohw = p.OH * p.OW;
+
+    // prefetch the residual chunk for the first tile of this CTA
+    if (p.use_tma_residual && leader && int(blockIdx.x) < num_tiles) {
+      const int m_tile = blockIdx.x / p.num_n_tiles;
+      const int n_tile = blockIdx.x - m_tile * p.num_n_tiles;
+      mbar_arrive_expect_tx(&res_bar[0], chunk_bytes);
+      tma_load_2d(&tmRes, &res_bar[0], epi_res_buf, n_tile * p.block_n, m_tile * kConvBlockM);
+    }
+
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
-      const int row = m_tile * kConvBlockM + row_in_tile;
+      const int m0 = m_tile * kConvBlockM;
+      const int row = m0 + row_in_tile;
       const int n0 = n_tile * p.block_n;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc) * 256u;
       const bool row_ok = row < p.M;
-      const size_t row_off = size_t(row) * p.Kout + n0;
-      for (int j = 0; j < p.block_n; j += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + uint32_t(j), v);
-        tmem_ld_wait();
-        if (row_ok) {
+      size_t row_off;
+      if (p.strided_out) {
+        const int n_img = row / ohw;
+        const int rem = row - n_img * ohw;
+        const int oh = rem / p.OW;
+        const int ow = rem - oh * p.OW;
+        row_off = size_t(n_img) * p.out_sn + size_t(oh) * p.out_sh + size_t(ow) * p.out_sw + n0;
+      } else {
+        row_off = size_t(row) * p.ldc + n0;
+      }
+
+      for (int q = 0; q < chunks_per_tile; ++q, ++chunk_ctr) {
+        const uint32_t buf = chunk_ctr & 1u;
+        uint8_t* sbuf = epi_store_buf + buf * kEpiStageBytes;
+        uint8_t* rbuf = epi_res_buf + buf * kEpiStageBytes;
+        if (p.use_tma_store) {
+          // the TMA store that last read this staging buffer (two chunks ago) must have drained it
+          if (leader) tma_store_wait_read<1>();
+        }
+        if (p.use_tma_residual && leader) {
+          // prefetch the next residual chunk (next chunk of this tile, or first chunk of the next tile)
+          int nq = q + 1, ntile = tile;
+          if (nq == chunks_per_tile) { nq = 0; ntile = tile + gridDim.x; }
+          if (ntile < num_tiles) {
+            const int nm = ntile / p.num_n_tiles;
+            const int nn = ntile - nm * p.num_n_tiles;
+            const uint32_t nbuf = (chunk_ctr + 1) & 1u;
+            mbar_arrive_expect_tx(&res_bar[nbuf], chunk_bytes);
+            tma_load_2d(&tmRes, &res_bar[nbuf], epi_res_buf + nbuf * kEpiStageBytes, nn * p.block_n + nq * cw,
+                        nm * kConvBlockM);
+          }
+        }
+        if (p.use_tma_store) epi_bar_sync();  // staging buffer `buf` is free for everyone
+        if (p.use_tma_residual) mbar_wait(&res_bar[buf], (chunk_ctr >> 1) & 1u);
+
+        for (int jj = 0; jj < cw; jj += 16) {
+          const int j = q * cw + jj;  // column inside the tile
+          uint32_t v[16];
+          tmem_ld16(taddr + uint32_t(j), v);
+          tmem_ld_wait();
           float x[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
@@ -215,10 +298,16 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
           if (p.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + j);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const uint4 rv = __ldg(rp + h);
+              uint4 rv;
+              if (p.use_tma_residual) {
+                rv = *reinterpret_cast<const uint4*>(rbuf + swz_off(row_in_tile, jj / 8 + h, pitch, swz_mask));
+              } else if (row_ok) {
+                rv = __ldg(reinterpret_cast<const uint4*>(p.residual + row_off + j) + h);
+              } else {
+                rv = make_uint4(0, 0, 0, 0);
+              }
               const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -237,14 +326,27 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             __half2* o2 = reinterpret_cast<__half2*>(o);
 #pragma unroll
             for (int i = 0; i < 8; ++i) o2[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
-            uint4* op = reinterpret_cast<uint4*>(p.out + row_off + j);
-            op[0] = o[0];
-            op[1] = o[1];
+            if (p.use_tma_store) {
+              *reinterpret_cast<uint4*>(sbuf + swz_off(row_in_tile, jj / 8, pitch, swz_mask)) = o[0];
+              *reinterpret_cast<uint4*>(sbuf + swz_off(row_in_tile, jj / 8 + 1, pitch, swz_mask)) = o[1];
+            } else if (row_ok) {
+              uint4* op = reinterpret_cast<uint4*>(p.out + row_off + j);
+              op[0] = o[0];
+              op[1] = o[1];
+            }
           }
-          if (p.out_f32) {
+          if (p.out_f32 && row_ok) {
             float4* fp = reinterpret_cast<float4*>(p.out_f32 + row_off + j);
 #pragma unroll
             for (int i = 0; i < 4; ++i) fp[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+          }
+        }
+        if (p.use_tma_store) {
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          epi_bar_sync();
+          if (leader) {
+            tma_store_2d(&tmOut, sbuf, n0 + q * cw, m0);  // rows beyond M are clipped by the tensor map
+            tma_store_commit();
           }
         }
       }
@@ -254,6 +356,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (p.use_tma_store && leader) tma_store_wait<0>();
   }
 
   tc_fence_before();

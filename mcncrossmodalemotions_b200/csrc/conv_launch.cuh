@@ -2,6 +2,9 @@
 // tcgen05 implicit-GEMM convolution kernels.
 #pragma once
 #include "conv_fprop.cuh"
+#include "conv_wgrad.cuh"
+#include <string.h>
+
 #include "tma_host.h"
 
 namespace xemo {
@@ -11,9 +14,12 @@ struct ConvGeom {
   int Kout, R, S;     // filters [Kout][R][S][Cin]
   int sh, sw;         // stride
   int pt, pb, pl, pr; // MatConvNet pad = [top bottom left right]
+  // explicit output size (0 = derive).  Used by the parity-decomposed data gradient of strided
+  // convolutions, whose sub-problems produce ceil((H - ph) / sh) rows regardless of the padding.
+  int oh_override = 0, ow_override = 0;
   // vl_nnconv output size: floor((H + pt + pb - R) / sh) + 1
-  int OH() const { return (H + pt + pb - R) / sh + 1; }
-  int OW() const { return (W + pl + pr - S) / sw + 1; }
+  int OH() const { return oh_override ? oh_override : (H + pt + pb - R) / sh + 1; }
+  int OW() const { return ow_override ? ow_override : (W + pl + pr - S) / sw + 1; }
 };
 
 struct ConvEpilogue {
@@ -23,10 +29,15 @@ struct ConvEpilogue {
   int relu = 0;
   __half* out = nullptr;
   float* out_f32 = nullptr;
+  int ldc = 0;                 // row pitch of out/out_f32/residual (0 -> Kout)
+  // strided-output mode: row address = n*out_sn + oh*out_sh + ow*out_sw (elements)
+  int strided_out = 0;
+  long long out_sn = 0, out_sh = 0, out_sw = 0;
+  int allow_tma_epilogue = 1;  // 0 forces the direct-store epilogue
 };
 
 struct ConvPlan {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmOut, tmRes;
   ConvFpropParams p;
   int bk = 0;
   int grid = 0;
@@ -78,14 +89,20 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   p.num_m_tiles = (p.M + kConvBlockM - 1) / kConvBlockM;
   p.num_n_tiles = g.Kout / p.block_n;
   const int stage_bytes = conv_stage_bytes(bk, p.block_n);
-  int stages = (kSmemBudget - 1024 - 256) / stage_bytes;
+  p.scale = e.scale; p.shift = e.shift; p.residual = e.residual; p.relu = e.relu;
+  p.out = e.out; p.out_f32 = e.out_f32;
+  p.ldc = e.ldc ? e.ldc : g.Kout;
+  p.strided_out = e.strided_out; p.out_sn = e.out_sn; p.out_sh = e.out_sh; p.out_sw = e.out_sw;
+  p.use_tma_store = (e.allow_tma_epilogue && e.out && !e.strided_out && (p.ldc % 8 == 0)) ? 1 : 0;
+  p.use_tma_residual = (p.use_tma_store && e.residual) ? 1 : 0;
+  p.epi_cw = (p.block_n % 64 == 0) ? 64 : (p.block_n % 32 == 0) ? 32 : 16;
+  const int epi_bytes = (p.use_tma_store ? 2 * kEpiStageBytes : 0) + (p.use_tma_residual ? 2 * kEpiStageBytes : 0);
+  int stages = (kSmemBudget - 1024 - 256 - epi_bytes) / stage_bytes;
   if (stages > 12) stages = 12;
   if (stages < 2) return false;
   p.num_stages = stages;
-  p.scale = e.scale; p.shift = e.shift; p.residual = e.residual; p.relu = e.relu;
-  p.out = e.out; p.out_f32 = e.out_f32;
   plan->bk = bk;
-  plan->smem = stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16;
+  plan->smem = stages * stage_bytes + epi_bytes + 1024 + (2 * stages + 6) * 8 + 16;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   plan->grid = tiles < num_sms ? tiles : num_sms;
   plan->flops = 2.0 * double(p.M) * g.Kout * g.R * g.S * g.Cin;
@@ -101,6 +118,16 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   if (!make_tmap_2d_f16(&plan->tmB, w, uint64_t(g.Kout), uint64_t(g.R) * g.S * g.Cin, uint64_t(g.R) * g.S * g.Cin,
                         uint32_t(bk), uint32_t(p.block_n), swz))
     return false;
+  memset(&plan->tmOut, 0, sizeof(CUtensorMap));
+  memset(&plan->tmRes, 0, sizeof(CUtensorMap));
+  if (p.use_tma_store &&
+      !make_tmap_2d_f16(&plan->tmOut, e.out, uint64_t(p.M), uint64_t(g.Kout), uint64_t(p.ldc), uint32_t(p.epi_cw),
+                        uint32_t(kConvBlockM), swizzle_for_bytes(p.epi_cw * 2)))
+    return false;
+  if (p.use_tma_residual &&
+      !make_tmap_2d_f16(&plan->tmRes, e.residual, uint64_t(p.M), uint64_t(g.Kout), uint64_t(p.ldc),
+                        uint32_t(p.epi_cw), uint32_t(kConvBlockM), swizzle_for_bytes(p.epi_cw * 2)))
+    return false;
   return true;
 }
 
@@ -111,25 +138,112 @@ inline cudaError_t conv_fprop_run(const ConvPlan& plan, cudaStream_t stream) {
       static bool attr = false;
       if (!attr) { err = cudaFuncSetAttribute(conv_fprop_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget); attr = true; }
       if (err != cudaSuccess) return err;
-      conv_fprop_kernel<64><<<plan.grid, kConvThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.p);
+      conv_fprop_kernel<64><<<plan.grid, kConvThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
       break;
     }
     case 32: {
       static bool attr = false;
       if (!attr) { err = cudaFuncSetAttribute(conv_fprop_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget); attr = true; }
       if (err != cudaSuccess) return err;
-      conv_fprop_kernel<32><<<plan.grid, kConvThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.p);
+      conv_fprop_kernel<32><<<plan.grid, kConvThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
       break;
     }
     case 16: {
       static bool attr = false;
       if (!attr) { err = cudaFuncSetAttribute(conv_fprop_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget); attr = true; }
       if (err != cudaSuccess) return err;
-      conv_fprop_kernel<16><<<plan.grid, kConvThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.p);
+      conv_fprop_kernel<16><<<plan.grid, kConvThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
       break;
     }
     default: return cudaErrorInvalidValue;
   }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// filter gradient
+struct WgradPlan {
+  CUtensorMap tmY, tmX;
+  ConvWgradParams p;
+  int grid = 0;
+  int smem = 0;
+  double flops = 0;
+};
+
+inline int pick_chunk(int n) { return (n % 64 == 0) ? 64 : (n % 32 == 0) ? 32 : 16; }
+
+// x: NHWC fp16 [N][H][W][Cin] (Cin % 16 == 0); dy: [P][ldy] fp16 (ldy % 16 == 0, Kout <= ldy);
+// dF: [Kout][R][S][Cin] fp32, accumulated into.
+inline bool conv_wgrad_plan(WgradPlan* plan, const ConvGeom& g, const __half* x, const __half* dy, int ldy, float* dF,
+                            float scale, int num_sms) {
+  if (g.Cin % 16 || ldy % 16 || g.Kout > ldy) {
+    fprintf(stderr, "[xemo] wgrad: Cin=%d / ldy=%d must be multiples of 16 and Kout=%d <= ldy\n", g.Cin, ldy, g.Kout);
+    return false;
+  }
+  const int OH = g.OH(), OW = g.OW();
+  if (OH <= 0 || OW <= 0) return false;
+  ConvWgradParams& p = plan->p;
+  p.P = g.N * OH * OW;
+  p.Kout = g.Kout;
+  p.ldy = ldy;
+  p.Cin = g.Cin; p.R = g.R; p.S = g.S;
+  p.OH = OH; p.OW = OW;
+  p.stride_h = g.sh; p.stride_w = g.sw; p.pad_t = g.pt; p.pad_l = g.pl;
+  p.chunk_a = ldy >= 64 ? 64 : pick_chunk(ldy);
+  p.chunk_b = pick_chunk(g.Cin);
+  // channels per sub-tile: the largest divisor of Cin that is a multiple of chunk_b and <= 256
+  int block_c = p.chunk_b;
+  for (int c = p.chunk_b; c <= 256 && c <= g.Cin; c += p.chunk_b)
+    if (g.Cin % c == 0) block_c = c;
+  p.block_c = block_c;
+  p.c_tiles = g.Cin / block_c;
+  const int total_sub = g.R * g.S * p.c_tiles;
+  int T = 512 / block_c;
+  if (T > total_sub) T = total_sub;
+  // keep the stage small enough for >= 3 pipeline stages
+  while (T > 1 && wgrad_stage_bytes(T, block_c) * 3 > kSmemBudget - 2048) --T;
+  p.T = T;
+  p.groups = (total_sub + T - 1) / T;
+  p.m_tiles = (g.Kout + kWgBlockM - 1) / kWgBlockM;
+  const int pix_blocks = (p.P + kWgPix - 1) / kWgPix;
+  const int base_items = p.m_tiles * p.groups;
+  // split the pixel reduction so that there are ~2 items per SM, each at least 8 pixel blocks long
+  int splits = (2 * num_sms + base_items - 1) / base_items;
+  const int max_splits = (pix_blocks + 7) / 8;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.pix_blocks_per_split = (pix_blocks + splits - 1) / splits;
+  p.splits = (pix_blocks + p.pix_blocks_per_split - 1) / p.pix_blocks_per_split;
+  const int stage_bytes = wgrad_stage_bytes(T, block_c);
+  int stages = (kSmemBudget - 2048) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return false;
+  p.num_stages = stages;
+  p.dF = dF;
+  p.scale = scale;
+  plan->smem = stages * stage_bytes + 1024 + (2 * stages + 2) * 8 + 16;
+  const int items = p.m_tiles * p.groups * p.splits;
+  plan->grid = items < num_sms ? items : num_sms;
+  plan->flops = 2.0 * double(p.P) * g.Kout * g.R * g.S * g.Cin;
+  const int upper_w = (OW - 1) * g.sw - g.pl - (g.W - 1);
+  const int upper_h = (OH - 1) * g.sh - g.pt - (g.H - 1);
+  if (!make_tmap_im2col_nhwc_f16(&plan->tmX, x, g.N, g.H, g.W, g.Cin, -g.pl, -g.pt, upper_w, upper_h, g.sw, g.sh,
+                                 uint32_t(p.chunk_b), uint32_t(kWgPix), swizzle_for_bytes(p.chunk_b * 2)))
+    return false;
+  if (!make_tmap_2d_f16(&plan->tmY, dy, uint64_t(p.P), uint64_t(ldy), uint64_t(ldy), uint32_t(p.chunk_a),
+                        uint32_t(kWgPix), swizzle_for_bytes(p.chunk_a * 2)))
+    return false;
+  return true;
+}
+
+inline cudaError_t conv_wgrad_run(const WgradPlan& plan, cudaStream_t stream) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t err = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (err != cudaSuccess) return err;
+    attr = true;
+  }
+  conv_wgrad_kernel<<<plan.grid, kWgThreads, plan.smem, stream>>>(plan.tmY, plan.tmX, plan.p);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,224 @@
+// conv_wgrad.cuh -- filter gradient of vl_nnconv (DF) as an implicit GEMM on tcgen05 (sm_100a).
+//
+//   dF[kout, r, s, c] = sum_{pixels p=(n,oh,ow)} dY[p, kout] * X[n, oh*sy+r-pt, ow*sx+s-pl, c]
+//
+// The reduction runs over output pixels, so both operands are "MN-major" for the tensor core: a tile
+// of dY is [32 pixels][128 kout] with kout contiguous, a tile of im2col(X) is [32 pixels][block_c
+// channels] with channels contiguous (the same TMA im2col loads as the forward pass, one per filter
+// tap).  One work item owns a 128-kout slice, up to T (tap, channel-tile) sub-tiles whose fp32
+// accumulators fill the 512 TMEM columns (the dY tile is fetched once per stage and reused by all T),
+// and one split of the pixel range; partial sums are combined with fp32 red.global.add.
+//
+// Reference call site: dagnn.Conv.backward under cnn_train_dag, emoVoxCeleb/run_distillation.m:170.
+#pragma once
+#include "xemo_ptx.cuh"
+
+namespace xemo {
+
+constexpr int kWgPix = 32;        // pixels (GEMM-K) per pipeline stage
+constexpr int kWgBlockM = 128;    // kout per item
+constexpr int kWgThreads = 192;
+
+struct ConvWgradParams {
+  int P;        // N*OH*OW pixels
+  int Kout;     // logical output channels (rows of dF)
+  int ldy;      // row pitch of dY (elements)
+  int Cin, R, S;
+  int OH, OW;
+  int stride_h, stride_w, pad_t, pad_l;
+  int chunk_a;  // contiguous kout elements per smem chunk: 64 / 32 / 16
+  int chunk_b;  // contiguous channel elements per smem chunk
+  int block_c;  // channels per sub-tile (multiple of 16, <= 256)
+  int c_tiles;  // ceil(Cin / block_c)
+  int T;        // sub-tiles per item, T * block_c <= 512
+  int groups;   // ceil(R*S*c_tiles / T)
+  int m_tiles;  // ceil(Kout / 128)
+  int splits;
+  int pix_blocks_per_split;
+  int num_stages;
+  float* dF;    // [Kout][R][S][Cin] fp32, accumulated into (caller zeroes)
+  float scale;  // applied to the accumulators before the atomic add (1/grad_scale)
+};
+
+__host__ __device__ inline int wgrad_stage_bytes(int T, int block_c) {
+  return kWgPix * kWgBlockM * 2 + T * kWgPix * block_c * 2;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
+                  const ConvWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_bytes = kWgPix * kWgBlockM * 2;
+  const int b_sub_bytes = kWgPix * p.block_c * 2;
+  const int stage_bytes = wgrad_stage_bytes(p.T, p.block_c);
+  const int num_stages = p.num_stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(num_stages) * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + num_stages;
+  uint64_t* tmem_full_bar = bars + 2 * num_stages;
+  uint64_t* tmem_empty_bar = bars + 2 * num_stages + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * num_stages + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmY);
+    prefetch_tensormap(&tmX);
+    for (int s = 0; s < num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(tmem_empty_bar, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_items = p.m_tiles * p.groups * p.splits;
+  const int total_sub = p.R * p.S * p.c_tiles;
+  const int pix_blocks = (p.P + kWgPix - 1) / kWgPix;
+  const int ohw = p.OH * p.OW;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int a_chunks = kWgBlockM / p.chunk_a;
+      const int a_chunk_bytes = kWgPix * p.chunk_a * 2;
+      const int b_chunks = p.block_c / p.chunk_b;
+      const int b_chunk_bytes = kWgPix * p.chunk_b * 2;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int split = item % p.splits;
+        const int grp = (item / p.splits) % p.groups;
+        const int m_tile = item / (p.splits * p.groups);
+        const int sub0 = grp * p.T;
+        const int nsub = min(p.T, total_sub - sub0);
+        const int pb0 = split * p.pix_blocks_per_split;
+        const int pb1 = min(pb0 + p.pix_blocks_per_split, pix_blocks);
+        for (int pb = pb0; pb < pb1; ++pb) {
+          const int p0 = pb * kWgPix;
+          const int n_img = p0 / ohw;
+          const int rem = p0 - n_img * ohw;
+          const int oh = rem / p.OW;
+          const int ow = rem - oh * p.OW;
+          const int w_base = ow * p.stride_w - p.pad_l;
+          const int h_base = oh * p.stride_h - p.pad_t;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + size_t(stage) * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], uint32_t(a_bytes + nsub * b_sub_bytes));
+          for (int ca = 0; ca < a_chunks; ++ca)
+            tma_load_2d(&tmY, &full_bar[stage], sa + ca * a_chunk_bytes, m_tile * kWgBlockM + ca * p.chunk_a, p0);
+          for (int t = 0; t < nsub; ++t) {
+            const int sub = sub0 + t;
+            const int tap = sub / p.c_tiles;
+            const int c0 = (sub - tap * p.c_tiles) * p.block_c;
+            const int r = tap / p.S, s = tap - r * p.S;
+            for (int cb = 0; cb < b_chunks; ++cb)
+              tma_load_im2col_4d(&tmX, &full_bar[stage], sb + t * b_sub_bytes + cb * b_chunk_bytes,
+                                 c0 + cb * p.chunk_b, w_base, h_base, n_img, uint16_t(s), uint16_t(r));
+          }
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_f16(kWgBlockM, p.block_c, 1, 1);  // A and B MN-major
+      const uint32_t swz_a = (p.chunk_a == 64) ? 2u : (p.chunk_a == 32) ? 4u : 6u;
+      const uint32_t swz_b = (p.chunk_b == 64) ? 2u : (p.chunk_b == 32) ? 4u : 6u;
+      const uint32_t sbo_a = 8 * p.chunk_a * 2, lbo_a = kWgPix * p.chunk_a * 2;
+      const uint32_t sbo_b = 8 * p.chunk_b * 2, lbo_b = kWgPix * p.chunk_b * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t item_phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int split = item % p.splits;
+        const int grp = (item / p.splits) % p.groups;
+        const int sub0 = grp * p.T;
+        const int nsub = min(p.T, total_sub - sub0);
+        const int pb0 = split * p.pix_blocks_per_split;
+        const int pb1 = min(pb0 + p.pix_blocks_per_split, pix_blocks);
+        mbar_wait(tmem_empty_bar, item_phase ^ 1);
+        tc_fence_after();
+        for (int pb = pb0; pb < pb1; ++pb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + size_t(stage) * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < kWgPix / 16; ++k) {
+            // 16 pixels (GEMM-K) = two 8-row groups: advance by 2*SBO
+            const uint64_t a_desc = make_smem_desc(sa + k * 2 * sbo_a, lbo_a, sbo_a, swz_a);
+            for (int t = 0; t < nsub; ++t) {
+              const uint64_t b_desc = make_smem_desc(sb + t * b_sub_bytes + k * 2 * sbo_b, lbo_b, sbo_b, swz_b);
+              umma_f16_ss(tmem_base + uint32_t(t * p.block_c), a_desc, b_desc, idesc, (pb > pb0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tmem_full_bar);
+        item_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps 2..5
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    uint32_t item_phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int grp = (item / p.splits) % p.groups;
+      const int m_tile = item / (p.splits * p.groups);
+      const int split = item % p.splits;
+      const int sub0 = grp * p.T;
+      const int nsub = min(p.T, total_sub - sub0);
+      const int pb0 = split * p.pix_blocks_per_split;
+      const bool has_work = pb0 < pix_blocks;
+      mbar_wait(tmem_full_bar, item_phase);
+      tc_fence_after();
+      const int kout = m_tile * kWgBlockM + row_in_tile;
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16);
+      for (int t = 0; t < nsub; ++t) {
+        const int sub = sub0 + t;
+        const int tap = sub / p.c_tiles;
+        const int c0 = (sub - tap * p.c_tiles) * p.block_c;
+        float* dst = p.dF + (size_t(kout) * p.R * p.S + tap) * p.Cin + c0;
+        for (int j = 0; j < p.block_c; j += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + uint32_t(t * p.block_c + j), v);
+          tmem_ld_wait();
+          if (has_work && kout < p.Kout) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + j + i < p.Cin) atomicAdd(dst + j + i, __uint_as_float(v[i]) * p.scale);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar);
+      item_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace xemo

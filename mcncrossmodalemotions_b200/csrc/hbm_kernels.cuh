@@ -1,0 +1,807 @@
+// hbm_kernels.cuh -- the memory-bound operators of the distillation hot path as coalesced,
+// vectorised NHWC kernels (fp16 storage, fp32 math, warp-shuffle reductions).
+//
+// Operator semantics follow MatConvNet / mcnExtraLayers; the reference reaches
+// them through dagnn blocks inside dag.eval (emoVoxCeleb/fetch_emovoxceleb_imdb.m:129,
+// external/compute_visual_feats.m:90, external/compute_audio_feats.m:126) and cnn_train_dag
+// (emoVoxCeleb/run_distillation.m:170).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xemo {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Eight consecutive channels of storage type T (fp16 inside the fused graphs, fp32 at the MatConvNet
+// boundary operators, where results must not be re-quantised).
+template <typename T>
+struct Vec8;
+template <>
+struct Vec8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = a;
+    *reinterpret_cast<float4*>(p + 4) = b;
+  }
+  __device__ __forceinline__ void to_float(float (&f)[8]) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  __device__ __forceinline__ void from_float(const float (&f)[8]) {
+    a = make_float4(f[0], f[1], f[2], f[3]);
+    b = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+template <>
+struct Vec8<__half> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __half* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(__half* p) const { *reinterpret_cast<uint4*>(p) = u; }
+  __device__ __forceinline__ void to_float(float (&f)[8]) const {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __half22float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ __forceinline__ void from_float(const float (&f)[8]) {
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  }
+};
+typedef Vec8<__half> Half8;
+// value as it would be stored in T (the fused pooling read must compare what a separate pass stores)
+template <typename T>
+__device__ __forceinline__ float round_to(float v);
+template <>
+__device__ __forceinline__ float round_to<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float round_to<__half>(float v) { return __half2float(__float2half_rn(v)); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+// ============================================================================================
+// Layout conversion at the MatConvNet boundary.  MatConvNet: H x W x C x N column-major fp32
+// (index h + H*(w + W*(c + C*n))).  Device-native: NHWC fp16, channel pitch Cp >= C (zero padded).
+// ============================================================================================
+template <typename T>
+__global__ void hwcn_f32_to_nhwc_kernel(const float* __restrict__ src, int H, int W, int C, int N,
+                                            T* __restrict__ dst, int Cp) {
+  // tile transpose over (h, c) for fixed (n, w): reads coalesced along h, writes coalesced along c
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z / W, w = blockIdx.z % W;
+  const int h0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, h = h0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && h < H) ? src[h + size_t(H) * (w + size_t(W) * (c + size_t(C) * n))] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int h = h0 + j, c = c0 + threadIdx.x;
+    if (h < H && c < Cp) dst[((size_t(n) * H + h) * W + w) * Cp + c] = from_f32<T>(tile[threadIdx.x][j]);
+  }
+}
+
+template <typename TSrc>
+__global__ void nhwc_to_hwcn_f32_kernel(const TSrc* __restrict__ src, int H, int W, int C, int N, int Cp,
+                                        float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z / W, w = blockIdx.z % W;
+  const int h0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int h = h0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (h < H && c < C) ? float(src[((size_t(n) * H + h) * W + w) * Cp + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, h = h0 + threadIdx.x;
+    if (c < C && h < H) dst[h + size_t(H) * (w + size_t(W) * (c + size_t(C) * n))] = tile[threadIdx.x][j];
+  }
+}
+
+// filters FH x FW x FC x K (column-major fp32) -> [Kp][FH][FW][Cp] fp16 (zero padded), optionally
+// flipped+transposed for dgrad: dst[c][FH-1-r][FW-1-s][k].
+__global__ void filters_to_krsc_f16_kernel(const float* __restrict__ f, int FH, int FW, int FC, int K,
+                                           __half* __restrict__ dst, int Kp, int Cp, int flip_transpose) {
+  const size_t total = flip_transpose ? size_t(Cp) * FH * FW * Kp : size_t(Kp) * FH * FW * Cp;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    float v = 0.f;
+    if (!flip_transpose) {
+      const int c = int(i % Cp);
+      const int s = int((i / Cp) % FW);
+      const int r = int((i / (size_t(Cp) * FW)) % FH);
+      const int k = int(i / (size_t(Cp) * FW * FH));
+      if (c < FC && k < K) v = f[r + size_t(FH) * (s + size_t(FW) * (c + size_t(FC) * k))];
+    } else {
+      const int k = int(i % Kp);
+      const int s2 = int((i / Kp) % FW);
+      const int r2 = int((i / (size_t(Kp) * FW)) % FH);
+      const int c = int(i / (size_t(Kp) * FW * FH));
+      const int r = FH - 1 - r2, s = FW - 1 - s2;
+      if (c < FC && k < K) v = f[r + size_t(FH) * (s + size_t(FW) * (c + size_t(FC) * k))];
+    }
+    dst[i] = __float2half_rn(v);
+  }
+}
+
+// ============================================================================================
+// Teacher input: faces 224x224x3xN (HWCN fp32, already mean-subtracted) -> "row-im2col" tensor
+// Xr[n][h][ow][32] with Xr[.., s*4+c] = x[h, 2*ow + s - pad_l, c]  (s < S, c < C; zero elsewhere), so
+// that the 7x7/2 stem becomes a 7x1 convolution with 32 input channels for the tcgen05 kernel.
+// Generic in (S, stride_w, pad_l, C<=4).
+// ============================================================================================
+__global__ void rows_im2col_from_hwcn_kernel(const float* __restrict__ src, int H, int W, int C, int N, int S,
+                                             int stride_w, int pad_l, int OW, __half* __restrict__ dst) {
+  // one thread per (n, h, ow): writes 32 halves (64 B)
+  const size_t total = size_t(N) * H * OW;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int h = int(i % H);  // h fastest so that the HWCN source is read coalesced
+    const int ow = int((i / H) % OW);
+    const int n = int(i / (size_t(H) * OW));
+    __align__(16) __half v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __float2half_rn(0.f);
+    for (int s = 0; s < S; ++s) {
+      const int w = ow * stride_w + s - pad_l;
+      if (w < 0 || w >= W) continue;
+      for (int c = 0; c < C; ++c)
+        v[s * 4 + c] = __float2half_rn(src[h + size_t(H) * (w + size_t(W) * (c + size_t(C) * n))]);
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + ((size_t(n) * H + h) * OW + ow) * 32);
+    const uint4* vi = reinterpret_cast<const uint4*>(v);
+    o[0] = vi[0]; o[1] = vi[1]; o[2] = vi[2]; o[3] = vi[3];
+  }
+}
+
+// Student input: spectrograms H x W x 1 x N (HWCN fp32) -> space-to-depth tensor
+// Y[n][hp][ow][16] with Y[.., dr*8+s] = x[2*hp + dr - pad_t, 2*ow + s - pad_l]  (dr<2, s<7), so that the
+// 7x7/2 stem becomes a 4x1 stride-1 convolution with 16 input channels (K = 64).
+__global__ void spec_s2d_from_hwcn_kernel(const float* __restrict__ src, int H, int W, int N, int pad_t, int pad_l,
+                                          int HP, int OW, __half* __restrict__ dst) {
+  const size_t total = size_t(N) * HP * OW;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int hp = int(i % HP);
+    const int ow = int((i / HP) % OW);
+    const int n = int(i / (size_t(HP) * OW));
+    __align__(16) __half v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __float2half_rn(0.f);
+#pragma unroll
+    for (int dr = 0; dr < 2; ++dr) {
+      const int h = 2 * hp + dr - pad_t;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 7; ++s) {
+        const int w = 2 * ow + s - pad_l;
+        if (w < 0 || w >= W) continue;
+        v[dr * 8 + s] = __float2half_rn(src[h + size_t(H) * (w + size_t(W) * size_t(n))]);
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + ((size_t(n) * HP + hp) * OW + ow) * 16);
+    const uint4* vi = reinterpret_cast<const uint4*>(v);
+    o[0] = vi[0]; o[1] = vi[1];
+  }
+}
+
+// ============================================================================================
+// Max pooling (vl_nnpool 'max'), NHWC fp16, 8 channels per thread.  Optional fused input transform
+// z = relu(a[c]*x + b[c]) (train/test-mode BN + ReLU folded into the pooling read).  Emits the
+// window-local arg-max idx = dw*PH + dh (first maximum in MatConvNet's memory-order scan: w outer,
+// h inner, strict '>'), which the backward pass consumes -- the "bit-exact pooling indices".
+// Padding acts as -inf.
+// ============================================================================================
+struct PoolGeom {
+  int N, H, W, C;       // input
+  int PH, PW, sh, sw, pt, pl;
+  int OH, OW;
+};
+
+template <typename T, bool kAffineRelu>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, PoolGeom g, const float* __restrict__ a,
+                                   const float* __restrict__ b, T* __restrict__ y, uint8_t* __restrict__ idx) {
+  const int C8 = g.C >> 3;
+  const size_t total = size_t(g.N) * g.OH * g.OW * C8;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int c8 = int(i % C8);
+    const int ow = int((i / C8) % g.OW);
+    const int oh = int((i / (size_t(C8) * g.OW)) % g.OH);
+    const int n = int(i / (size_t(C8) * g.OW * g.OH));
+    float best[8];
+    uint8_t arg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; arg[k] = 0; }
+    float av[8], bv[8];
+    if (kAffineRelu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { av[k] = a[c8 * 8 + k]; bv[k] = b[c8 * 8 + k]; }
+    }
+    for (int dw = 0; dw < g.PW; ++dw) {
+      const int w = ow * g.sw + dw - g.pl;
+      if (w < 0 || w >= g.W) continue;
+      for (int dh = 0; dh < g.PH; ++dh) {
+        const int h = oh * g.sh + dh - g.pt;
+        if (h < 0 || h >= g.H) continue;
+        Vec8<T> v;
+        v.load(x + ((size_t(n) * g.H + h) * g.W + w) * g.C + c8 * 8);
+        float f[8];
+        v.to_float(f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float z = f[k];
+          if (kAffineRelu) {
+            // round through fp16 so that the value compared here is exactly what a separate
+            // bn+relu pass would have stored
+            z = round_to<T>(fmaxf(fmaf(av[k], z, bv[k]), 0.f));
+          }
+          if (z > best[k]) { best[k] = z; arg[k] = uint8_t(dw * g.PH + dh); }
+        }
+      }
+    }
+    Vec8<T> o;
+    o.from_float(best);
+    const size_t off = ((size_t(n) * g.OH + oh) * g.OW + ow) * g.C + c8 * 8;
+    o.store(y + off);
+    if (idx) {
+      uint2 pk;
+      pk.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (uint32_t(arg[3]) << 24);
+      pk.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (uint32_t(arg[7]) << 24);
+      *reinterpret_cast<uint2*>(idx + off) = pk;
+    }
+  }
+}
+
+// Backward of max pooling as a gather: every input position collects dy from the windows whose
+// recorded arg-max points at it (no atomics, deterministic).
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, PoolGeom g,
+                                   T* __restrict__ dx) {
+  const int C8 = g.C >> 3;
+  const size_t total = size_t(g.N) * g.H * g.W * C8;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int c8 = int(i % C8);
+    const int w = int((i / C8) % g.W);
+    const int h = int((i / (size_t(C8) * g.W)) % g.H);
+    const int n = int(i / (size_t(C8) * g.W * g.H));
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    // windows (oh, ow) covering (h, w): oh*sh - pt <= h < oh*sh - pt + PH
+    const int oh_hi = min((h + g.pt) / g.sh, g.OH - 1);
+    const int ow_hi = min((w + g.pl) / g.sw, g.OW - 1);
+    for (int oh = oh_hi; oh >= 0; --oh) {
+      const int dh = h + g.pt - oh * g.sh;
+      if (dh >= g.PH) break;
+      for (int ow = ow_hi; ow >= 0; --ow) {
+        const int dw = w + g.pl - ow * g.sw;
+        if (dw >= g.PW) break;
+        const size_t off = ((size_t(n) * g.OH + oh) * g.OW + ow) * g.C + c8 * 8;
+        const uint2 pk = *reinterpret_cast<const uint2*>(idx + off);
+        Vec8<T> v;
+        v.load(dy + off);
+        float f[8];
+        v.to_float(f);
+        const uint32_t me = uint32_t(dw * g.PH + dh);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t a = ((k < 4 ? pk.x : pk.y) >> (8 * (k & 3))) & 0xFF;
+          if (a == me) acc[k] += f[k];
+        }
+      }
+    }
+    Vec8<T> o;
+    o.from_float(acc);
+    o.store(dx + ((size_t(n) * g.H + h) * g.W + w) * g.C + c8 * 8);
+  }
+}
+
+// Average pooling (vl_nnpool 'avg'): divides by the number of in-bounds window elements.
+template <typename T>
+__global__ void avgpool_fwd_kernel(const T* __restrict__ x, PoolGeom g, T* __restrict__ y) {
+  const int C8 = g.C >> 3;
+  const size_t total = size_t(g.N) * g.OH * g.OW * C8;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int c8 = int(i % C8);
+    const int ow = int((i / C8) % g.OW);
+    const int oh = int((i / (size_t(C8) * g.OW)) % g.OH);
+    const int n = int(i / (size_t(C8) * g.OW * g.OH));
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    int cnt = 0;
+    for (int dh = 0; dh < g.PH; ++dh) {
+      const int h = oh * g.sh + dh - g.pt;
+      if (h < 0 || h >= g.H) continue;
+      for (int dw = 0; dw < g.PW; ++dw) {
+        const int w = ow * g.sw + dw - g.pl;
+        if (w < 0 || w >= g.W) continue;
+        Vec8<T> v;
+        v.load(x + ((size_t(n) * g.H + h) * g.W + w) * g.C + c8 * 8);
+        float f[8];
+        v.to_float(f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += f[k];
+        ++cnt;
+      }
+    }
+    const float inv = 1.f / float(cnt);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] *= inv;
+    Vec8<T> o;
+    o.from_float(acc);
+    o.store(y + ((size_t(n) * g.OH + oh) * g.OW + ow) * g.C + c8 * 8);
+  }
+}
+
+template <typename T>
+__global__ void avgpool_bwd_kernel(const T* __restrict__ dy, PoolGeom g, T* __restrict__ dx) {
+  const int C8 = g.C >> 3;
+  const size_t total = size_t(g.N) * g.H * g.W * C8;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int c8 = int(i % C8);
+    const int w = int((i / C8) % g.W);
+    const int h = int((i / (size_t(C8) * g.W)) % g.H);
+    const int n = int(i / (size_t(C8) * g.W * g.H));
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const int oh_hi = min((h + g.pt) / g.sh, g.OH - 1);
+    const int ow_hi = min((w + g.pl) / g.sw, g.OW - 1);
+    for (int oh = oh_hi; oh >= 0; --oh) {
+      if (h + g.pt - oh * g.sh >= g.PH) break;
+      for (int ow = ow_hi; ow >= 0; --ow) {
+        if (w + g.pl - ow * g.sw >= g.PW) break;
+        // in-bounds element count of window (oh, ow)
+        const int h0 = max(oh * g.sh - g.pt, 0), h1 = min(oh * g.sh - g.pt + g.PH, g.H);
+        const int w0 = max(ow * g.sw - g.pl, 0), w1 = min(ow * g.sw - g.pl + g.PW, g.W);
+        const float inv = 1.f / float((h1 - h0) * (w1 - w0));
+        Vec8<T> v;
+        v.load(dy + ((size_t(n) * g.OH + oh) * g.OW + ow) * g.C + c8 * 8);
+        float f[8];
+        v.to_float(f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += f[k] * inv;
+      }
+    }
+    Vec8<T> o;
+    o.from_float(acc);
+    o.store(dx + ((size_t(n) * g.H + h) * g.W + w) * g.C + c8 * 8);
+  }
+}
+
+// ============================================================================================
+// Batch normalisation (vl_nnbnorm).  x: [P = N*H*W][C] fp16.
+//   stats pass : per-channel sum / sum of squares in fp32 -> (double) atomics into acc[2*C]
+//   finalize   : mu = S1/P, var = S2/P - mu^2 (biased), sigma = sqrt(var + eps); moments = [mu sigma];
+//                a = g/sigma, b = beta - a*mu  (the affine the apply / pooling kernels consume)
+//   apply      : y = a*x + b (+ReLU)
+//   backward   : reduce db = sum(dz), dg = sum(dz * xhat) with dz = dy * [y>0] when ReLU is fused;
+//                dx = a * (dz - db/P - xhat*dg/P)
+// ============================================================================================
+constexpr int kBnRowsPerBlock = 256;
+
+template <typename T>
+__global__ void bn_stats_kernel(const T* __restrict__ x, size_t P, int C, double* __restrict__ acc) {
+  // block = (C/8 lanes) x rows; each thread owns 8 channels and strides over rows
+  const int C8 = C >> 3;
+  const int lanes = C8 < int(blockDim.x) ? C8 : int(blockDim.x);
+  const int rows_par = blockDim.x / lanes;
+  const int rl = threadIdx.x / lanes;
+  const int cl = threadIdx.x - rl * lanes;
+  if (rl >= rows_par) return;
+  const size_t row0 = size_t(blockIdx.x) * kBnRowsPerBlock;
+  const size_t row1 = row0 + kBnRowsPerBlock < P ? row0 + kBnRowsPerBlock : P;
+  for (int c8 = cl + blockIdx.y * lanes; c8 < C8; c8 += lanes * gridDim.y) {
+    float s1[8], s2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+    for (size_t r = row0 + rl; r < row1; r += rows_par) {
+      Vec8<T> v;
+      v.load(x + r * C + c8 * 8);
+      float f[8];
+      v.to_float(f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s1[k] += f[k]; s2[k] = fmaf(f[k], f[k], s2[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&acc[c8 * 8 + k], double(s1[k]));
+      atomicAdd(&acc[C + c8 * 8 + k], double(s2[k]));
+    }
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ acc, size_t P, int C, const float* __restrict__ g,
+                                   const float* __restrict__ beta, float eps, float* __restrict__ moments,
+                                   float* __restrict__ a, float* __restrict__ b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = acc[c] / double(P);
+  double var = acc[C + c] / double(P) - mu * mu;
+  if (var < 0) var = 0;
+  const double sigma = sqrt(var + double(eps));
+  moments[c] = float(mu);
+  moments[C + c] = float(sigma);  // C x 2 column-major: [mu | sigma]
+  const double aa = double(g[c]) / sigma;
+  a[c] = float(aa);
+  b[c] = float(double(beta[c]) - aa * mu);
+}
+
+// test mode: moments given (C x 2 = [mu sigma])
+__global__ void bn_affine_from_moments_kernel(const float* __restrict__ moments, int C, const float* __restrict__ g,
+                                              const float* __restrict__ beta, float* __restrict__ a,
+                                              float* __restrict__ b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float aa = g[c] / moments[C + c];
+  a[c] = aa;
+  b[c] = beta[c] - aa * moments[c];
+}
+
+template <typename T>
+__global__ void affine_act_kernel(const T* __restrict__ x, size_t P, int C, const float* __restrict__ a,
+                                  const float* __restrict__ b, int relu, T* __restrict__ y) {
+  const int C8 = C >> 3;
+  const size_t total = P * C8;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int c8 = int(i % C8);
+    Vec8<T> v;
+    v.load(x + i * 8);
+    float f[8];
+    v.to_float(f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float z = a ? fmaf(a[c8 * 8 + k], f[k], b[c8 * 8 + k]) : f[k];
+      if (relu) z = fmaxf(z, 0.f);
+      f[k] = z;
+    }
+    v.from_float(f);
+    v.store(y + i * 8);
+  }
+}
+
+// backward reduce: acc[0..C) += sum dz ; acc[C..2C) += sum dz * xhat, xhat = (x - mu)/sigma.
+// dz = dy * [a*x+b > 0] when relu_mask.
+template <typename T>
+__global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, size_t P, int C,
+                                     const float* __restrict__ moments, const float* __restrict__ a,
+                                     const float* __restrict__ b, int relu_mask, double* __restrict__ acc) {
+  const int C8 = C >> 3;
+  const int lanes = C8 < int(blockDim.x) ? C8 : int(blockDim.x);
+  const int rows_par = blockDim.x / lanes;
+  const int rl = threadIdx.x / lanes;
+  const int cl = threadIdx.x - rl * lanes;
+  if (rl >= rows_par) return;
+  const size_t row0 = size_t(blockIdx.x) * kBnRowsPerBlock;
+  const size_t row1 = row0 + kBnRowsPerBlock < P ? row0 + kBnRowsPerBlock : P;
+  for (int c8 = cl + blockIdx.y * lanes; c8 < C8; c8 += lanes * gridDim.y) {
+    float s1[8], s2[8], mu[8], isg[8], av[8], bv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s1[k] = 0.f; s2[k] = 0.f;
+      mu[k] = moments[c8 * 8 + k];
+      isg[k] = 1.f / moments[C + c8 * 8 + k];
+      av[k] = a[c8 * 8 + k];
+      bv[k] = b[c8 * 8 + k];
+    }
+    for (size_t r = row0 + rl; r < row1; r += rows_par) {
+      Vec8<T> vx, vd;
+      vx.load(x + r * C + c8 * 8);
+      vd.load(dy + r * C + c8 * 8);
+      float fx[8], fd[8];
+      vx.to_float(fx);
+      vd.to_float(fd);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float dz = fd[k];
+        if (relu_mask && !(fmaf(av[k], fx[k], bv[k]) > 0.f)) dz = 0.f;
+        s1[k] += dz;
+        s2[k] = fmaf(dz, (fx[k] - mu[k]) * isg[k], s2[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&acc[c8 * 8 + k], double(s1[k]));
+      atomicAdd(&acc[C + c8 * 8 + k], double(s2[k]));
+    }
+  }
+}
+
+// dx = a * (dz - db/P - xhat * dg/P); also emits dg, db (fp32, scaled by 1/grad_scale) once.
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, size_t P, int C,
+                                    const float* __restrict__ moments, const float* __restrict__ a,
+                                    const float* __restrict__ b, int relu_mask, const double* __restrict__ acc,
+                                    T* __restrict__ dx) {
+  const int C8 = C >> 3;
+  const size_t total = P * C8;
+  const float invP = 1.f / float(P);
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int c8 = int(i % C8);
+    Vec8<T> vx, vd;
+    vx.load(x + i * 8);
+    vd.load(dy + i * 8);
+    float fx[8], fd[8];
+    vx.to_float(fx);
+    vd.to_float(fd);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c8 * 8 + k;
+      const float av = a[c], bv = b[c];
+      float dz = fd[k];
+      if (relu_mask && !(fmaf(av, fx[k], bv) > 0.f)) dz = 0.f;
+      const float xhat = (fx[k] - moments[c]) / moments[C + c];
+      fd[k] = av * (dz - float(acc[c]) * invP - xhat * float(acc[C + c]) * invP);
+    }
+    vd.from_float(fd);
+    vd.store(dx + i * 8);
+  }
+}
+
+__global__ void bn_bwd_params_kernel(const double* __restrict__ acc, int C, float inv_grad_scale,
+                                     float* __restrict__ dg, float* __restrict__ db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  db[c] = float(acc[c]) * inv_grad_scale;
+  dg[c] = float(acc[C + c]) * inv_grad_scale;
+}
+
+// plain ReLU backward: dx = dy * [y > 0] (y = ReLU output)
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy, size_t n8,
+                                T* __restrict__ dx) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {
+    Vec8<T> vy, vd;
+    vy.load(y + i * 8);
+    vd.load(dy + i * 8);
+    float fy[8], fd[8];
+    vy.to_float(fy);
+    vd.to_float(fd);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fd[k] = fy[k] > 0.f ? fd[k] : 0.f;
+    vd.from_float(fd);
+    vd.store(dx + i * 8);
+  }
+}
+
+// ============================================================================================
+// Squeeze-and-excitation (mcnExtraLayers GlobalPooling / Conv 1x1 / Sigmoid / Axpy).
+//   squeeze : s[n][c] = mean_{h,w} u[n,h,w,c]                       (fp32 out)
+//   gate    : a = sigmoid(W2 * relu(W1 * s + b1) + b2)              (one block per sample)
+//   excite  : y = relu(a[n][c] * u + shortcut)                      (vectorised pass)
+// ============================================================================================
+template <typename T>
+__global__ void se_squeeze_kernel(const T* __restrict__ u, int HW, int C, float* __restrict__ s) {
+  // grid: (C/8/32 chunks, N); block 32 x 8: lane -> channel group, y -> pixel stride
+  const int n = blockIdx.y;
+  const int c8 = blockIdx.x * 32 + threadIdx.x;
+  __shared__ float part[8][32][8];
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (c8 * 8 < C) {
+    for (int p = threadIdx.y; p < HW; p += 8) {
+      Vec8<T> v;
+      v.load(u + (size_t(n) * HW + p) * C + c8 * 8);
+      float f[8];
+      v.to_float(f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += f[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) part[threadIdx.y][threadIdx.x][k] = acc[k];
+  __syncthreads();
+  if (threadIdx.y == 0 && c8 * 8 < C) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = 0.f;
+      for (int j = 0; j < 8; ++j) t += part[j][threadIdx.x][k];
+      s[size_t(n) * C + c8 * 8 + k] = t / float(HW);
+    }
+  }
+}
+
+// one block (256 threads) per sample.  w1: [Cr][C] fp32, w2: [C][Cr] fp32.
+__global__ void se_gate_kernel(const float* __restrict__ s, int C, int Cr, const float* __restrict__ w1,
+                               const float* __restrict__ b1, const float* __restrict__ w2,
+                               const float* __restrict__ b2, float* __restrict__ gate) {
+  extern __shared__ float sm[];
+  float* sv = sm;        // [C]
+  float* hid = sm + C;   // [Cr]
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sv[c] = s[size_t(n) * C + c];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < Cr; j += nwarps) {
+    float t = 0.f;
+    for (int c = lane; c < C; c += 32) t = fmaf(w1[size_t(j) * C + c], sv[c], t);
+    t = warp_sum(t);
+    if (lane == 0) hid[j] = fmaxf(t + (b1 ? b1[j] : 0.f), 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = b2 ? b2[c] : 0.f;
+    for (int j = 0; j < Cr; ++j) t = fmaf(w2[size_t(c) * Cr + j], hid[j], t);
+    gate[size_t(n) * C + c] = 1.f / (1.f + __expf(-t));
+  }
+}
+
+template <typename T>
+__global__ void se_excite_kernel(const T* __restrict__ u, const float* __restrict__ gate,
+                                 const T* __restrict__ shortcut, int HW, int C, size_t total8, int relu,
+                                 T* __restrict__ y) {
+  const int C8 = C >> 3;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total8; i += size_t(gridDim.x) * blockDim.x) {
+    const int c8 = int(i % C8);
+    const size_t n = i / (size_t(C8) * HW);
+    Vec8<T> vu, vs;
+    vu.load(u + i * 8);
+    float fu[8], fs[8];
+    vu.to_float(fu);
+    if (shortcut) { vs.load(shortcut + i * 8); vs.to_float(fs); }
+    const float4 g0 = *reinterpret_cast<const float4*>(gate + n * C + c8 * 8);
+    const float4 g1 = *reinterpret_cast<const float4*>(gate + n * C + c8 * 8 + 4);
+    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float z = fmaf(gv[k], fu[k], shortcut ? fs[k] : 0.f);
+      if (relu) z = fmaxf(z, 0.f);
+      fu[k] = z;
+    }
+    vu.from_float(fu);
+    vu.store(y + i * 8);
+  }
+}
+
+// element-wise add (+ReLU): dagnn.Sum for the cases not fused into a conv epilogue
+template <typename T>
+__global__ void add_act_kernel(const T* __restrict__ a, const T* __restrict__ b, size_t n8, int relu,
+                               T* __restrict__ y) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {
+    Vec8<T> va, vb;
+    va.load(a + i * 8);
+    vb.load(b + i * 8);
+    float fa[8], fb[8];
+    va.to_float(fa);
+    vb.to_float(fb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float z = fa[k] + fb[k];
+      fa[k] = relu ? fmaxf(z, 0.f) : z;
+    }
+    va.from_float(fa);
+    va.store(y + i * 8);
+  }
+}
+
+// ============================================================================================
+// Teacher -> student coupling (emoVoxCeleb/getBatchEmoVoxCeleb.m:133-159,179-188,210-214): per clip,
+// aggregate ('max' default, or 'mean') the frame logits lgts[start:end, :] over the frames selected for
+// the audio crop.  frame_logits: [sum F_i][ldl] fp32 (row-major per frame), first numPred classes used.
+// ============================================================================================
+__global__ void logit_aggregate_kernel(const float* __restrict__ frame_logits, int ldl, const int* __restrict__ start,
+                                       const int* __restrict__ end, int N, int numPred, int use_mean,
+                                       float* __restrict__ target /* [N][numPred] */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * numPred) return;
+  const int n = i / numPred, c = i - n * numPred;
+  float acc = use_mean ? 0.f : -INFINITY;
+  for (int f = start[n]; f < end[n]; ++f) {
+    const float v = frame_logits[size_t(f) * ldl + c];
+    acc = use_mean ? acc + v : fmaxf(acc, v);
+  }
+  if (use_mean) acc /= float(end[n] - start[n]);
+  target[i] = acc;
+}
+
+// ============================================================================================
+// Distillation loss (mcnExtraLayers vl_nnsoftmaxceloss wired at emoVoxCeleb/emoVoxZoo.m:151-157) fused
+// with its backward and with the reference's metric layers (classerror / ErrorStats,
+// emoVoxZoo.m:160-169).  One thread per sample, C <= 16 classes.
+//   p = softmax(t/T) (logitTargets) ; q = softmax(x/T) ; loss = sum_n w_n * -sum_c p log q
+//   dx = dzdy * w_n * (q - p)/T   (stored fp16, scaled by grad_scale, row pitch ldx)
+//   maxLabel = argmax_c t (first max, 1-based) ; nerr += [argmax x != maxLabel] ; per-class counters.
+// out_scalars: [0]=loss [1]=classerror ; class_stats: [C] correct, [C] count.
+// ============================================================================================
+constexpr int kLossMaxC = 16;
+__global__ void softmaxce_fused_kernel(const __half* __restrict__ x, int ldx, const float* __restrict__ t, int ldt,
+                                       const float* __restrict__ w, int N, int C, float T, int logit_targets,
+                                       float dzdy, float grad_scale, __half* __restrict__ dx,
+                                       float* __restrict__ out_scalars, float* __restrict__ class_stats,
+                                       int* __restrict__ max_label) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  float loss = 0.f, err = 0.f;
+  if (n < N) {
+    float xv[kLossMaxC], tv[kLossMaxC];
+    float xm = -INFINITY, tm = -INFINITY;
+    int xa = 0, ta = 0;
+    for (int c = 0; c < C; ++c) {
+      xv[c] = __half2float(x[size_t(n) * ldx + c]);
+      tv[c] = t[size_t(n) * ldt + c];
+      if (xv[c] > xm) { xm = xv[c]; xa = c; }
+      if (tv[c] > tm) { tm = tv[c]; ta = c; }
+    }
+    const float invT = 1.f / T;
+    float xs = 0.f, ts = 0.f;
+    for (int c = 0; c < C; ++c) {
+      xv[c] = (xv[c] - xm) * invT;
+      xs += expf(xv[c]);
+      if (logit_targets) { tv[c] = expf((tv[c] - tm) * invT); ts += tv[c]; }
+    }
+    const float lse = logf(xs);
+    const float wn = w ? w[n] : 1.f;
+    for (int c = 0; c < C; ++c) {
+      const float p = logit_targets ? tv[c] / ts : tv[c];
+      const float logq = xv[c] - lse;
+      loss -= p * logq;
+      if (dx) dx[size_t(n) * ldx + c] = __float2half_rn(grad_scale * dzdy * wn * (expf(logq) - p) * invT);
+    }
+    loss *= wn;
+    err = (xa != ta) ? 1.f : 0.f;
+    if (max_label) max_label[n] = ta + 1;
+    if (class_stats) {
+      atomicAdd(&class_stats[C + ta], 1.f);
+      if (xa == ta) atomicAdd(&class_stats[ta], 1.f);
+    }
+  }
+  loss = warp_sum(loss);
+  err = warp_sum(err);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&out_scalars[0], loss);
+    atomicAdd(&out_scalars[1], err);
+  }
+}
+
+// ============================================================================================
+// cnn_train_dag's SGD-momentum update (defaults inherited at emoVoxCeleb/run_distillation.m:170-182):
+//   m <- mu*m - (lambda*wd_mult*w + g/B) ;  w <- w + lr*lr_mult*m
+// fused with the refresh of the fp16 KRSC filter copy the tcgen05 kernels read.  `g` may carry the
+// loss scale (inv_grad_scale undoes it).  One launch per parameter tensor (flat fp32 master copy).
+// ============================================================================================
+__global__ void sgd_momentum_kernel(float* __restrict__ w, float* __restrict__ m, const float* __restrict__ g, size_t n,
+                                    float lr, float momentum, float wd, float inv_batch, float inv_grad_scale,
+                                    __half* __restrict__ w16) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const float wi = w[i];
+    const float mi = momentum * m[i] - (wd * wi + g[i] * inv_grad_scale * inv_batch);
+    const float wn = wi + lr * mi;
+    m[i] = mi;
+    w[i] = wn;
+    if (w16) w16[i] = __float2half_rn(wn);
+  }
+}
+
+// BN moments moving average (dagnn.BatchNorm moments param: trainMethod 'average', learningRate 0.1):
+//   moments <- (1 - rate) * moments + rate * batch_moments
+__global__ void moments_average_kernel(float* __restrict__ moments, const float* __restrict__ batch_moments, int n,
+                                       float rate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) moments[i] = (1.f - rate) * moments[i] + rate * batch_moments[i];
+}
+
+__global__ void f32_to_f16_kernel(const float* __restrict__ s, size_t n, __half* __restrict__ d) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    d[i] = __float2half_rn(s[i]);
+}
+__global__ void f16_to_f32_kernel(const __half* __restrict__ s, size_t n, float scale, float* __restrict__ d) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    d[i] = __half2float(s[i]) * scale;
+}
+
+}  // namespace xemo

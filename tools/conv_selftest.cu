@@ -216,6 +216,140 @@ static int run_case(const Case& c, bool perf) {
   return bad ? 1 : 0;
 }
 
+// ------------------------------------------------------------------ filter gradient
+struct WCase {
+  const char* name;
+  ConvGeom g;
+  int kpad;  // dY row pitch (0 -> Kout)
+};
+static const WCase kWCases[] = {
+    {"wgrad 1x1 c64 k128", {2, 16, 16, 64, 128, 1, 1, 1, 1, 0, 0, 0, 0}, 0},
+    {"wgrad 3x3 p1 c64 k64 14x14 n3", {3, 14, 14, 64, 64, 3, 3, 1, 1, 1, 1, 1, 1}, 0},
+    {"wgrad 3x3 p1 c256 k384 30x17 n2", {2, 30, 17, 256, 384, 3, 3, 1, 1, 1, 1, 1, 1}, 0},
+    {"wgrad 5x5 s2 p1 c96 k256 30x21", {2, 30, 21, 96, 256, 5, 5, 2, 2, 1, 1, 1, 1}, 0},
+    {"wgrad 9x1 c256 k512 9x8 (fc6-like)", {3, 9, 8, 256, 512, 9, 1, 1, 1, 0, 0, 0, 0}, 0},
+    {"wgrad 4x1 c16 k96 (student conv1 s2d)", {2, 33, 20, 16, 96, 4, 1, 1, 1, 0, 0, 0, 0}, 0},
+    {"wgrad 1x1 c1024 k8 pitch16 (fc8)", {37, 1, 1, 1024, 8, 1, 1, 1, 1, 0, 0, 0, 0}, 16},
+    {"wgrad 1x1 c4096 k1024 n50 (fc7)", {50, 1, 1, 4096, 1024, 1, 1, 1, 1, 0, 0, 0, 0}, 0},
+    {"wgrad 3x3 c384 k256 (block_c 192)", {2, 10, 9, 384, 256, 3, 3, 1, 1, 1, 1, 1, 1}, 0},
+    {"wgrad 3x3 c32 k48 pitch48", {2, 10, 9, 32, 48, 3, 3, 1, 1, 1, 1, 1, 1}, 0},
+};
+static const int kNumWCases = sizeof(kWCases) / sizeof(kWCases[0]);
+static const WCase kWPerf[] = {
+    {"vox conv1 s2d 4x1 c16 k96 257x148 n128", {128, 257, 148, 16, 96, 4, 1, 1, 1, 0, 0, 0, 0}, 0},
+    {"vox conv2 5x5 s2 c96 k256 126x73 n128", {128, 126, 73, 96, 256, 5, 5, 2, 2, 1, 1, 1, 1}, 0},
+    {"vox conv3 3x3 c256 k384 30x17 n128", {128, 30, 17, 256, 384, 3, 3, 1, 1, 1, 1, 1, 1}, 0},
+    {"vox conv4 3x3 c384 k256 30x17 n128", {128, 30, 17, 384, 256, 3, 3, 1, 1, 1, 1, 1, 1}, 0},
+    {"vox fc6 9x1 c256 k4096 9x8 n128", {128, 9, 8, 256, 4096, 9, 1, 1, 1, 0, 0, 0, 0}, 0},
+    {"vox fc7 1x1 c4096 k1024 n128", {128, 1, 1, 4096, 1024, 1, 1, 1, 1, 0, 0, 0, 0}, 0},
+};
+static const int kNumWPerf = sizeof(kWPerf) / sizeof(kWPerf[0]);
+
+// one thread per sampled filter element (k, r, s, c)
+__global__ void naive_wgrad(const __half* x, const __half* dy, int ldy, float* ref, ConvGeom g, int OH, int OW,
+                            long total, int step) {
+  const long t = blockIdx.x * long(blockDim.x) + threadIdx.x;
+  if (t * step >= total) return;
+  const long i = t * step;
+  const int c = int(i % g.Cin);
+  const int s = int((i / g.Cin) % g.S);
+  const int r = int((i / (long(g.Cin) * g.S)) % g.R);
+  const int k = int(i / (long(g.Cin) * g.S * g.R));
+  double acc = 0;
+  for (int n = 0; n < g.N; ++n)
+    for (int oh = 0; oh < OH; ++oh) {
+      const int h = oh * g.sh + r - g.pt;
+      if (h < 0 || h >= g.H) continue;
+      for (int ow = 0; ow < OW; ++ow) {
+        const int w = ow * g.sw + s - g.pl;
+        if (w < 0 || w >= g.W) continue;
+        acc += double(__half2float(x[((size_t(n) * g.H + h) * g.W + w) * g.Cin + c])) *
+               double(__half2float(dy[((size_t(n) * OH + oh) * OW + ow) * ldy + k]));
+      }
+    }
+  ref[t] = float(acc);
+}
+
+static int run_wcase(const WCase& c, bool perf) {
+  const ConvGeom& g = c.g;
+  const int OH = g.OH(), OW = g.OW();
+  const int ldy = c.kpad ? c.kpad : g.Kout;
+  const size_t nx = size_t(g.N) * g.H * g.W * g.Cin;
+  const size_t P = size_t(g.N) * OH * OW;
+  const size_t ny = P * ldy;
+  const size_t nw = size_t(g.Kout) * g.R * g.S * g.Cin;
+  printf("[%s] N=%d HxW=%dx%d Cin=%d Kout=%d (pitch %d) RxS=%dx%d stride=%d,%d pad=%d,%d,%d,%d P=%zu\n", c.name, g.N, g.H,
+         g.W, g.Cin, g.Kout, ldy, g.R, g.S, g.sh, g.sw, g.pt, g.pb, g.pl, g.pr, P);
+  std::vector<__half> hx(nx), hy(ny);
+  uint32_t seed = 4321u + uint32_t(g.Cin * 3 + g.Kout);
+  for (auto& v : hx) v = __float2half(frand(seed) * 2.f);
+  for (size_t i = 0; i < ny; ++i) hy[i] = __float2half((int(i % ldy) < g.Kout) ? frand(seed) * 2.f : 0.f);
+  __half *dx, *dy;
+  float *ddf, *dref;
+  CK(cudaMalloc(&dx, nx * 2));
+  CK(cudaMalloc(&dy, ny * 2));
+  CK(cudaMalloc(&ddf, nw * 4));
+  CK(cudaMemcpy(dx, hx.data(), nx * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dy, hy.data(), ny * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(ddf, 0, nw * 4));
+  int dev = 0, sms = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  WgradPlan plan;
+  if (!conv_wgrad_plan(&plan, g, dx, dy, ldy, ddf, 1.f, sms)) { printf("  PLAN FAILED\n"); return 3; }
+  printf("  plan: chunk_a=%d chunk_b=%d block_c=%d c_tiles=%d T=%d groups=%d m_tiles=%d splits=%d (x%d blocks) stages=%d grid=%d smem=%d\n",
+         plan.p.chunk_a, plan.p.chunk_b, plan.p.block_c, plan.p.c_tiles, plan.p.T, plan.p.groups, plan.p.m_tiles,
+         plan.p.splits, plan.p.pix_blocks_per_split, plan.p.num_stages, plan.grid, plan.smem);
+  CK(conv_wgrad_run(plan, 0));
+  CK(cudaDeviceSynchronize());
+  std::vector<float> hdf(nw);
+  CK(cudaMemcpy(hdf.data(), ddf, nw * 4, cudaMemcpyDeviceToHost));
+  if (perf) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) CK(conv_wgrad_run(plan, 0));
+    const int iters = 10;
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) CK(conv_wgrad_run(plan, 0));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= iters;
+    const double bytes = double(nx) * 2 + double(ny) * 2 + double(nw) * 4;
+    printf("  time %.3f ms  %.1f TFLOP/s  (min-traffic %.1f MB -> %.0f GB/s)\n", ms, plan.flops / ms * 1e-9, bytes * 1e-6,
+           bytes / ms * 1e-6);
+  }
+  const int step = perf ? 997 : 1;
+  const long total = long(nw);
+  const long nref = (total + step - 1) / step;
+  CK(cudaMalloc(&dref, nref * 4));
+  naive_wgrad<<<unsigned((nref + 127) / 128), 128>>>(dx, dy, ldy, dref, g, OH, OW, total, step);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> href(nref);
+  CK(cudaMemcpy(href.data(), dref, nref * 4, cudaMemcpyDeviceToHost));
+  double max_ref = 0, max_err = 0;
+  for (long t = 0; t < nref; ++t) max_ref = fmax(max_ref, fabs(href[t]));
+  size_t bad = 0, shown = 0;
+  for (long t = 0; t < nref; ++t) {
+    const double e = fabs(double(hdf[t * step]) - href[t]);
+    if (!(e == e)) max_err = INFINITY;
+    max_err = fmax(max_err, e);
+    if (!(e <= 1e-4 * max_ref + 1e-5)) {
+      ++bad;
+      if (shown < 12) {
+        const long i = t * step;
+        printf("  MISMATCH k=%ld r=%ld s=%ld c=%ld got=%g ref=%g\n", i / (long(g.Cin) * g.S * g.R),
+               (i / (long(g.Cin) * g.S)) % g.R, (i / g.Cin) % g.S, i % g.Cin, hdf[i], href[t]);
+        ++shown;
+      }
+    }
+  }
+  printf("  max|ref|=%.4g  max_err=%.3g  bad=%zu/%ld  => %s\n", max_ref, max_err, bad, nref, bad ? "FAIL" : "PASS");
+  return bad ? 1 : 0;
+}
+
 // ------------------------------------------------------------------ im2col diagnostics
 __global__ void im2col_dump_kernel(const __grid_constant__ CUtensorMap tm, __half* out, int bytes, int c, int w, int h,
                                    int n, int off_w, int off_h) {
@@ -311,12 +445,14 @@ static int run_diag() {
 
 int main(int argc, char** argv) {
   if (argc < 2) { printf("usage: conv_selftest list|case i|perf i|diag\n"); return 64; }
-  if (!strcmp(argv[1], "list")) { printf("%d %d\n", kNumCases, kNumPerf); return 0; }
+  if (!strcmp(argv[1], "list")) { printf("%d %d %d %d\n", kNumCases, kNumPerf, kNumWCases, kNumWPerf); return 0; }
   if (!tma_api().ok) { printf("TMA driver entry points unavailable\n"); return 4; }
   if (!strcmp(argv[1], "diag")) return run_diag();
   if (argc < 3) return 64;
   const int i = atoi(argv[2]);
   if (!strcmp(argv[1], "case")) { if (i < 0 || i >= kNumCases) return 64; return run_case(kCases[i], false); }
   if (!strcmp(argv[1], "perf")) { if (i < 0 || i >= kNumPerf) return 64; return run_case(kPerf[i], true); }
+  if (!strcmp(argv[1], "wcase")) { if (i < 0 || i >= kNumWCases) return 64; return run_wcase(kWCases[i], false); }
+  if (!strcmp(argv[1], "wperf")) { if (i < 0 || i >= kNumWPerf) return 64; return run_wcase(kWPerf[i], true); }
   return 64;
 }

@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv >> $
 B=build/conv_selftest
 echo "== diag" >> $LOG
 timeout 60 $B diag >> $LOG 2>&1; echo "exit=$?" >> $LOG
-read NC NP < <($B list)
+read NC NP NWC NWP < <($B list)
 for i in $(seq 0 $((NC-1))); do
   echo "== case $i" >> $LOG
   timeout 60 $B case $i >> $LOG 2>&1; echo "exit=$?" >> $LOG
@@ -16,4 +16,12 @@ for i in $(seq 0 $((NP-1))); do
   echo "== perf $i" >> $LOG
   timeout 120 $B perf $i >> $LOG 2>&1; echo "exit=$?" >> $LOG
 done
-grep -E "PASS|FAIL|exit=|TFLOP" $LOG | tail -80
+for i in $(seq 0 $((NWC-1))); do
+  echo "== wcase $i" >> $LOG
+  timeout 60 $B wcase $i >> $LOG 2>&1; echo "exit=$?" >> $LOG
+done
+for i in $(seq 0 $((NWP-1))); do
+  echo "== wperf $i" >> $LOG
+  timeout 120 $B wperf $i >> $LOG 2>&1; echo "exit=$?" >> $LOG
+done
+grep -E "PASS|FAIL|exit=[1-9]|TFLOP" $LOG | tail -120
