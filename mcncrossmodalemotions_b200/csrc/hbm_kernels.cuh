@@ -117,7 +117,7 @@ __global__ void nhwc_to_hwcn_f32_kernel(const TSrc* __restrict__ src, int H, int
 
 // filters FH x FW x FC x K (column-major fp32) -> [Kp][FH][FW][Cp] fp16 (zero padded), optionally
 // flipped+transposed for dgrad: dst[c][FH-1-r][FW-1-s][k].
-__global__ void filters_to_krsc_f16_kernel(const float* __restrict__ f, int FH, int FW, int FC, int K,
+static __global__ void filters_to_krsc_f16_kernel(const float* __restrict__ f, int FH, int FW, int FC, int K,
                                            __half* __restrict__ dst, int Kp, int Cp, int flip_transpose) {
   const size_t total = flip_transpose ? size_t(Cp) * FH * FW * Kp : size_t(Kp) * FH * FW * Cp;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
@@ -146,7 +146,7 @@ __global__ void filters_to_krsc_f16_kernel(const float* __restrict__ f, int FH, 
 // that the 7x7/2 stem becomes a 7x1 convolution with 32 input channels for the tcgen05 kernel.
 // Generic in (S, stride_w, pad_l, C<=4).
 // ============================================================================================
-__global__ void rows_im2col_from_hwcn_kernel(const float* __restrict__ src, int H, int W, int C, int N, int S,
+static __global__ void rows_im2col_from_hwcn_kernel(const float* __restrict__ src, int H, int W, int C, int N, int S,
                                              int stride_w, int pad_l, int OW, __half* __restrict__ dst) {
   // one thread per (n, h, ow): writes 32 halves (64 B)
   const size_t total = size_t(N) * H * OW;
@@ -172,7 +172,7 @@ __global__ void rows_im2col_from_hwcn_kernel(const float* __restrict__ src, int 
 // Student input: spectrograms H x W x 1 x N (HWCN fp32) -> space-to-depth tensor
 // Y[n][hp][ow][16] with Y[.., dr*8+s] = x[2*hp + dr - pad_t, 2*ow + s - pad_l]  (dr<2, s<7), so that the
 // 7x7/2 stem becomes a 4x1 stride-1 convolution with 16 input channels (K = 64).
-__global__ void spec_s2d_from_hwcn_kernel(const float* __restrict__ src, int H, int W, int N, int pad_t, int pad_l,
+static __global__ void spec_s2d_from_hwcn_kernel(const float* __restrict__ src, int H, int W, int N, int pad_t, int pad_l,
                                           int HP, int OW, __half* __restrict__ dst) {
   const size_t total = size_t(N) * HP * OW;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
@@ -426,7 +426,7 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, size_t P, int C, double
   }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ acc, size_t P, int C, const float* __restrict__ g,
+static __global__ void bn_finalize_kernel(const double* __restrict__ acc, size_t P, int C, const float* __restrict__ g,
                                    const float* __restrict__ beta, float eps, float* __restrict__ moments,
                                    float* __restrict__ a, float* __restrict__ b) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -443,7 +443,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ acc, size_t P, int
 }
 
 // test mode: moments given (C x 2 = [mu sigma])
-__global__ void bn_affine_from_moments_kernel(const float* __restrict__ moments, int C, const float* __restrict__ g,
+static __global__ void bn_affine_from_moments_kernel(const float* __restrict__ moments, int C, const float* __restrict__ g,
                                               const float* __restrict__ beta, float* __restrict__ a,
                                               float* __restrict__ b) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -553,7 +553,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
   }
 }
 
-__global__ void bn_bwd_params_kernel(const double* __restrict__ acc, int C, float inv_grad_scale,
+static __global__ void bn_bwd_params_kernel(const double* __restrict__ acc, int C, float inv_grad_scale,
                                      float* __restrict__ dg, float* __restrict__ db) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -618,7 +618,7 @@ __global__ void se_squeeze_kernel(const T* __restrict__ u, int HW, int C, float*
 }
 
 // one block (256 threads) per sample.  w1: [Cr][C] fp32, w2: [C][Cr] fp32.
-__global__ void se_gate_kernel(const float* __restrict__ s, int C, int Cr, const float* __restrict__ w1,
+static __global__ void se_gate_kernel(const float* __restrict__ s, int C, int Cr, const float* __restrict__ w1,
                                const float* __restrict__ b1, const float* __restrict__ w2,
                                const float* __restrict__ b2, float* __restrict__ gate) {
   extern __shared__ float sm[];
@@ -695,7 +695,7 @@ __global__ void add_act_kernel(const T* __restrict__ a, const T* __restrict__ b,
 // aggregate ('max' default, or 'mean') the frame logits lgts[start:end, :] over the frames selected for
 // the audio crop.  frame_logits: [sum F_i][ldl] fp32 (row-major per frame), first numPred classes used.
 // ============================================================================================
-__global__ void logit_aggregate_kernel(const float* __restrict__ frame_logits, int ldl, const int* __restrict__ start,
+static __global__ void logit_aggregate_kernel(const float* __restrict__ frame_logits, int ldl, const int* __restrict__ start,
                                        const int* __restrict__ end, int N, int numPred, int use_mean,
                                        float* __restrict__ target /* [N][numPred] */) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -720,7 +720,7 @@ __global__ void logit_aggregate_kernel(const float* __restrict__ frame_logits, i
 // out_scalars: [0]=loss [1]=classerror ; class_stats: [C] correct, [C] count.
 // ============================================================================================
 constexpr int kLossMaxC = 16;
-__global__ void softmaxce_fused_kernel(const __half* __restrict__ x, int ldx, const float* __restrict__ t, int ldt,
+static __global__ void softmaxce_fused_kernel(const __half* __restrict__ x, int ldx, const float* __restrict__ t, int ldt,
                                        const float* __restrict__ w, int N, int C, float T, int logit_targets,
                                        float dzdy, float grad_scale, __half* __restrict__ dx,
                                        float* __restrict__ out_scalars, float* __restrict__ class_stats,
@@ -774,7 +774,7 @@ __global__ void softmaxce_fused_kernel(const __half* __restrict__ x, int ldx, co
 // fused with the refresh of the fp16 KRSC filter copy the tcgen05 kernels read.  `g` may carry the
 // loss scale (inv_grad_scale undoes it).  One launch per parameter tensor (flat fp32 master copy).
 // ============================================================================================
-__global__ void sgd_momentum_kernel(float* __restrict__ w, float* __restrict__ m, const float* __restrict__ g, size_t n,
+static __global__ void sgd_momentum_kernel(float* __restrict__ w, float* __restrict__ m, const float* __restrict__ g, size_t n,
                                     float lr, float momentum, float wd, float inv_batch, float inv_grad_scale,
                                     __half* __restrict__ w16) {
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
@@ -789,17 +789,17 @@ __global__ void sgd_momentum_kernel(float* __restrict__ w, float* __restrict__ m
 
 // BN moments moving average (dagnn.BatchNorm moments param: trainMethod 'average', learningRate 0.1):
 //   moments <- (1 - rate) * moments + rate * batch_moments
-__global__ void moments_average_kernel(float* __restrict__ moments, const float* __restrict__ batch_moments, int n,
+static __global__ void moments_average_kernel(float* __restrict__ moments, const float* __restrict__ batch_moments, int n,
                                        float rate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) moments[i] = (1.f - rate) * moments[i] + rate * batch_moments[i];
 }
 
-__global__ void f32_to_f16_kernel(const float* __restrict__ s, size_t n, __half* __restrict__ d) {
+static __global__ void f32_to_f16_kernel(const float* __restrict__ s, size_t n, __half* __restrict__ d) {
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
     d[i] = __float2half_rn(s[i]);
 }
-__global__ void f16_to_f32_kernel(const __half* __restrict__ s, size_t n, float scale, float* __restrict__ d) {
+static __global__ void f16_to_f32_kernel(const __half* __restrict__ s, size_t n, float scale, float* __restrict__ d) {
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
     d[i] = __half2float(s[i]) * scale;
 }

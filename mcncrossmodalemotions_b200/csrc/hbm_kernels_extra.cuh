@@ -1,0 +1,247 @@
+// hbm_kernels_extra.cuh -- the remaining memory-bound pieces of the hot path: bias gradient, dgrad
+// filter packing, boundary-only element-wise operators (sigmoid, leaky ReLU, softmax, class error,
+// global pooling backward, Axpy), layout conversion of filters / uint8 indices, and the
+// device-hyper-parameter SGD update that CUDA-graph replays need.
+#pragma once
+#include "hbm_kernels.cuh"
+
+namespace xemo {
+
+// ------------------------------------------------------------------------------------------------
+// bias gradient of vl_nnconv: out[c] (+)= scale * sum_p dy[p][c].  dy: [P][ld] of T.
+// grid (ceil(C/32), row_blocks): each block reduces a slab of rows for 32 channels; fp32 atomics
+// combine slabs (out must be zeroed by the caller; the wrapper does it).
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ dy, size_t P, int ld, int C, float scale, float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const size_t rows_per = (P + gridDim.y - 1) / gridDim.y;
+  const size_t r0 = size_t(blockIdx.y) * rows_per;
+  const size_t r1 = r0 + rows_per < P ? r0 + rows_per : P;
+  float acc = 0.f;
+  if (c < C)
+    for (size_t r = r0 + threadIdx.y; r < r1; r += 8) acc += float(dy[r * ld + c]);
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += part[j][threadIdx.x];
+    atomicAdd(out + c, t * scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Data-gradient filter packing.  Source: KRSC fp16 [Kout][R][S][Cin].  For every output parity class
+// (ph, pw) of a stride-(sh, sw) convolution the data gradient is a stride-1 correlation of dY with
+//   G[c][j'][i'][k] = F[k][r0 + sh*(Jh-1-j')][s0 + sw*(Jw-1-i')][c],  r0 = (ph+pt) mod sh, s0 = (pw+pl) mod sw
+// stored class after class (the class tables are recomputed identically on the host).
+struct DgradClass {
+  int r0, s0, Jh, Jw;
+  long long offset;  // element offset of this class inside the packed buffer
+};
+struct DgradPackParams {
+  DgradClass cls[16];
+  int num_classes;
+  int Kout, R, S, Cin, sh, sw;
+};
+static __global__ void dgrad_pack_kernel(const __half* __restrict__ w, DgradPackParams p, __half* __restrict__ dst) {
+  const DgradClass c = p.cls[blockIdx.y];
+  const size_t total = size_t(p.Cin) * c.Jh * c.Jw * p.Kout;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int k = int(i % p.Kout);
+    const int i2 = int((i / p.Kout) % c.Jw);
+    const int j2 = int((i / (size_t(p.Kout) * c.Jw)) % c.Jh);
+    const int ch = int(i / (size_t(p.Kout) * c.Jw * c.Jh));
+    const int r = c.r0 + p.sh * (c.Jh - 1 - j2);
+    const int s = c.s0 + p.sw * (c.Jw - 1 - i2);
+    dst[c.offset + i] = w[((size_t(k) * p.R + r) * p.S + s) * p.Cin + ch];
+  }
+}
+
+// dF [Kp][R][S][Cp] fp32 (device layout) -> FH x FW x FC x K column-major fp32 (MatConvNet)
+static __global__ void krsc_f32_to_filters_kernel(const float* __restrict__ src, int FH, int FW, int FC, int K, int Cp,
+                                           float* __restrict__ dst) {
+  const size_t total = size_t(FH) * FW * FC * K;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int r = int(i % FH);
+    const int s = int((i / FH) % FW);
+    const int c = int((i / (size_t(FH) * FW)) % FC);
+    const int k = int(i / (size_t(FH) * FW * FC));
+    dst[i] = src[((size_t(k) * FH + r) * FW + s) * Cp + c];
+  }
+}
+
+// generic (slow-path, boundary only) NHWC <-> HWCN conversion for uint8 index tensors
+static __global__ void nhwc_to_hwcn_u8_kernel(const uint8_t* __restrict__ src, int H, int W, int C, int N, int Cp,
+                                       uint8_t* __restrict__ dst) {
+  const size_t total = size_t(H) * W * C * N;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int h = int(i % H);
+    const int w = int((i / H) % W);
+    const int c = int((i / (size_t(H) * W)) % C);
+    const int n = int(i / (size_t(H) * W * C));
+    dst[i] = src[((size_t(n) * H + h) * W + w) * Cp + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// boundary element-wise operators on flat fp32 arrays (layout-agnostic)
+static __global__ void relu_f32_kernel(const float* __restrict__ x, const float* __restrict__ dy, size_t n, float leak,
+                                float* __restrict__ out) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const float v = x[i];
+    if (dy) out[i] = dy[i] * (v > 0.f ? 1.f : leak);
+    else out[i] = v > 0.f ? v : leak * v;
+  }
+}
+static __global__ void sigmoid_f32_kernel(const float* __restrict__ x, const float* __restrict__ dy, size_t n,
+                                   float* __restrict__ out) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const float y = 1.f / (1.f + expf(-x[i]));
+    out[i] = dy ? dy[i] * y * (1.f - y) : y;
+  }
+}
+// softmax over the channel dimension of an H x W x C x N column-major array: one thread per (h,w,n)
+static __global__ void softmaxt_hwcn_kernel(const float* __restrict__ x, int HW, int C, int N, float invT,
+                                     float* __restrict__ y) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= size_t(HW) * N) return;
+  const size_t n = i / HW, hw = i % HW;
+  const float* xp = x + n * size_t(C) * HW + hw;
+  float* yp = y + n * size_t(C) * HW + hw;
+  float m = -INFINITY;
+  for (int c = 0; c < C; ++c) m = fmaxf(m, xp[size_t(c) * HW] * invT);
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += expf(xp[size_t(c) * HW] * invT - m);
+  for (int c = 0; c < C; ++c) yp[size_t(c) * HW] = expf(xp[size_t(c) * HW] * invT - m) / s;
+}
+// vl_nnloss 'classerror' on 1 x 1 x C x N logits (column-major == [N][C] row-major); labels 1-based
+static __global__ void classerror_kernel(const float* __restrict__ x, const float* __restrict__ labels, int C, int N,
+                                  float* __restrict__ nerr) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  float e = 0.f;
+  if (n < N) {
+    float m = -INFINITY;
+    int a = 0;
+    for (int c = 0; c < C; ++c) {
+      const float v = x[size_t(n) * C + c];
+      if (v > m) { m = v; a = c; }
+    }
+    e = (a + 1 != int(labels[n])) ? 1.f : 0.f;
+  }
+  e = warp_sum(e);
+  if ((threadIdx.x & 31) == 0 && e != 0.f) atomicAdd(nerr, e);
+}
+// T-softmax CE on fp32 [N][C] logits (boundary variant of softmaxce_fused_kernel: fp32 in / out)
+static __global__ void softmaxce_f32_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                     const float* __restrict__ w, int N, int C, float T, int logit_targets,
+                                     const float* __restrict__ dzdy, float* __restrict__ dx, float* __restrict__ loss) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.f;
+  if (n < N) {
+    float xv[kLossMaxC], tv[kLossMaxC];
+    float xm = -INFINITY, tm = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+      xv[c] = x[size_t(n) * C + c];
+      tv[c] = t[size_t(n) * C + c];
+      xm = fmaxf(xm, xv[c]);
+      tm = fmaxf(tm, tv[c]);
+    }
+    const float invT = 1.f / T;
+    float xs = 0.f, ts = 0.f;
+    for (int c = 0; c < C; ++c) {
+      xv[c] = (xv[c] - xm) * invT;
+      xs += expf(xv[c]);
+      if (logit_targets) { tv[c] = expf((tv[c] - tm) * invT); ts += tv[c]; }
+    }
+    const float lse = logf(xs);
+    const float wn = w ? w[n] : 1.f;
+    const float dz = dzdy ? dzdy[0] : 1.f;
+    for (int c = 0; c < C; ++c) {
+      const float p = logit_targets ? tv[c] / ts : tv[c];
+      const float logq = xv[c] - lse;
+      l -= p * logq;
+      if (dx) dx[size_t(n) * C + c] = dz * wn * (expf(logq) - p) * invT;
+    }
+    l *= wn;
+  }
+  l = warp_sum(l);
+  if (loss && (threadIdx.x & 31) == 0) atomicAdd(loss, l);
+}
+
+// global average pooling backward: dx[h,w,c,n] = dy[c,n] / (H*W)   (HWCN column-major, flat)
+static __global__ void globalpool_bwd_hwcn_kernel(const float* __restrict__ dy, int HW, size_t total, float* __restrict__ dx) {
+  const float inv = 1.f / float(HW);
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x)
+    dx[i] = dy[i / HW] * inv;
+}
+// global average pooling forward on HWCN column-major: one warp per (c,n) plane
+static __global__ void globalpool_fwd_hwcn_kernel(const float* __restrict__ x, int HW, size_t planes, float* __restrict__ y) {
+  const size_t warp = (blockIdx.x * size_t(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= planes) return;
+  float acc = 0.f;
+  for (int i = lane; i < HW; i += 32) acc += x[warp * HW + i];
+  acc = warp_sum(acc);
+  if (lane == 0) y[warp] = acc / float(HW);
+}
+// Axpy on HWCN column-major: out = a[c,n] * x + y
+static __global__ void axpy_hwcn_kernel(const float* __restrict__ a, const float* __restrict__ x, const float* __restrict__ y,
+                                 int HW, size_t total, float* __restrict__ out) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x)
+    out[i] = fmaf(a[i / HW], x[i], y[i]);
+}
+
+static __global__ void fill_strided_f32_kernel(float* __restrict__ dst, int outer, size_t outer_stride, size_t inner_off,
+                                        int inner, float value) {
+  const size_t total = size_t(outer) * inner;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x)
+    dst[(i / inner) * outer_stride + inner_off + (i % inner)] = value;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cnn_train_dag update with the hyper-parameters in device memory (hyper = {lr, momentum, wd, 1/B}),
+// so that a captured CUDA graph follows the learning-rate schedule without re-capture.
+static __global__ void sgd_momentum_dev_kernel(float* __restrict__ w, float* __restrict__ m, const float* __restrict__ g,
+                                        size_t n, const float* __restrict__ hyper, float lr_mult, float wd_mult,
+                                        float inv_grad_scale, __half* __restrict__ w16) {
+  const float lr = hyper[0] * lr_mult, momentum = hyper[1], wd = hyper[2] * wd_mult, inv_batch = hyper[3];
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const float wi = w[i];
+    const float mi = momentum * m[i] - (wd * wi + g[i] * inv_grad_scale * inv_batch);
+    const float wn = wi + lr * mi;
+    m[i] = mi;
+    w[i] = wn;
+    if (w16) w16[i] = __float2half_rn(wn);
+  }
+}
+
+// test-mode BN backward: dx = a * dz, dz = dy * [a*x+b > 0] when relu_mask
+template <typename T>
+__global__ void bn_bwd_test_kernel(const T* __restrict__ x, const T* __restrict__ dy, size_t P, int C,
+                                   const float* __restrict__ a, const float* __restrict__ b, int relu_mask,
+                                   T* __restrict__ dx) {
+  const int C8 = C >> 3;
+  const size_t total = P * C8;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int c8 = int(i % C8);
+    Vec8<T> vx, vd;
+    vx.load(x + i * 8);
+    vd.load(dy + i * 8);
+    float fx[8], fd[8];
+    vx.to_float(fx);
+    vd.to_float(fd);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float av = a[c8 * 8 + k], bv = b[c8 * 8 + k];
+      float dz = fd[k];
+      if (relu_mask && !(fmaf(av, fx[k], bv) > 0.f)) dz = 0.f;
+      fd[k] = av * dz;
+    }
+    vd.from_float(fd);
+    vd.store(dx + i * 8);
+  }
+}
+
+}  // namespace xemo

@@ -1,0 +1,563 @@
+// xemo_ops.cu -- context management, CUDA-graph capture and the device-native building blocks
+// (xemo_op_*) of libxemo.so.  See include/xemo.h for the contract of every entry point.
+#include "xemo_internal.h"
+
+#include "conv_launch.cuh"
+#include "hbm_kernels_extra.cuh"
+
+using namespace xemo;
+
+// ================================================================================================
+// context
+extern "C" int xemo_version(void) { return 100; }
+
+extern "C" int xemo_create(int device, void* cuda_stream, xemo_ctx** out) {
+  if (!out) return XEMO_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return XEMO_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return XEMO_ERR_NO_DEVICE;
+  if (prop.major != 10) return XEMO_ERR_NO_DEVICE;  // sm_100a only: there is no fallback path
+  if (cudaSetDevice(device) != cudaSuccess) return XEMO_ERR_CUDA;
+  if (!tma_api().ok) return XEMO_ERR_NO_DEVICE;
+  xemo_ctx* ctx = new xemo_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cuda_stream) {
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  } else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete ctx;
+      return XEMO_ERR_CUDA;
+    }
+    ctx->own_stream = true;
+  }
+  *out = ctx;
+  return XEMO_OK;
+}
+
+extern "C" void xemo_destroy(xemo_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* xemo_last_error(xemo_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int xemo_sync(xemo_ctx* ctx) {
+  XEMO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return XEMO_OK;
+}
+extern "C" int xemo_num_sms(xemo_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+extern "C" uint64_t xemo_launch_count(xemo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int xemo_h2d(xemo_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  XEMO_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return XEMO_OK;
+}
+extern "C" int xemo_d2h(xemo_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  XEMO_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return XEMO_OK;
+}
+extern "C" int xemo_memset(xemo_ctx* ctx, void* dst, int byte, size_t bytes) {
+  XEMO_CUDA(ctx, cudaMemsetAsync(dst, byte, bytes, ctx->stream));
+  return XEMO_OK;
+}
+
+// ================================================================================================
+// CUDA-graph capture
+extern "C" int xemo_capture_begin(xemo_ctx* ctx) {
+  XEMO_REQUIRE(ctx, !ctx->capturing, "capture already in progress");
+  XEMO_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  ctx->capturing = true;
+  ctx->capture_mark = ctx->launches;
+  return XEMO_OK;
+}
+
+extern "C" int xemo_capture_end(xemo_ctx* ctx, xemo_graph** out) {
+  XEMO_REQUIRE(ctx, ctx->capturing && out, "no capture in progress");
+  ctx->capturing = false;
+  cudaGraph_t graph = nullptr;
+  XEMO_CUDA(ctx, cudaStreamEndCapture(ctx->stream, &graph));
+  xemo_graph* g = new xemo_graph();
+  g->graph = graph;
+  g->num_kernels = int(ctx->launches - ctx->capture_mark);
+  ctx->launches = ctx->capture_mark;  // captured launches did not execute
+  cudaError_t e = cudaGraphInstantiate(&g->exec, graph, 0);
+  if (e != cudaSuccess) {
+    cudaGraphDestroy(graph);
+    delete g;
+    return fail(ctx, XEMO_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+  }
+  *out = g;
+  return XEMO_OK;
+}
+
+extern "C" int xemo_graph_launch(xemo_ctx* ctx, xemo_graph* g) {
+  XEMO_REQUIRE(ctx, g && g->exec, "null graph");
+  XEMO_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+  ctx->launches += uint64_t(g->num_kernels);
+  return XEMO_OK;
+}
+extern "C" int xemo_graph_num_kernels(xemo_graph* g) { return g ? g->num_kernels : 0; }
+extern "C" void xemo_graph_destroy(xemo_graph* g) {
+  if (!g) return;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+}
+
+// ================================================================================================
+// layout conversion
+extern "C" int xemo_op_hwcn_to_nhwc(xemo_ctx* ctx, const float* src, int H, int W, int C, int N, void* dst, int Cp,
+                                    int dst_f32) {
+  XEMO_REQUIRE(ctx, src && dst && Cp >= C && H > 0 && W > 0 && W <= 65535 && C > 0 && N > 0, "hwcn_to_nhwc: bad arguments");
+  dim3 block(32, 8), grid((H + 31) / 32, (Cp + 31) / 32, 1);
+  const int per = 65535 / W;  // gridDim.z <= 65535: whole images per launch
+  for (int n0 = 0; n0 < N; n0 += per) {
+    const int nn = N - n0 < per ? N - n0 : per;
+    grid.z = unsigned(nn) * W;
+    const float* s = src + size_t(n0) * H * W * C;
+    if (dst_f32)
+      hwcn_f32_to_nhwc_kernel<float><<<grid, block, 0, ctx->stream>>>(s, H, W, C, nn,
+                                                                    static_cast<float*>(dst) + size_t(n0) * H * W * Cp, Cp);
+    else
+      hwcn_f32_to_nhwc_kernel<__half><<<grid, block, 0, ctx->stream>>>(s, H, W, C, nn,
+                                                                     static_cast<__half*>(dst) + size_t(n0) * H * W * Cp, Cp);
+    XEMO_LAUNCHED(ctx, 1);
+  }
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_nhwc_to_hwcn(xemo_ctx* ctx, const void* src, int src_f32, int H, int W, int C, int N, int Cp,
+                                    float* dst) {
+  XEMO_REQUIRE(ctx, src && dst && Cp >= C && H > 0 && W > 0 && W <= 65535 && C > 0 && N > 0, "nhwc_to_hwcn: bad arguments");
+  dim3 block(32, 8), grid((H + 31) / 32, (C + 31) / 32, 1);
+  const int per = 65535 / W;
+  for (int n0 = 0; n0 < N; n0 += per) {
+    const int nn = N - n0 < per ? N - n0 : per;
+    grid.z = unsigned(nn) * W;
+    float* d = dst + size_t(n0) * H * W * C;
+    if (src_f32)
+      nhwc_to_hwcn_f32_kernel<float><<<grid, block, 0, ctx->stream>>>(static_cast<const float*>(src) + size_t(n0) * H * W * Cp, H,
+                                                                    W, C, nn, Cp, d);
+    else
+      nhwc_to_hwcn_f32_kernel<__half><<<grid, block, 0, ctx->stream>>>(static_cast<const __half*>(src) + size_t(n0) * H * W * Cp,
+                                                                     H, W, C, nn, Cp, d);
+    XEMO_LAUNCHED(ctx, 1);
+  }
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_filters_to_krsc(xemo_ctx* ctx, const float* f, int FH, int FW, int FC, int K, void* dst16, int Kp,
+                                       int Cp, int flip_transpose) {
+  XEMO_REQUIRE(ctx, f && dst16 && Kp >= K && Cp >= FC, "filters_to_krsc: bad arguments");
+  const size_t total = size_t(Kp) * FH * FW * Cp;
+  filters_to_krsc_f16_kernel<<<grid_for(total, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+      f, FH, FW, FC, K, static_cast<__half*>(dst16), Kp, Cp, flip_transpose);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_face_rows_im2col(xemo_ctx* ctx, const float* faces, int H, int W, int C, int N, int S, int stride_w,
+                                        int pad_l, int OW, void* dst16) {
+  XEMO_REQUIRE(ctx, faces && dst16 && C <= 4 && S * 4 <= 32, "face_rows_im2col: needs C <= 4 and S <= 8");
+  const size_t total = size_t(N) * H * OW;
+  rows_im2col_from_hwcn_kernel<<<grid_for(total, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
+      faces, H, W, C, N, S, stride_w, pad_l, OW, static_cast<__half*>(dst16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_spec_s2d(xemo_ctx* ctx, const float* spec, int H, int W, int N, int pad_t, int pad_l, int HP, int OW,
+                                void* dst16) {
+  XEMO_REQUIRE(ctx, spec && dst16, "spec_s2d: null pointer");
+  const size_t total = size_t(N) * HP * OW;
+  spec_s2d_from_hwcn_kernel<<<grid_for(total, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
+      spec, H, W, N, pad_t, pad_l, HP, OW, static_cast<__half*>(dst16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+// ================================================================================================
+// convolution
+static int run_fprop(xemo_ctx* ctx, const ConvGeom& g, const __half* x, const __half* w, const ConvEpilogue& e) {
+  ConvPlan plan;
+  if (!conv_fprop_plan(&plan, g, x, w, e, ctx->num_sms))
+    return fail(ctx, XEMO_ERR_INVALID,
+                "conv: unsupported geometry N=%d H=%d W=%d Cin=%d Kout=%d R=%d S=%d stride=%d,%d pad=%d,%d,%d,%d", g.N, g.H,
+                g.W, g.Cin, g.Kout, g.R, g.S, g.sh, g.sw, g.pt, g.pb, g.pl, g.pr);
+  cudaError_t err = conv_fprop_run(plan, ctx->stream);
+  if (err != cudaSuccess) return fail(ctx, XEMO_ERR_CUDA, "conv_fprop launch failed: %s", cudaGetErrorString(err));
+  ctx->launches += 1;
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_conv_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int Cin, const void* w16, int Kout, int R,
+                                int S, int sh, int sw, int pt, int pb, int pl, int pr, const float* scale, const float* shift,
+                                const void* residual16, int relu, void* out16, float* out32, int ldc) {
+  XEMO_REQUIRE(ctx, x16 && w16 && (out16 || out32), "conv_fwd: null pointer");
+  XEMO_REQUIRE(ctx, Cin % 16 == 0 && Kout % 16 == 0, "conv_fwd: Cin=%d and Kout=%d must be multiples of 16", Cin, Kout);
+  XEMO_REQUIRE(ctx, pl <= 127 && pt <= 127 && R <= 256 && S <= 256, "conv_fwd: pad / filter out of TMA range");
+  ConvGeom g{N, H, W, Cin, Kout, R, S, sh, sw, pt, pb, pl, pr};
+  XEMO_REQUIRE(ctx, g.OH() > 0 && g.OW() > 0, "conv_fwd: empty output");
+  ConvEpilogue e;
+  e.scale = scale; e.shift = shift; e.residual = static_cast<const __half*>(residual16); e.relu = relu;
+  e.out = static_cast<__half*>(out16); e.out_f32 = out32; e.ldc = ldc ? ldc : Kout;
+  XEMO_REQUIRE(ctx, e.ldc >= Kout && e.ldc % 8 == 0, "conv_fwd: ldc=%d must be >= Kout and a multiple of 8", e.ldc);
+  return run_fprop(ctx, g, static_cast<const __half*>(x16), static_cast<const __half*>(w16), e);
+}
+
+// parity classes of the data gradient (see hbm_kernels_extra.cuh)
+static int dgrad_classes(int Cin, int Kout, int R, int S, int sh, int sw, int pt, int pl, DgradPackParams* p) {
+  p->num_classes = 0;
+  p->Kout = Kout; p->R = R; p->S = S; p->Cin = Cin; p->sh = sh; p->sw = sw;
+  long long off = 0;
+  if (sh * sw > 16) return -1;
+  for (int ph = 0; ph < sh; ++ph)
+    for (int pw = 0; pw < sw; ++pw) {
+      DgradClass& c = p->cls[p->num_classes++];
+      c.r0 = (ph + pt) % sh;
+      c.s0 = (pw + pl) % sw;
+      c.Jh = c.r0 < R ? (R - c.r0 + sh - 1) / sh : 0;
+      c.Jw = c.s0 < S ? (S - c.s0 + sw - 1) / sw : 0;
+      c.offset = off;
+      off += (long long)Cin * c.Jh * c.Jw * Kout;
+    }
+  return 0;
+}
+
+extern "C" size_t xemo_dgrad_pack_elems(int Cin, int Kout, int R, int S, int sh, int sw) {
+  (void)sh; (void)sw;
+  return size_t(Cin) * R * S * Kout;  // every filter tap belongs to exactly one parity class
+}
+
+extern "C" int xemo_op_pack_dgrad_filters(xemo_ctx* ctx, const void* w16_krsc, int Kout, int R, int S, int Cin, int sh,
+                                          int sw, int pt, int pl, void* packed16) {
+  XEMO_REQUIRE(ctx, w16_krsc && packed16, "pack_dgrad_filters: null pointer");
+  DgradPackParams p;
+  XEMO_REQUIRE(ctx, dgrad_classes(Cin, Kout, R, S, sh, sw, pt, pl, &p) == 0, "pack_dgrad_filters: stride too large");
+  dim3 grid(grid_for(size_t(Cin) * R * S * Kout / p.num_classes + 1, 256, ctx->num_sms), p.num_classes);
+  dgrad_pack_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const __half*>(w16_krsc), p, static_cast<__half*>(packed16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+// shared by xemo_op_conv_dgrad (fp16 out) and the vl_nnconv boundary (fp32 out)
+int xemo_conv_dgrad_impl(xemo_ctx* ctx, const void* dy16, int N, int H, int W, int Cin, const void* packed16, int Kout, int R,
+                         int S, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16, float* dx32) {
+  XEMO_REQUIRE(ctx, dy16 && packed16 && (dx16 || dx32), "conv_dgrad: null pointer");
+  XEMO_REQUIRE(ctx, Cin % 16 == 0 && Kout % 16 == 0, "conv_dgrad: Cin=%d and Kout=%d must be multiples of 16", Cin, Kout);
+  const int OH = (H + pt + pb - R) / sh + 1, OW = (W + pl + pr - S) / sw + 1;
+  XEMO_REQUIRE(ctx, OH > 0 && OW > 0, "conv_dgrad: empty output");
+  DgradPackParams p;
+  XEMO_REQUIRE(ctx, dgrad_classes(Cin, Kout, R, S, sh, sw, pt, pl, &p) == 0, "conv_dgrad: stride too large");
+  bool any_empty = false;
+  for (int i = 0; i < p.num_classes; ++i) any_empty |= (p.cls[i].Jh == 0 || p.cls[i].Jw == 0);
+  // rows / columns of x that no output window reaches keep a zero gradient only through taps that
+  // fall outside dY, which the TMA zero-fills -- but classes without any tap are never written
+  if (any_empty) {
+    if (dx16) XEMO_CUDA(ctx, cudaMemsetAsync(dx16, 0, size_t(N) * H * W * Cin * 2, ctx->stream));
+    if (dx32) XEMO_CUDA(ctx, cudaMemsetAsync(dx32, 0, size_t(N) * H * W * Cin * 4, ctx->stream));
+  }
+  int ci = 0;
+  for (int ph = 0; ph < sh; ++ph)
+    for (int pw = 0; pw < sw; ++pw, ++ci) {
+      const DgradClass& c = p.cls[ci];
+      if (c.Jh == 0 || c.Jw == 0) continue;
+      const int sub_h = (H - ph + sh - 1) / sh, sub_w = (W - pw + sw - 1) / sw;
+      if (sub_h <= 0 || sub_w <= 0) continue;
+      const int qh = (ph + pt) / sh, qw = (pw + pl) / sw;
+      const int pad_t = c.Jh - 1 - qh, pad_l = c.Jw - 1 - qw;
+      XEMO_REQUIRE(ctx, pad_t >= 0 && pad_l >= 0, "conv_dgrad: padding larger than the filter is not supported");
+      ConvGeom g{N, OH, OW, Kout, Cin, c.Jh, c.Jw, 1, 1, pad_t, 0, pad_l, 0};
+      g.oh_override = sub_h;
+      g.ow_override = sub_w;
+      ConvEpilogue e;
+      const size_t base = (size_t(ph) * W + pw) * Cin;
+      if (sh == 1 && sw == 1) {
+        e.out = static_cast<__half*>(dx16);
+        e.out_f32 = dx32;
+        e.ldc = Cin;
+      } else {
+        e.out = dx16 ? static_cast<__half*>(dx16) + base : nullptr;
+        e.out_f32 = dx32 ? dx32 + base : nullptr;
+        e.strided_out = 1;
+        e.out_sn = (long long)H * W * Cin;
+        e.out_sh = (long long)sh * W * Cin;
+        e.out_sw = (long long)sw * Cin;
+        e.ldc = Cin;
+      }
+      int rc = run_fprop(ctx, g, static_cast<const __half*>(dy16), static_cast<const __half*>(packed16) + c.offset, e);
+      if (rc) return rc;
+    }
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_conv_dgrad(xemo_ctx* ctx, const void* dy16, int N, int H, int W, int Cin, const void* packed16,
+                                  int Kout, int R, int S, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16) {
+  return xemo_conv_dgrad_impl(ctx, dy16, N, H, W, Cin, packed16, Kout, R, S, sh, sw, pt, pb, pl, pr, dx16, nullptr);
+}
+
+extern "C" int xemo_op_conv_wgrad(xemo_ctx* ctx, const void* x16, int N, int H, int W, int Cin, const void* dy16, int ldy,
+                                  int Kout, int R, int S, int sh, int sw, int pt, int pb, int pl, int pr, float* dF,
+                                  float scale) {
+  XEMO_REQUIRE(ctx, x16 && dy16 && dF, "conv_wgrad: null pointer");
+  ConvGeom g{N, H, W, Cin, Kout, R, S, sh, sw, pt, pb, pl, pr};
+  WgradPlan plan;
+  if (!conv_wgrad_plan(&plan, g, static_cast<const __half*>(x16), static_cast<const __half*>(dy16), ldy, dF, scale,
+                       ctx->num_sms))
+    return fail(ctx, XEMO_ERR_INVALID, "conv_wgrad: unsupported geometry Cin=%d Kout=%d ldy=%d R=%d S=%d", Cin, Kout, ldy, R, S);
+  cudaError_t err = conv_wgrad_run(plan, ctx->stream);
+  if (err != cudaSuccess) return fail(ctx, XEMO_ERR_CUDA, "conv_wgrad launch failed: %s", cudaGetErrorString(err));
+  ctx->launches += 1;
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_colsum(xemo_ctx* ctx, const void* dy16, size_t P, int ld, int C, float scale, float* out) {
+  XEMO_REQUIRE(ctx, dy16 && out && C <= ld, "colsum: bad arguments");
+  XEMO_CUDA(ctx, cudaMemsetAsync(out, 0, size_t(C) * 4, ctx->stream));
+  int row_blocks = int((P + 511) / 512);
+  const int cap = ctx->num_sms * 4;
+  if (row_blocks > cap) row_blocks = cap;
+  if (row_blocks < 1) row_blocks = 1;
+  dim3 grid((C + 31) / 32, row_blocks), block(32, 8);
+  colsum_kernel<__half><<<grid, block, 0, ctx->stream>>>(static_cast<const __half*>(dy16), P, ld, C, scale, out);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+// ================================================================================================
+// pooling
+static bool pool_geom(PoolGeom* g, int N, int H, int W, int C, int PH, int PW, int sh, int sw, int pt, int pb, int pl, int pr) {
+  g->N = N; g->H = H; g->W = W; g->C = C; g->PH = PH; g->PW = PW; g->sh = sh; g->sw = sw; g->pt = pt; g->pl = pl;
+  g->OH = (H + pt + pb - PH) / sh + 1;
+  g->OW = (W + pl + pr - PW) / sw + 1;
+  return g->OH > 0 && g->OW > 0 && C % 8 == 0 && PH * PW <= 255;
+}
+
+extern "C" int xemo_op_maxpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
+                                   int pt, int pb, int pl, int pr, const float* a, const float* b, void* y16,
+                                   uint8_t* argmax) {
+  PoolGeom g;
+  XEMO_REQUIRE(ctx, x16 && y16 && pool_geom(&g, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr), "maxpool_fwd: bad geometry");
+  const size_t total = size_t(N) * g.OH * g.OW * (C / 8);
+  const int grid = grid_for(total, 256, ctx->num_sms, 16);
+  if (a)
+    maxpool_fwd_kernel<__half, true><<<grid, 256, 0, ctx->stream>>>(static_cast<const __half*>(x16), g, a, b,
+                                                                  static_cast<__half*>(y16), argmax);
+  else
+    maxpool_fwd_kernel<__half, false><<<grid, 256, 0, ctx->stream>>>(static_cast<const __half*>(x16), g, nullptr, nullptr,
+                                                                   static_cast<__half*>(y16), argmax);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_maxpool_bwd(xemo_ctx* ctx, const void* dy16, const uint8_t* argmax, int N, int H, int W, int C, int PH,
+                                   int PW, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16) {
+  PoolGeom g;
+  XEMO_REQUIRE(ctx, dy16 && argmax && dx16 && pool_geom(&g, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr),
+               "maxpool_bwd: bad geometry");
+  const size_t total = size_t(N) * H * W * (C / 8);
+  maxpool_bwd_kernel<__half><<<grid_for(total, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
+      static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_avgpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
+                                   int pt, int pb, int pl, int pr, void* y16) {
+  PoolGeom g;
+  XEMO_REQUIRE(ctx, x16 && y16 && pool_geom(&g, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr), "avgpool_fwd: bad geometry");
+  const size_t total = size_t(N) * g.OH * g.OW * (C / 8);
+  avgpool_fwd_kernel<__half><<<grid_for(total, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
+      static_cast<const __half*>(x16), g, static_cast<__half*>(y16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_avgpool_bwd(xemo_ctx* ctx, const void* dy16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
+                                   int pt, int pb, int pl, int pr, void* dx16) {
+  PoolGeom g;
+  XEMO_REQUIRE(ctx, dy16 && dx16 && pool_geom(&g, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr), "avgpool_bwd: bad geometry");
+  const size_t total = size_t(N) * H * W * (C / 8);
+  avgpool_bwd_kernel<__half><<<grid_for(total, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
+      static_cast<const __half*>(dy16), g, static_cast<__half*>(dx16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+// ================================================================================================
+// batch normalisation
+template <typename T>
+int bn_stats_launch(xemo_ctx* ctx, const T* x, size_t P, int C, double* ws) {
+  XEMO_CUDA(ctx, cudaMemsetAsync(ws, 0, size_t(2) * C * sizeof(double), ctx->stream));
+  const int C8 = C / 8;
+  const int lanes = C8 < 256 ? C8 : 256;
+  dim3 grid(unsigned((P + kBnRowsPerBlock - 1) / kBnRowsPerBlock), unsigned((C8 + lanes - 1) / lanes));
+  bn_stats_kernel<T><<<grid, 256, 0, ctx->stream>>>(x, P, C, ws);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+template int bn_stats_launch<float>(xemo_ctx*, const float*, size_t, int, double*);
+
+extern "C" int xemo_op_bn_train(xemo_ctx* ctx, const void* x16, size_t P, int C, const float* g, const float* beta, float eps,
+                                double* ws, float* moments, float* a, float* b) {
+  XEMO_REQUIRE(ctx, x16 && g && beta && ws && moments && a && b && C % 8 == 0 && P > 0, "bn_train: bad arguments");
+  int rc = bn_stats_launch<__half>(ctx, static_cast<const __half*>(x16), P, C, ws);
+  if (rc) return rc;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ctx->stream>>>(ws, P, C, g, beta, eps, moments, a, b);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_bn_test(xemo_ctx* ctx, const float* moments, int C, const float* g, const float* beta, float* a,
+                               float* b) {
+  XEMO_REQUIRE(ctx, moments && g && beta && a && b, "bn_test: null pointer");
+  bn_affine_from_moments_kernel<<<(C + 127) / 128, 128, 0, ctx->stream>>>(moments, C, g, beta, a, b);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_affine_act(xemo_ctx* ctx, const void* x16, size_t P, int C, const float* a, const float* b, int relu,
+                                  void* y16) {
+  XEMO_REQUIRE(ctx, x16 && y16 && C % 8 == 0, "affine_act: bad arguments");
+  affine_act_kernel<__half><<<grid_for(P * (C / 8), 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
+      static_cast<const __half*>(x16), P, C, a, b, relu, static_cast<__half*>(y16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_bn_bwd(xemo_ctx* ctx, const void* x16, const void* dy16, size_t P, int C, const float* moments,
+                              const float* a, const float* b, int relu_mask, int test_mode, double* ws, void* dx16,
+                              float* dg, float* db, float inv_grad_scale) {
+  XEMO_REQUIRE(ctx, x16 && dy16 && moments && a && b && ws && dx16 && C % 8 == 0, "bn_bwd: bad arguments");
+  const __half* x = static_cast<const __half*>(x16);
+  const __half* dy = static_cast<const __half*>(dy16);
+  XEMO_CUDA(ctx, cudaMemsetAsync(ws, 0, size_t(2) * C * sizeof(double), ctx->stream));
+  const int C8 = C / 8;
+  const int lanes = C8 < 256 ? C8 : 256;
+  dim3 grid(unsigned((P + kBnRowsPerBlock - 1) / kBnRowsPerBlock), unsigned((C8 + lanes - 1) / lanes));
+  bn_bwd_reduce_kernel<__half><<<grid, 256, 0, ctx->stream>>>(x, dy, P, C, moments, a, b, relu_mask, ws);
+  XEMO_LAUNCHED(ctx, 1);
+  const int egrid = grid_for(P * C8, 256, ctx->num_sms, 16);
+  if (test_mode)
+    bn_bwd_test_kernel<__half><<<egrid, 256, 0, ctx->stream>>>(x, dy, P, C, a, b, relu_mask, static_cast<__half*>(dx16));
+  else
+    bn_bwd_apply_kernel<__half><<<egrid, 256, 0, ctx->stream>>>(x, dy, P, C, moments, a, b, relu_mask, ws,
+                                                              static_cast<__half*>(dx16));
+  XEMO_LAUNCHED(ctx, 1);
+  if (dg && db) {
+    bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, ctx->stream>>>(ws, C, inv_grad_scale, dg, db);
+    XEMO_LAUNCHED(ctx, 1);
+  }
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_relu_bwd(xemo_ctx* ctx, const void* y16, const void* dy16, size_t n, void* dx16) {
+  XEMO_REQUIRE(ctx, y16 && dy16 && dx16 && n % 8 == 0, "relu_bwd: bad arguments");
+  relu_bwd_kernel<__half><<<grid_for(n / 8, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
+      static_cast<const __half*>(y16), static_cast<const __half*>(dy16), n / 8, static_cast<__half*>(dx16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_add_act(xemo_ctx* ctx, const void* a16, const void* b16, size_t n, int relu, void* y16) {
+  XEMO_REQUIRE(ctx, a16 && b16 && y16 && n % 8 == 0, "add_act: bad arguments");
+  add_act_kernel<__half><<<grid_for(n / 8, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
+      static_cast<const __half*>(a16), static_cast<const __half*>(b16), n / 8, relu, static_cast<__half*>(y16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+// ================================================================================================
+// squeeze-and-excitation
+extern "C" int xemo_op_se_squeeze(xemo_ctx* ctx, const void* u16, int N, int HW, int C, float* s) {
+  XEMO_REQUIRE(ctx, u16 && s && C % 8 == 0, "se_squeeze: bad arguments");
+  dim3 grid((C / 8 + 31) / 32, N), block(32, 8);
+  se_squeeze_kernel<__half><<<grid, block, 0, ctx->stream>>>(static_cast<const __half*>(u16), HW, C, s);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_se_gate(xemo_ctx* ctx, const float* s, int N, int C, int Cr, const float* w1, const float* b1,
+                               const float* w2, const float* b2, float* gate) {
+  XEMO_REQUIRE(ctx, s && w1 && w2 && gate && (C + Cr) * 4 <= 48 * 1024, "se_gate: bad arguments");
+  se_gate_kernel<<<N, 256, size_t(C + Cr) * 4, ctx->stream>>>(s, C, Cr, w1, b1, w2, b2, gate);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_se_excite(xemo_ctx* ctx, const void* u16, const float* gate, const void* shortcut16, int N, int HW,
+                                 int C, int relu, void* y16) {
+  XEMO_REQUIRE(ctx, u16 && gate && y16 && C % 8 == 0, "se_excite: bad arguments");
+  const size_t total8 = size_t(N) * HW * (C / 8);
+  se_excite_kernel<__half><<<grid_for(total8, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
+      static_cast<const __half*>(u16), gate, static_cast<const __half*>(shortcut16), HW, C, total8, relu,
+      static_cast<__half*>(y16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+// ================================================================================================
+// coupling, loss, update
+extern "C" int xemo_op_logit_aggregate(xemo_ctx* ctx, const float* frame_logits, int ldl, const int* start, const int* end,
+                                       int N, int num_pred, int use_mean, float* target) {
+  XEMO_REQUIRE(ctx, frame_logits && start && end && target && num_pred <= ldl, "logit_aggregate: bad arguments");
+  logit_aggregate_kernel<<<(N * num_pred + 127) / 128, 128, 0, ctx->stream>>>(frame_logits, ldl, start, end, N, num_pred,
+                                                                             use_mean, target);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_softmaxce(xemo_ctx* ctx, const void* x16, int ldx, const float* t, int ldt, const float* w, int N, int C,
+                                 float T, int logit_targets, float dzdy, float grad_scale, void* dx16, float* scalars,
+                                 float* class_stats, int* max_label) {
+  XEMO_REQUIRE(ctx, x16 && t && scalars && C <= kLossMaxC && C <= ldx && C <= ldt && T > 0.f, "softmaxce: bad arguments");
+  softmaxce_fused_kernel<<<(N + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const __half*>(x16), ldx, t, ldt, w, N, C, T,
+                                                                  logit_targets, dzdy, grad_scale,
+                                                                  static_cast<__half*>(dx16), scalars, class_stats,
+                                                                  max_label);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_sgd_momentum(xemo_ctx* ctx, float* w, float* m, const float* g, size_t n, const float* hyper,
+                                    float lr_mult, float wd_mult, float inv_grad_scale, void* w16) {
+  XEMO_REQUIRE(ctx, w && m && g && hyper, "sgd_momentum: null pointer");
+  sgd_momentum_dev_kernel<<<grid_for(n, 256, ctx->num_sms, 8), 256, 0, ctx->stream>>>(w, m, g, n, hyper, lr_mult, wd_mult,
+                                                                                     inv_grad_scale,
+                                                                                     static_cast<__half*>(w16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_moments_average(xemo_ctx* ctx, float* moments, const float* batch_moments, int n, float rate) {
+  XEMO_REQUIRE(ctx, moments && batch_moments, "moments_average: null pointer");
+  moments_average_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(moments, batch_moments, n, rate);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_cast_f32_f16(xemo_ctx* ctx, const float* src, size_t n, void* dst16) {
+  XEMO_REQUIRE(ctx, src && dst16, "cast: null pointer");
+  f32_to_f16_kernel<<<grid_for(n, 256, ctx->num_sms, 8), 256, 0, ctx->stream>>>(src, n, static_cast<__half*>(dst16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+extern "C" int xemo_op_cast_f16_f32(xemo_ctx* ctx, const void* src16, size_t n, float scale, float* dst) {
+  XEMO_REQUIRE(ctx, src16 && dst, "cast: null pointer");
+  f16_to_f32_kernel<<<grid_for(n, 256, ctx->num_sms, 8), 256, 0, ctx->stream>>>(static_cast<const __half*>(src16), n, scale,
+                                                                               dst);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+extern "C" int xemo_op_fill_strided_f32(xemo_ctx* ctx, float* dst, int outer, size_t outer_stride, size_t inner_off, int inner,
+                                        float value) {
+  XEMO_REQUIRE(ctx, dst && outer > 0 && inner > 0, "fill_strided: bad arguments");
+  fill_strided_f32_kernel<<<grid_for(size_t(outer) * inner, 256, ctx->num_sms, 4), 256, 0, ctx->stream>>>(
+      dst, outer, outer_stride, inner_off, inner, value);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
