@@ -1,0 +1,177 @@
+"""ctypes binding of libxemo.so (include/xemo.h).  No torch types cross this boundary: plain
+pointers and sizes only.  There is no CPU fallback -- if the library or an sm_100 device is
+missing, importing the binding or creating a context fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libxemo.so")
+
+c_int, c_float, c_size_t, c_void_p, c_int64, c_uint64 = C.c_int, C.c_float, C.c_size_t, C.c_void_p, C.c_int64, C.c_uint64
+P = C.POINTER
+
+
+class XemoArray(C.Structure):
+    """xemo_array: single-precision H x W x C x N column-major (MATLAB) array."""
+
+    _fields_ = [("data", c_void_p), ("h", c_int64), ("w", c_int64), ("c", c_int64), ("n", c_int64)]
+
+
+class XemoError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("xemo error %d: %s" % (code, msg))
+        self.code = code
+
+
+I4 = c_int * 4
+I2 = c_int * 2
+_AP = P(XemoArray)
+
+# name -> (restype, argtypes); every symbol declared in include/xemo.h
+SIGNATURES = {
+    "xemo_version": (c_int, []),
+    "xemo_create": (c_int, [c_int, c_void_p, P(c_void_p)]),
+    "xemo_destroy": (None, [c_void_p]),
+    "xemo_last_error": (C.c_char_p, [c_void_p]),
+    "xemo_sync": (c_int, [c_void_p]),
+    "xemo_num_sms": (c_int, [c_void_p]),
+    "xemo_launch_count": (c_uint64, [c_void_p]),
+    "xemo_h2d": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    "xemo_d2h": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    "xemo_memset": (c_int, [c_void_p, c_void_p, c_int, c_size_t]),
+    "xemo_capture_begin": (c_int, [c_void_p]),
+    "xemo_capture_end": (c_int, [c_void_p, P(c_void_p)]),
+    "xemo_graph_launch": (c_int, [c_void_p, c_void_p]),
+    "xemo_graph_num_kernels": (c_int, [c_void_p]),
+    "xemo_graph_destroy": (None, [c_void_p]),
+    "xemo_out_size": (c_int, [c_int64, c_int64, c_int, c_int, P(c_int), P(c_int), P(c_int64), P(c_int64)]),
+    "xemo_vl_nnconv": (c_int, [c_void_p, _AP, _AP, _AP, _AP, P(c_int), P(c_int), _AP, _AP, _AP, _AP]),
+    "xemo_vl_nnpool": (c_int, [c_void_p, _AP, P(c_int), _AP, P(c_int), P(c_int), c_int, _AP, c_void_p]),
+    "xemo_vl_nnbnorm": (c_int, [c_void_p, _AP, c_void_p, c_void_p, _AP, c_float, c_void_p, _AP, c_void_p, c_void_p, c_void_p]),
+    "xemo_vl_nnrelu": (c_int, [c_void_p, _AP, _AP, c_float, _AP]),
+    "xemo_vl_nnsigmoid": (c_int, [c_void_p, _AP, _AP, _AP]),
+    "xemo_vl_nnsoftmaxt": (c_int, [c_void_p, _AP, c_float, _AP]),
+    "xemo_vl_nnsoftmaxceloss": (c_int, [c_void_p, _AP, _AP, c_void_p, c_float, c_int, c_void_p, c_void_p, _AP]),
+    "xemo_vl_nnloss_classerror": (c_int, [c_void_p, _AP, c_void_p, c_void_p]),
+    "xemo_vl_nnglobalpool": (c_int, [c_void_p, _AP, _AP, _AP]),
+    "xemo_vl_nnaxpy": (c_int, [c_void_p, _AP, _AP, _AP, _AP]),
+    "xemo_op_hwcn_to_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int]),
+    "xemo_op_nhwc_to_hwcn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "xemo_op_filters_to_krsc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int]),
+    "xemo_op_face_rows_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "xemo_op_spec_s2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "xemo_op_conv_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int]),
+    "xemo_dgrad_pack_elems": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "xemo_op_pack_dgrad_filters": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "xemo_op_conv_dgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, c_int, c_int, c_void_p]),
+    "xemo_op_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, c_int, c_int, c_int, c_void_p, c_float]),
+    "xemo_op_colsum": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_float, c_void_p]),
+    "xemo_op_maxpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "xemo_op_maxpool_bwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]),
+    "xemo_op_avgpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]),
+    "xemo_op_avgpool_bwd": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]),
+    "xemo_op_bn_train": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "xemo_op_bn_test": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "xemo_op_affine_act": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "xemo_op_bn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_float]),
+    "xemo_op_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "xemo_op_add_act": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "xemo_op_se_squeeze": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "xemo_op_se_gate": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "xemo_op_se_excite": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "xemo_op_logit_aggregate": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "xemo_op_softmaxce": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_int, c_float,
+                                  c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "xemo_op_sgd_momentum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_float, c_float, c_float, c_void_p]),
+    "xemo_op_moments_average": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float]),
+    "xemo_op_cast_f32_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "xemo_op_cast_f16_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p]),
+    "xemo_op_fill_strided_f32": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_size_t, c_int, c_float]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen libxemo.so (built in-tree by mcncrossmodalemotions_b200.build) and type every symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s is missing: build it with `python -m mcncrossmodalemotions_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class Context:
+    """xemo_ctx bound to one device and one stream.  Every xemo_* entry point is reachable as a
+    method without the `xemo_` prefix and with the context argument supplied; non-zero status codes
+    raise XemoError carrying xemo_last_error()."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load_library()
+        h = c_void_p()
+        rc = self.lib.xemo_create(int(device), c_void_p(stream or 0), C.byref(h))
+        if rc != 0:
+            raise XemoError(rc, "xemo_create failed (no sm_100 device, or TMA driver entry points unavailable); no CPU fallback exists")
+        self.handle = h
+        self.device = device
+        self.num_sms = self.lib.xemo_num_sms(h)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.xemo_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def call(self, name, *args):
+        fn = getattr(self.lib, "xemo_" + name)
+        rc = fn(self.handle, *args)
+        if rc != 0:
+            raise XemoError(rc, self.lib.xemo_last_error(self.handle).decode())
+
+    def __getattr__(self, name):
+        if name.startswith(("op_", "vl_")) or name in ("sync", "h2d", "d2h", "memset", "capture_begin", "graph_launch"):
+            return lambda *a: self.call(name, *a)
+        raise AttributeError(name)
+
+    def launch_count(self):
+        return int(self.lib.xemo_launch_count(self.handle))
+
+    def capture_end(self):
+        g = c_void_p()
+        self.call("capture_end", C.byref(g))
+        return Graph(self, g)
+
+
+class Graph:
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+        self.num_kernels = ctx.lib.xemo_graph_num_kernels(handle)
+
+    def launch(self):
+        self.ctx.call("graph_launch", self.handle)
+
+    def destroy(self):
+        if self.handle:
+            self.ctx.lib.xemo_graph_destroy(self.handle)
+            self.handle = None

@@ -270,7 +270,9 @@ int xemo_conv_dgrad_impl(xemo_ctx* ctx, const void* dy16, int N, int H, int W, i
       if (sub_h <= 0 || sub_w <= 0) continue;
       const int qh = (ph + pt) / sh, qw = (pw + pl) / sw;
       const int pad_t = c.Jh - 1 - qh, pad_l = c.Jw - 1 - qw;
-      XEMO_REQUIRE(ctx, pad_t >= 0 && pad_l >= 0, "conv_dgrad: padding larger than the filter is not supported");
+      // a negative value (forward padding larger than the sub-filter reach) simply starts the TMA
+      // im2col bounding box inside dY
+      XEMO_REQUIRE(ctx, pad_t >= -127 && pad_l >= -127 && pad_t <= 127 && pad_l <= 127, "conv_dgrad: padding out of TMA range");
       ConvGeom g{N, OH, OW, Kout, Cin, c.Jh, c.Jw, 1, 1, pad_t, 0, pad_l, 0};
       g.oh_override = sub_h;
       g.ow_override = sub_w;

@@ -87,6 +87,27 @@ class TorchOps:
     relu = staticmethod(M.vl_nnrelu)
 
 
+def _r16(a):
+    return a.astype(np.float16).astype(a.dtype)
+
+
+class Fp16ModelOps(TorchOps):
+    """The device number-format model: convolution operands (activations, filters, output gradients)
+    rounded to fp16 before a wide-accumulate contraction; activations and data gradients stored in
+    fp16; everything else as in TorchOps.  Used to separate "the kernels implement the fp16 model
+    exactly" (tight tolerance against this back-end) from "the fp16 model is close to fp32" (the
+    documented tolerance against TorchOps / NumpyOps)."""
+
+    name = "fp16-model"
+
+    @classmethod
+    def conv(cls, x, f, b=None, dzdy=None, pad=0, stride=1):
+        if dzdy is None:
+            return _r16(TorchOps.conv(_r16(x), _r16(f), b, None, pad, stride))
+        dx, df, db = TorchOps.conv(_r16(x), _r16(f), b, _r16(dzdy), pad, stride)
+        return _r16(dx), df, db
+
+
 # ------------------------------------------------------------------------------------------------
 # VGGVox student (SURVEY.md Appendix A.1).  Layer tuples: (name, type, args)
 

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b|: the relative-to-range criterion used for every floating-point parity check
+    (north_star: 1e-3 relative fp32 tolerance)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    d = np.abs(b).max()
+    return float(np.abs(a - b).max() / (d if d > 0 else 1.0))
+
+
+@pytest.fixture(scope="session")
+def rel():
+    return rel_err

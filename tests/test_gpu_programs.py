@@ -1,0 +1,155 @@
+"""Parity of the fused device programs (teacher forward, student forward / training step) against the
+CPU oracle, through libxemo.so.
+
+Tolerances.  north_star: logits within 1e-3 relative (max|a-b| <= 1e-3 * max|ref|) of the fp32/fp64
+CPU path; pooling indices / class-error counts exact.  Convolution operands are fp16 (fp32
+accumulation), so a single contraction is good to ~3e-4 and a 50-layer teacher to ~7e-4 (measured;
+tools/precision_emulation.py reproduces it on the CPU).  Train-mode quantities that are *discontinuous*
+in the activations (ReLU masks under batch-statistics BN) cannot be held to 1e-3 by any 16-bit-operand
+pipeline: they are checked (a) tightly against the oracle's fp16 number-format model
+(oracle.nets.Fp16ModelOps) and (b) against the exact oracle through continuous quantities (objective,
+batch moments, updated parameters) at 1e-3 and through the gradient direction (cosine)."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def nets():
+    from oracle import nets
+
+    return nets
+
+
+def _f64(p):
+    return {k: (v.astype(np.float64) if isinstance(v, np.ndarray) else v) for k, v in p.items()}
+
+
+@pytest.mark.parametrize("arch", ["resnet50", "senet50"])
+def test_teacher_logits(nets, arch):
+    from mcncrossmodalemotions_b200.programs import TeacherProgram
+
+    n = 8
+    p = nets.teacher_init(arch)
+    x = nets.synth_faces(n)
+    ref = nets.teacher_forward(_f64(p), x.astype(np.float64), nets.TorchOps).reshape(8, n).T
+    eager = TeacherProgram(p, n, use_graph=False).forward(x)
+    prog = TeacherProgram(p, n, use_graph=True)
+    g1 = prog.forward(x)
+    g2 = prog.forward(x)  # CUDA-graph replay
+    assert rel_err(eager, ref) < TOL
+    assert np.array_equal(eager, g1) and np.array_equal(g1, g2), "graph replay must be bit-identical to eager launches"
+    # a different batch through the same captured graph
+    x2 = nets.synth_faces(n, seed=10)
+    ref2 = nets.teacher_forward(_f64(p), x2.astype(np.float64), nets.TorchOps).reshape(8, n).T
+    assert rel_err(prog.forward(x2), ref2) < TOL
+
+
+def test_teacher_48x48_plumbing_config(nets):
+    """BASELINE config 1: 48 x 48 grey faces -> 224 x 224 x 3 (a2) -> SENet50 logits."""
+    from mcncrossmodalemotions_b200.programs import TeacherProgram
+
+    n = 4
+    p = nets.teacher_init("senet50")
+    x = nets.faces48_to_input(nets.synth_faces48(n))
+    ref = nets.teacher_forward(_f64(p), x.astype(np.float64), nets.TorchOps).reshape(8, n).T
+    assert rel_err(TeacherProgram(p, n).forward(x), ref) < TOL
+
+
+@pytest.mark.parametrize("width,n", [(300, 8), (100, 5), (400, 3)])
+def test_student_test_mode_forward(nets, width, n):
+    from mcncrossmodalemotions_b200.programs import StudentProgram
+
+    p = nets.student_randomize_bn(nets.student_init())
+    spec = nets.synth_spectrograms(n, width)
+    ref, _ = nets.student_forward(_f64(p), spec.astype(np.float64), "test", nets.TorchOps)
+    prog = StudentProgram(p, n, width)
+    got = prog.forward(spec, "test")
+    assert rel_err(got, ref.reshape(8, n).T) < TOL
+    assert np.array_equal(got, prog.forward(spec, "test"))  # graph replay
+
+
+def _cos(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+
+
+def _l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64).reshape(np.shape(a))
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_student_training_step(nets, use_graph):
+    from mcncrossmodalemotions_b200.programs import StudentProgram
+
+    n, width, lr = 16, 300, 1e-4
+    p = nets.student_randomize_bn(nets.student_init())
+    spec = nets.synth_spectrograms(n, width)
+    tgt = nets.synth_teacher_logits(n)
+    exact_p, model_p = _f64(p), _f64(p)
+    exact = nets.distillation_student_step(exact_p, {}, spec.astype(np.float64), tgt.astype(np.float64), lr=lr, ops=nets.TorchOps)
+    model = nets.distillation_student_step(model_p, {}, spec.astype(np.float64), tgt.astype(np.float64), lr=lr, ops=nets.Fp16ModelOps)
+    prog = StudentProgram(p, n, width, use_graph=use_graph)
+    prog.set_hyper(lr=lr)
+    prog.reset_metrics()
+    prog.train_step(spec, tgt)
+    m = prog.metrics()
+    grads, params = prog.export_grads(), prog.export_params()
+    # continuous quantities against the exact oracle at the north_star tolerance
+    assert abs(m["objective"] - exact["objective"]) <= TOL * abs(exact["objective"])
+    assert m["classerror"] == exact["classerror"]
+    correct, count = nets.M.error_stats(exact["prediction"], exact["max_label"], 8)
+    assert np.array_equal(m["count"], count) and np.array_equal(m["correct"], correct)
+    for k in params:
+        if k.endswith("x"):
+            assert rel_err(grads[k], exact["grads"][k]) < TOL, k      # batch moments [mu sigma]
+        if np.abs(p[k]).max() == 0:
+            continue  # zero-initialised biases: the updated value is -lr*g/B, covered by the gradient checks below
+        assert rel_err(params[k], exact_p[k].reshape(params[k].shape)) < TOL, k
+    # the gradient against the fp16 number-format model (same rounding points, fp64 accumulation) and its
+    # direction against the exact oracle
+    for k in grads:
+        if k.endswith("x") or (k.endswith("b") and not k.startswith("bn") and k != "fc8b"):
+            continue  # moments checked above; conv biases ahead of train-mode BN have an exactly-zero gradient
+        # ReLU-mask flips make the gradient chaotic at the ~1e-1 level under ANY perturbation of size 2^-11
+        # (the fp16 model itself sits 0.04-0.13 from the exact oracle, see DESIGN.md "Precision"): the
+        # kernels must be no further from the model than the model is from the truth, and point the same way
+        assert _l2(grads[k], model["grads"][k]) < 0.15, (k, _l2(grads[k], model["grads"][k]))
+        assert _cos(grads[k], exact["grads"][k]) > 0.97, (k, _cos(grads[k], exact["grads"][k]))
+    # SGD-momentum bookkeeping is exact given the gradient: w' = w + lr * (-(wd*w + g/B))
+    for k in ("fc8f", "conv3f", "bn2m"):
+        expect = p[k].astype(np.float64) - lr * (5e-4 * p[k].astype(np.float64) + grads[k].reshape(p[k].shape).astype(np.float64) / n)
+        assert rel_err(params[k], expect) < 1e-6, k
+
+
+def test_student_bias_before_train_bn_has_zero_gradient(nets):
+    from mcncrossmodalemotions_b200.programs import StudentProgram
+
+    n = 8
+    p = nets.student_init()
+    prog = StudentProgram(p, n, 100, use_graph=False)
+    prog.reset_metrics()
+    prog.set_input(nets.synth_spectrograms(n, 100), nets.synth_teacher_logits(n))
+    prog.grad_step()
+    g = prog.export_grads()
+    for i in range(1, 8):
+        name = ("conv%d" % i) if i < 6 else ("fc%d" % i)
+        assert np.abs(g[name + "b"]).max() <= 2e-2 * np.abs(g["bn%db" % i]).max(), name
+
+
+def test_launch_counter_counts_graph_nodes(nets):
+    from mcncrossmodalemotions_b200.programs import TeacherProgram
+
+    n = 2
+    prog = TeacherProgram(nets.teacher_init("resnet50"), n)
+    prog.forward(nets.synth_faces(n))
+    c0 = prog.ctx.launch_count()
+    prog.run()
+    prog.sync()
+    assert prog.ctx.launch_count() - c0 == prog.graph.num_kernels > 50
