@@ -129,6 +129,11 @@ int xemo_op_filters_to_krsc(xemo_ctx* ctx, const float* f, int FH, int FW, int F
 /* teacher stem staging: faces H x W x C x N (fp32 HWCN) -> [N][H][OW][32] fp16 row-im2col (7x7/2 -> 7x1, 32 ch) */
 int xemo_op_face_rows_im2col(xemo_ctx* ctx, const float* faces, int H, int W, int C, int N, int S, int stride_w,
                              int pad_l, int OW, void* dst16);
+/* the same staging fused with the reference's face preprocessing (emoVoxCeleb/fetch_emovoxceleb_imdb.m:175-193,
+ * teacher/ferplus_baselines.m:203-213): uint8 grey IH x IW x N (column-major) -> 3 channels, single, minus
+ * mean3[c] (device, fp32[3]), corner-aligned bilinear resize to OHt x OWt -> [N][OHt][OW][32] fp16 */
+int xemo_op_face_u8_rows_im2col(xemo_ctx* ctx, const uint8_t* faces, int IH, int IW, int N, int OHt, int OWt,
+                                const float* mean3, int S, int stride_w, int pad_l, int OW, void* dst16);
 /* student stem staging: spectrograms H x W x 1 x N -> [N][HP][OW][16] fp16 space-to-depth (7x7/2 -> 4x1, 16 ch) */
 int xemo_op_spec_s2d(xemo_ctx* ctx, const float* spec, int H, int W, int N, int pad_t, int pad_l, int HP, int OW,
                      void* dst16);

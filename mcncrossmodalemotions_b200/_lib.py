@@ -61,6 +61,7 @@ SIGNATURES = {
     "xemo_op_nhwc_to_hwcn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "xemo_op_filters_to_krsc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int]),
     "xemo_op_face_rows_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "xemo_op_face_u8_rows_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "xemo_op_spec_s2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "xemo_op_conv_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int]),
@@ -130,6 +131,7 @@ class Context:
             raise XemoError(rc, "xemo_create failed (no sm_100 device, or TMA driver entry points unavailable); no CPU fallback exists")
         self.handle = h
         self.device = device
+        self.profiler = None  # optional object with before(name, args) / after(name, args) hooks (bench.py)
         self.num_sms = self.lib.xemo_num_sms(h)
 
     def close(self):
@@ -145,7 +147,12 @@ class Context:
 
     def call(self, name, *args):
         fn = getattr(self.lib, "xemo_" + name)
+        prof = self.profiler
+        if prof is not None:
+            prof.before(name, args)
         rc = fn(self.handle, *args)
+        if prof is not None:
+            prof.after(name, args)
         if rc != 0:
             raise XemoError(rc, self.lib.xemo_last_error(self.handle).decode())
 

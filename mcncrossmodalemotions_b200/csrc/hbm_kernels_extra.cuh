@@ -201,6 +201,53 @@ static __global__ void fill_strided_f32_kernel(float* __restrict__ dst, int oute
 }
 
 // ------------------------------------------------------------------------------------------------
+// Face preprocessing fused into the teacher stem staging (emoVoxCeleb/fetch_emovoxceleb_imdb.m:175-193,
+// teacher/ferplus_baselines.m:203-213): uint8 grey IH x IW x N (column-major) -> replicate to 3 channels,
+// single, subtract averageImage[c], bilinear resize to OHt x OWt (corner-aligned grid, as the identity
+// vl_nnaffinegrid + vl_nnbilinearsampler pair) -> row-im2col tensor Xr[n][h][ow][s*4+c] fp16 for the
+// 7x1 tcgen05 stem.  One thread per (n, h, ow).
+static __global__ void face_u8_rows_im2col_kernel(const uint8_t* __restrict__ src, int IH, int IW, int N, int OHt, int OWt,
+                                                  const float* __restrict__ mean, int S, int stride_w, int pad_l, int OW,
+                                                  __half* __restrict__ dst) {
+  const size_t total = size_t(N) * OHt * OW;
+  const float sy = OHt > 1 ? float(IH - 1) / float(OHt - 1) : 0.f;
+  const float sx = OWt > 1 ? float(IW - 1) / float(OWt - 1) : 0.f;
+  const float m0 = mean[0], m1 = mean[1], m2 = mean[2];
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int ow = int(i % OW);
+    const int h = int((i / OW) % OHt);
+    const int n = int(i / (size_t(OW) * OHt));
+    const uint8_t* img = src + size_t(n) * IH * IW;
+    const float ys = h * sy;
+    int y0 = int(floorf(ys));
+    y0 = min(max(y0, 0), IH - 1);
+    const int y1 = min(y0 + 1, IH - 1);
+    const float wy = ys - float(y0);
+    __align__(16) __half v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __float2half_rn(0.f);
+    for (int s = 0; s < S; ++s) {
+      const int w = ow * stride_w + s - pad_l;
+      if (w < 0 || w >= OWt) continue;
+      const float xs = w * sx;
+      int x0 = int(floorf(xs));
+      x0 = min(max(x0, 0), IW - 1);
+      const int x1 = min(x0 + 1, IW - 1);
+      const float wx = xs - float(x0);
+      const float top = float(img[y0 + IH * x0]) * (1.f - wx) + float(img[y0 + IH * x1]) * wx;
+      const float bot = float(img[y1 + IH * x0]) * (1.f - wx) + float(img[y1 + IH * x1]) * wx;
+      const float g = top * (1.f - wy) + bot * wy;
+      v[s * 4 + 0] = __float2half_rn(g - m0);
+      v[s * 4 + 1] = __float2half_rn(g - m1);
+      v[s * 4 + 2] = __float2half_rn(g - m2);
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + ((size_t(n) * OHt + h) * OW + ow) * 32);
+    const uint4* vi = reinterpret_cast<const uint4*>(v);
+    o[0] = vi[0]; o[1] = vi[1]; o[2] = vi[2]; o[3] = vi[3];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // cnn_train_dag update with the hyper-parameters in device memory (hyper = {lr, momentum, wd, 1/B}),
 // so that a captured CUDA graph follows the learning-rate schedule without re-capture.
 static __global__ void sgd_momentum_dev_kernel(float* __restrict__ w, float* __restrict__ m, const float* __restrict__ g,

@@ -170,6 +170,16 @@ extern "C" int xemo_op_face_rows_im2col(xemo_ctx* ctx, const float* faces, int H
   return XEMO_OK;
 }
 
+extern "C" int xemo_op_face_u8_rows_im2col(xemo_ctx* ctx, const uint8_t* faces, int IH, int IW, int N, int OHt, int OWt,
+                                           const float* mean3, int S, int stride_w, int pad_l, int OW, void* dst16) {
+  XEMO_REQUIRE(ctx, faces && mean3 && dst16 && S * 4 <= 32 && IH > 0 && IW > 0, "face_u8_rows_im2col: bad arguments");
+  const size_t total = size_t(N) * OHt * OW;
+  face_u8_rows_im2col_kernel<<<grid_for(total, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
+      faces, IH, IW, N, OHt, OWt, mean3, S, stride_w, pad_l, OW, static_cast<__half*>(dst16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
 extern "C" int xemo_op_spec_s2d(xemo_ctx* ctx, const float* spec, int H, int W, int N, int pad_t, int pad_l, int HP, int OW,
                                 void* dst16) {
   XEMO_REQUIRE(ctx, spec && dst16, "spec_s2d: null pointer");

@@ -1,0 +1,111 @@
+"""The full distillation step on one GPU: SENet50/ResNet50 teacher forward -> per-clip aggregation of the
+frame logits -> VGGVox student forward/backward with the temperature-softmax CE -> SGD-momentum update.
+
+The reference runs these as two stages (teacher logits cached offline by
+emoVoxCeleb/fetch_emovoxceleb_imdb.m:54-149, then cnn_train_dag at emoVoxCeleb/run_distillation.m:170-182
+with getBatchEmoVoxCeleb.m:133-188 selecting and max-pooling the cached frame logits); BASELINE.json's
+headline config fuses them, keeping the coupling operator (`max` / `mean` over the frames of the clip,
+first numPredEmotions classes, then softmax(. / T) inside the loss)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .programs import StudentProgram, TeacherProgram, _p
+
+
+class DistillationStep:
+    def __init__(self, teacher_params, student_params, batch, width=300, frames_per_clip=1, aggregator="max", device=0,
+                 face_input="u8", face_size=48, use_graph=True, grad_scale=1024.0, temperature=2.0):
+        self.N, self.F = batch, frames_per_clip
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.ctx = _lib.Context(device, self.stream.cuda_stream)
+        self.teacher = TeacherProgram(teacher_params, batch * frames_per_clip, device, self.stream, use_graph=False, ctx=self.ctx,
+                                      input_mode=face_input, face_size=face_size)
+        self.student = StudentProgram(student_params, batch, width, device, self.stream, use_graph=False, grad_scale=grad_scale,
+                                      temperature=temperature, ctx=self.ctx)
+        self.use_mean = 1 if aggregator == "mean" else 0
+        with torch.cuda.stream(self.stream):
+            self.start = torch.arange(0, batch * frames_per_clip, frames_per_clip, dtype=torch.int32, device=self.device)
+            self.end = self.start + frames_per_clip
+            # staging buffers the copy stream fills while the previous step computes
+            self.stage_faces = torch.empty_like(self.teacher.a["faces"])
+            self.stage_spec = torch.empty_like(self.student.a["spec"])
+            self.loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.use_graph = use_graph
+        self.g_grad = self.g_update = None
+        self.h2d_done = torch.cuda.Event()
+        self.stage_free = torch.cuda.Event()
+        self.stage_free.record(self.stream)
+        self.h2d_bytes = self.stage_faces.numel() * self.stage_faces.element_size() + self.stage_spec.numel() * 4
+        self.d2h_bytes = 8
+
+    # ---- phases
+    def _record_grad(self):
+        t, s = self.teacher, self.student
+        t._record()
+        self.ctx.op_logit_aggregate(_p(t.a["logits"]), t.a["logits"].shape[1], _p(self.start), _p(self.end), self.N, s.K, self.use_mean,
+                                    _p(s.a["target"]))
+        s._record_forward(True)
+        s._record_backward()
+
+    def grad_step(self):
+        if not self.use_graph:
+            self._record_grad()
+            return
+        if self.g_grad is None:
+            self._record_grad()  # eager warm-up (kernel attributes are set outside the capture)
+            self.student.reset_metrics()
+            self.ctx.capture_begin()
+            self._record_grad()
+            self.g_grad = self.ctx.capture_end()
+        self.g_grad.launch()
+
+    def update(self):
+        if not self.use_graph:
+            self.student._record_update()
+            return
+        if self.g_update is None:
+            self.ctx.capture_begin()
+            self.student._record_update()
+            self.g_update = self.ctx.capture_end()
+        self.g_update.launch()
+
+    def step_resident(self, allreduce=None):
+        """One step on the inputs already resident in HBM (teacher.a['faces'], student.a['spec'])."""
+        self.grad_step()
+        if allreduce is not None:
+            with torch.cuda.stream(self.stream):
+                allreduce(self.student.grad)
+        self.update()
+
+    # ---- end-to-end: host buffers in, loss out
+    def prefetch(self, faces_host, spec_host):
+        """Asynchronous H2D of the next step's inputs (pinned host tensors) on the copy stream."""
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.stage_free)
+            self.stage_faces.copy_(faces_host, non_blocking=True)
+            self.stage_spec.copy_(spec_host, non_blocking=True)
+            self.h2d_done.record(self.copy_stream)
+
+    def step_host(self, allreduce=None):
+        """Consume the prefetched inputs, run the step, copy objective / classerror back to pinned host
+        memory.  Returns immediately (asynchronous); call sync() before reading loss_host."""
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.h2d_done)
+            self.teacher.a["faces"].copy_(self.stage_faces, non_blocking=True)
+            self.student.a["spec"].copy_(self.stage_spec, non_blocking=True)
+            self.stage_free.record(self.stream)
+        self.step_resident(allreduce)
+        with torch.cuda.stream(self.stream):
+            self.loss_host.copy_(self.student.a["scalars"], non_blocking=True)
+
+    def sync(self):
+        self.ctx.sync()
+
+    def num_kernels(self):
+        return (self.g_grad.num_kernels if self.g_grad else 0) + (self.g_update.num_kernels if self.g_update else 0)

@@ -98,11 +98,13 @@ def teacher_conv1_to_rows(f):
 
 
 class _Base:
-    def __init__(self, device=0, stream=None):
+    def __init__(self, device=0, stream=None, ctx=None):
+        """`stream` (torch.cuda.Stream) and `ctx` may be shared between programs that are captured into
+        one CUDA graph (the distillation step)."""
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         self.stream = stream or torch.cuda.Stream(self.device)
-        self.ctx = _lib.Context(device, self.stream.cuda_stream)
+        self.ctx = ctx or _lib.Context(device, self.stream.cuda_stream)
         self._keep = []
 
     # ---- device memory (torch tensors as raw buffers)
@@ -136,11 +138,18 @@ def _out(h, w, fh, fw, stride, pad):
 class TeacherProgram(_Base):
     """ResNet50 / SENet50 -ferplus forward (test-mode BN folded into the conv epilogues)."""
 
-    def __init__(self, params, batch, device=0, stream=None, use_graph=True):
-        super().__init__(device, stream)
+    def __init__(self, params, batch, device=0, stream=None, use_graph=True, ctx=None, input_mode="hwcn224", face_size=48,
+                 average_image=(131.0912, 103.8827, 91.4953)):
+        """input_mode 'hwcn224': 224 x 224 x 3 x N single, already normalised (what dag.eval receives at
+        emoVoxCeleb/fetch_emovoxceleb_imdb.m:129).  'u8': face_size x face_size x N uint8 grey faces; the
+        reference's normalizeFace + resize (fetch_emovoxceleb_imdb.m:175-193) run fused on the device."""
+        super().__init__(device, stream, ctx)
         self.arch = params["arch"]
         self.N = batch
         self.use_graph = use_graph
+        self.input_mode = input_mode
+        self.face_size = face_size
+        self.mean3 = self.upload(np.asarray(average_image, np.float32))
         self.graph = None
         self._load(params)
         self._alloc()
@@ -180,7 +189,10 @@ class TeacherProgram(_Base):
     def _alloc(self):
         N = self.N
         A = self.a = {}
-        A["faces"] = self.f32(N * 3 * 224 * 224)          # H x W x C x N column-major fp32 (MatConvNet layout)
+        if self.input_mode == "u8":
+            A["faces"] = torch.zeros(N * self.face_size * self.face_size, dtype=torch.uint8, device=self.device)
+        else:
+            A["faces"] = self.f32(N * 3 * 224 * 224)      # H x W x C x N column-major fp32 (MatConvNet layout)
         A["rows"] = self.f16(N, 224, 112, 32)
         A["c1"] = self.f16(N, 112, 112, 64)
         A["p1"] = self.f16(N, 56, 56, 64)
@@ -202,7 +214,11 @@ class TeacherProgram(_Base):
 
     def _record(self):
         N, A, W, ctx = self.N, self.a, self.w, self.ctx
-        ctx.op_face_rows_im2col(_p(A["faces"]), 224, 224, 3, N, 7, 2, 3, 112, _p(A["rows"]))
+        if self.input_mode == "u8":
+            fs = self.face_size
+            ctx.op_face_u8_rows_im2col(_p(A["faces"]), fs, fs, N, 224, 224, _p(self.mean3), 7, 2, 3, 112, _p(A["rows"]))
+        else:
+            ctx.op_face_rows_im2col(_p(A["faces"]), 224, 224, 3, N, 7, 2, 3, 112, _p(A["rows"]))
         a, b = W["bn1"]
         self.conv(A["rows"], N, 224, 112, 32, W["conv1"], 64, 7, 1, (2, 1), (3, 3, 0, 0), a, b, None, 1, A["c1"])
         ctx.op_maxpool_fwd(_p(A["c1"]), N, 112, 112, 64, 3, 3, 2, 2, 0, 1, 0, 1, None, None, _p(A["p1"]), None)
@@ -252,7 +268,10 @@ class TeacherProgram(_Base):
         """faces: 224 x 224 x 3 x N numpy (MatConvNet layout) or a pinned/device flat torch tensor in
         column-major order."""
         if isinstance(faces, np.ndarray):
-            faces = torch.from_numpy(np.ascontiguousarray(faces.astype(np.float32).transpose(3, 2, 1, 0)).reshape(-1))
+            if self.input_mode == "u8":
+                faces = torch.from_numpy(np.ascontiguousarray(faces.astype(np.uint8).transpose(2, 1, 0)).reshape(-1))
+            else:
+                faces = torch.from_numpy(np.ascontiguousarray(faces.astype(np.float32).transpose(3, 2, 1, 0)).reshape(-1))
         with torch.cuda.stream(self.stream):
             self.a["faces"].copy_(faces.reshape(-1), non_blocking=True)
 
@@ -271,8 +290,8 @@ class StudentProgram(_Base):
     """VGGVox student: forward (train / test mode BN), backward, loss + metrics, SGD-momentum."""
 
     def __init__(self, params, batch, width=300, device=0, stream=None, use_graph=True, grad_scale=1024.0, num_classes=8,
-                 temperature=2.0):
-        super().__init__(device, stream)
+                 temperature=2.0, ctx=None):
+        super().__init__(device, stream, ctx)
         self.N, self.W = batch, width
         self.use_graph = use_graph
         self.grad_scale = float(grad_scale)
@@ -428,6 +447,7 @@ class StudentProgram(_Base):
         last = self.layers[-1]
         ctx.memset(_p(self.grad), 0, self.nparam * 4)
         ctx.memset(_p(A["fc8:draw"]), 0, A["fc8:draw"].numel() * 2)
+        ctx.memset(_p(A["scalars"]), 0, 8)  # objective / classerror of THIS batch (class_stats keep accumulating)
         ctx.op_softmaxce(_p(A["fc8:raw"]), last["kp"], _p(A["target"]), self.K, None, N, self.K, self.T, 1, 1.0, gs,
                          _p(A["fc8:draw"]), _p(A["scalars"]), _p(A["class_stats"]), _p(A["max_label"]))
         for i in range(len(self.layers) - 1, -1, -1):
