@@ -393,24 +393,44 @@ __global__ void avgpool_bwd_kernel(const T* __restrict__ dy, PoolGeom g, T* __re
 //   backward   : reduce db = sum(dz), dg = sum(dz * xhat) with dz = dy * [y>0] when ReLU is fused;
 //                dx = a * (dz - db/P - xhat*dg/P)
 // ============================================================================================
-constexpr int kBnRowsPerBlock = 256;
+// Reduction layout shared by the statistics and the backward-reduce kernels: a block of 256 threads
+// covers `lanes` = min(C/8, 256) channel groups x `rows_par` = 256 / lanes rows at a time and strides
+// over the rows of its slab in registers (fp32); the rows_par partial sums are combined through
+// shared memory and leave the block as ONE double atomic per channel and statistic.  The grid is
+// (row slabs ~ 4 per SM, channel slabs), so the atomic traffic is a few thousand adds per launch.
+constexpr int kBnThreads = 256;
+
+struct BnGrid {
+  int lanes, rows_par, slabs_x, slabs_y;
+};
+inline BnGrid bn_grid(size_t P, int C, int num_sms) {
+  BnGrid g;
+  const int C8 = C >> 3;
+  g.lanes = C8 < kBnThreads ? C8 : kBnThreads;
+  g.rows_par = kBnThreads / g.lanes;
+  g.slabs_y = (C8 + g.lanes - 1) / g.lanes;
+  size_t want = size_t(num_sms) * 4 / g.slabs_y;
+  if (want < 1) want = 1;
+  const size_t max_slabs = (P + size_t(g.rows_par) * 4 - 1) / (size_t(g.rows_par) * 4);  // >= 4 rows per thread
+  g.slabs_x = int(want < max_slabs ? want : (max_slabs < 1 ? 1 : max_slabs));
+  return g;
+}
 
 template <typename T>
-__global__ void bn_stats_kernel(const T* __restrict__ x, size_t P, int C, double* __restrict__ acc) {
-  // block = (C/8 lanes) x rows; each thread owns 8 channels and strides over rows
+__global__ void bn_stats_kernel(const T* __restrict__ x, size_t P, int C, int lanes, int rows_par,
+                                double* __restrict__ acc) {
+  __shared__ float red[2][kBnThreads][8];
   const int C8 = C >> 3;
-  const int lanes = C8 < int(blockDim.x) ? C8 : int(blockDim.x);
-  const int rows_par = blockDim.x / lanes;
   const int rl = threadIdx.x / lanes;
   const int cl = threadIdx.x - rl * lanes;
-  if (rl >= rows_par) return;
-  const size_t row0 = size_t(blockIdx.x) * kBnRowsPerBlock;
-  const size_t row1 = row0 + kBnRowsPerBlock < P ? row0 + kBnRowsPerBlock : P;
-  for (int c8 = cl + blockIdx.y * lanes; c8 < C8; c8 += lanes * gridDim.y) {
-    float s1[8], s2[8];
+  const int c8 = blockIdx.y * lanes + cl;
+  const bool active = rl < rows_par && c8 < C8;
+  float s1[8], s2[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
-    for (size_t r = row0 + rl; r < row1; r += rows_par) {
+  for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+  if (active) {
+    const size_t stride = size_t(gridDim.x) * rows_par;
+    for (size_t r = size_t(blockIdx.x) * rows_par + rl; r < P; r += stride) {
       Vec8<T> v;
       v.load(x + r * C + c8 * 8);
       float f[8];
@@ -418,10 +438,17 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, size_t P, int C, double
 #pragma unroll
       for (int k = 0; k < 8; ++k) { s1[k] += f[k]; s2[k] = fmaf(f[k], f[k], s2[k]); }
     }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { red[0][threadIdx.x][k] = s1[k]; red[1][threadIdx.x][k] = s2[k]; }
+  __syncthreads();
+  if (rl == 0 && c8 < C8) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      atomicAdd(&acc[c8 * 8 + k], double(s1[k]));
-      atomicAdd(&acc[C + c8 * 8 + k], double(s2[k]));
+      double t1 = 0.0, t2 = 0.0;
+      for (int j = 0; j < rows_par; ++j) { t1 += double(red[0][j * lanes + cl][k]); t2 += double(red[1][j * lanes + cl][k]); }
+      atomicAdd(&acc[c8 * 8 + k], t1);
+      atomicAdd(&acc[C + c8 * 8 + k], t2);
     }
   }
 }
@@ -476,30 +503,31 @@ __global__ void affine_act_kernel(const T* __restrict__ x, size_t P, int C, cons
 }
 
 // backward reduce: acc[0..C) += sum dz ; acc[C..2C) += sum dz * xhat, xhat = (x - mu)/sigma.
-// dz = dy * [a*x+b > 0] when relu_mask.
+// dz = dy * [a*x+b > 0] when relu_mask.  Same block layout as bn_stats_kernel.
 template <typename T>
-__global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, size_t P, int C,
-                                     const float* __restrict__ moments, const float* __restrict__ a,
+__global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, size_t P, int C, int lanes,
+                                     int rows_par, const float* __restrict__ moments, const float* __restrict__ a,
                                      const float* __restrict__ b, int relu_mask, double* __restrict__ acc) {
+  __shared__ float red[2][kBnThreads][8];
   const int C8 = C >> 3;
-  const int lanes = C8 < int(blockDim.x) ? C8 : int(blockDim.x);
-  const int rows_par = blockDim.x / lanes;
   const int rl = threadIdx.x / lanes;
   const int cl = threadIdx.x - rl * lanes;
-  if (rl >= rows_par) return;
-  const size_t row0 = size_t(blockIdx.x) * kBnRowsPerBlock;
-  const size_t row1 = row0 + kBnRowsPerBlock < P ? row0 + kBnRowsPerBlock : P;
-  for (int c8 = cl + blockIdx.y * lanes; c8 < C8; c8 += lanes * gridDim.y) {
-    float s1[8], s2[8], mu[8], isg[8], av[8], bv[8];
+  const int c8 = blockIdx.y * lanes + cl;
+  const bool active = rl < rows_par && c8 < C8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+  if (active) {
+    float mu[8], isg[8], av[8], bv[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      s1[k] = 0.f; s2[k] = 0.f;
       mu[k] = moments[c8 * 8 + k];
       isg[k] = 1.f / moments[C + c8 * 8 + k];
       av[k] = a[c8 * 8 + k];
       bv[k] = b[c8 * 8 + k];
     }
-    for (size_t r = row0 + rl; r < row1; r += rows_par) {
+    const size_t stride = size_t(gridDim.x) * rows_par;
+    for (size_t r = size_t(blockIdx.x) * rows_par + rl; r < P; r += stride) {
       Vec8<T> vx, vd;
       vx.load(x + r * C + c8 * 8);
       vd.load(dy + r * C + c8 * 8);
@@ -514,10 +542,17 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
         s2[k] = fmaf(dz, (fx[k] - mu[k]) * isg[k], s2[k]);
       }
     }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { red[0][threadIdx.x][k] = s1[k]; red[1][threadIdx.x][k] = s2[k]; }
+  __syncthreads();
+  if (rl == 0 && c8 < C8) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      atomicAdd(&acc[c8 * 8 + k], double(s1[k]));
-      atomicAdd(&acc[C + c8 * 8 + k], double(s2[k]));
+      double t1 = 0.0, t2 = 0.0;
+      for (int j = 0; j < rows_par; ++j) { t1 += double(red[0][j * lanes + cl][k]); t2 += double(red[1][j * lanes + cl][k]); }
+      atomicAdd(&acc[c8 * 8 + k], t1);
+      atomicAdd(&acc[C + c8 * 8 + k], t2);
     }
   }
 }

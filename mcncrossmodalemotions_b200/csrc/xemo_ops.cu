@@ -405,10 +405,9 @@ extern "C" int xemo_op_avgpool_bwd(xemo_ctx* ctx, const void* dy16, int N, int H
 template <typename T>
 int bn_stats_launch(xemo_ctx* ctx, const T* x, size_t P, int C, double* ws) {
   XEMO_CUDA(ctx, cudaMemsetAsync(ws, 0, size_t(2) * C * sizeof(double), ctx->stream));
-  const int C8 = C / 8;
-  const int lanes = C8 < 256 ? C8 : 256;
-  dim3 grid(unsigned((P + kBnRowsPerBlock - 1) / kBnRowsPerBlock), unsigned((C8 + lanes - 1) / lanes));
-  bn_stats_kernel<T><<<grid, 256, 0, ctx->stream>>>(x, P, C, ws);
+  const BnGrid bg = bn_grid(P, C, ctx->num_sms);
+  dim3 grid(bg.slabs_x, bg.slabs_y);
+  bn_stats_kernel<T><<<grid, kBnThreads, 0, ctx->stream>>>(x, P, C, bg.lanes, bg.rows_par, ws);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }
@@ -449,9 +448,9 @@ extern "C" int xemo_op_bn_bwd(xemo_ctx* ctx, const void* x16, const void* dy16, 
   const __half* dy = static_cast<const __half*>(dy16);
   XEMO_CUDA(ctx, cudaMemsetAsync(ws, 0, size_t(2) * C * sizeof(double), ctx->stream));
   const int C8 = C / 8;
-  const int lanes = C8 < 256 ? C8 : 256;
-  dim3 grid(unsigned((P + kBnRowsPerBlock - 1) / kBnRowsPerBlock), unsigned((C8 + lanes - 1) / lanes));
-  bn_bwd_reduce_kernel<__half><<<grid, 256, 0, ctx->stream>>>(x, dy, P, C, moments, a, b, relu_mask, ws);
+  const BnGrid bg = bn_grid(P, C, ctx->num_sms);
+  dim3 grid(bg.slabs_x, bg.slabs_y);
+  bn_bwd_reduce_kernel<__half><<<grid, kBnThreads, 0, ctx->stream>>>(x, dy, P, C, bg.lanes, bg.rows_par, moments, a, b, relu_mask, ws);
   XEMO_LAUNCHED(ctx, 1);
   const int egrid = grid_for(P * C8, 256, ctx->num_sms, 16);
   if (test_mode)

@@ -299,9 +299,9 @@ extern "C" int xemo_vl_nnbnorm(xemo_ctx* ctx, const xemo_array* x, const float* 
     if (ar.failed) return ar.finish();
     if ((rc = xemo_op_hwcn_to_nhwc(ctx, dyd, H, W, C, N, dyn, Cp, 1))) return rc;
     XEMO_CUDA(ctx, cudaMemsetAsync(ws, 0, size_t(2) * Cp * sizeof(double), ctx->stream));
-    const int lanes = C8 < 256 ? C8 : 256;
-    dim3 grid(unsigned((P + kBnRowsPerBlock - 1) / kBnRowsPerBlock), unsigned((C8 + lanes - 1) / lanes));
-    bn_bwd_reduce_kernel<float><<<grid, 256, 0, ctx->stream>>>(xn, dyn, P, Cp, mom, av, bv, 0, ws);
+    const BnGrid bg = bn_grid(P, Cp, ctx->num_sms);
+    dim3 grid(bg.slabs_x, bg.slabs_y);
+    bn_bwd_reduce_kernel<float><<<grid, kBnThreads, 0, ctx->stream>>>(xn, dyn, P, Cp, bg.lanes, bg.rows_par, mom, av, bv, 0, ws);
     XEMO_LAUNCHED(ctx, 1);
     if (moments_in)
       bn_bwd_test_kernel<float><<<egrid, 256, 0, ctx->stream>>>(xn, dyn, P, Cp, av, bv, 0, outn);

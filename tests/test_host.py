@@ -1,0 +1,151 @@
+"""CPU-side checks of the product package: the C-ABI library loads and exports every symbol include/xemo.h
+declares, the host-side layout transforms round-trip, the product zoo generates the same synthetic graphs as
+the oracle, and the data-parallel plumbing sums gradients across two gloo ranks."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "xemo.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(xemo_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    from mcncrossmodalemotions_b200 import _lib
+
+    lib = _lib.load_library()
+    syms = header_symbols()
+    assert len(syms) >= 58
+    for s in syms:
+        assert hasattr(lib, s), "libxemo.so does not export %s" % s
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes signatures and include/xemo.h disagree"
+    assert lib.xemo_version() >= 100
+
+
+def test_no_device_means_loud_failure_not_fallback():
+    import torch
+
+    from mcncrossmodalemotions_b200 import _lib
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.XemoError):
+        _lib.Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mcncrossmodalemotions_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("the oracle", ""), fn
+
+
+def test_out_size_rule():
+    import ctypes as C
+
+    from mcncrossmodalemotions_b200 import _lib
+
+    lib = _lib.load_library()
+    oh, ow = C.c_int64(), C.c_int64()
+    assert lib.xemo_out_size(512, 300, 7, 7, _lib.I4(1, 1, 1, 1), _lib.I2(2, 2), C.byref(oh), C.byref(ow)) == 0
+    assert (oh.value, ow.value) == (254, 148)
+    assert lib.xemo_out_size(4, 4, 5, 5, _lib.I4(0, 0, 0, 0), _lib.I2(1, 1), C.byref(oh), C.byref(ow)) != 0
+
+
+def test_filter_layout_round_trips():
+    from mcncrossmodalemotions_b200 import programs as P
+
+    rng = np.random.default_rng(0)
+    f = rng.standard_normal((7, 7, 1, 96)).astype(np.float32)
+    g = P.student_conv1_to_s2d(f)
+    assert g.shape == (96, 4, 1, 16) and np.array_equal(P.student_conv1_from_s2d(g), f)
+    assert np.all(g[:, :, 0, 7] == 0) and np.all(g[:, :, 0, 15] == 0) and np.all(g[:, 3, 0, 8:] == 0)
+    # the space-to-depth formulation computes the same convolution
+    x = rng.standard_normal((20, 18)).astype(np.float32)
+    oh, ow = (20 + 2 - 7) // 2 + 1, (18 + 2 - 7) // 2 + 1
+    xp = np.pad(x, 1)
+    direct = np.array([[(xp[2 * i:2 * i + 7, 2 * j:2 * j + 7] * f[:, :, 0, 5]).sum() for j in range(ow)] for i in range(oh)])
+    s2d = np.zeros((oh + 3, ow, 16), np.float32)
+    for hp in range(oh + 3):
+        for dr in range(2):
+            for s in range(7):
+                h, w = 2 * hp + dr - 1, 2 * np.arange(ow) + s - 1
+                ok = (0 <= h < 20) & (w >= 0) & (w < 18)
+                s2d[hp, ok, dr * 8 + s] = x[h, w[ok]] if 0 <= h < 20 else 0
+    via = np.array([[(s2d[i:i + 4, j, :] * g[5, :, 0, :]).sum() for j in range(ow)] for i in range(oh)])
+    assert np.allclose(direct, via, atol=1e-4)
+    k = rng.standard_normal((3, 3, 20, 24)).astype(np.float32)
+    assert P.krsc(k).shape == (32, 3, 3, 32) and np.array_equal(P.unkrsc(P.krsc(k), 3, 3, 20, 24), k)
+    t = rng.standard_normal((7, 7, 3, 64)).astype(np.float32)
+    r = P.teacher_conv1_to_rows(t)
+    assert r.shape == (64, 7, 1, 32) and r[9, 2, 0, 5 * 4 + 1] == t[2, 5, 1, 9] and np.all(r[:, :, 0, 3::4] == 0)
+
+
+def test_zoo_matches_oracle_graphs_and_buckets():
+    from mcncrossmodalemotions_b200 import zoo
+    from oracle import nets
+
+    a, b = zoo.student_init(), nets.student_init()
+    assert a.keys() == b.keys() and all(np.array_equal(a[k], b[k]) for k in a)
+    a, b = zoo.teacher_init("resnet50-ferplus"), nets.teacher_init("resnet50")
+    assert all(np.array_equal(a[k], b[k]) for k in a if k != "arch")
+    assert zoo.POOL6_BUCKETS == nets.POOL6_TABLE and zoo.pool6_window(400) == (1, 11)
+    with pytest.raises(ValueError):
+        zoo.pool6_window(350)
+
+
+def test_bucket_bounds_cover_buffer():
+    from mcncrossmodalemotions_b200.dist import bucket_bounds, shard_batch
+
+    segs = [("a", 0, 64), ("b", 64, 1000), ("c", 1088, 10), ("d", 1152, 5000), ("e", 6208, 3)]
+    b = bucket_bounds(segs, 1000)
+    assert b[0][0] == 0 and b[-1][1] == 6211 and all(x[1] <= y[0] for x, y in zip(b, b[1:]))
+    assert shard_batch(list(range(10)), 1, 4) == [1, 5, 9]
+
+
+WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from mcncrossmodalemotions_b200.dist import GradientAllReducer, bucket_bounds, shard_batch
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+segs = [("w%%d" %% i, i * 128, 100 + i) for i in range(9)]
+flat = torch.zeros(9 * 128)
+rng = np.random.default_rng(7)
+per_sample = torch.from_numpy(rng.standard_normal((8, 9 * 128)).astype(np.float32))   # gradient of each sample of the batch
+mask = torch.zeros(9 * 128)
+for _, off, n in segs:
+    mask[off:off + n] = 1                                                              # alignment padding between segments stays zero
+per_sample *= mask
+mine = shard_batch(list(range(8)), rank, world)
+flat += per_sample[mine].sum(0)
+for async_op in (False, True):
+    g = flat.clone()
+    GradientAllReducer(bucket_bounds(segs, 300), async_op=async_op)(g)
+    assert torch.allclose(g, per_sample.sum(0), atol=1e-5), "all-reduced gradient != full-batch gradient"
+# the update divides by the GLOBAL batch: identical on both ranks
+w = torch.ones(9 * 128) - 0.1 * (g / 8)
+ref = [torch.zeros_like(w) for _ in range(world)]
+dist.all_gather(ref, w)
+assert all(torch.equal(r, ref[0]) for r in ref)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_rank_gradient_sum_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
