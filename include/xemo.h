@@ -183,7 +183,8 @@ int xemo_op_bn_bwd(xemo_ctx* ctx, const void* x16, const void* dy16, size_t P, i
 int xemo_op_relu_bwd(xemo_ctx* ctx, const void* y16, const void* dy16, size_t n, void* dx16);
 int xemo_op_add_act(xemo_ctx* ctx, const void* a16, const void* b16, size_t n, int relu, void* y16);
 
-/* squeeze-and-excitation: s = mean_hw(u) ; gate = sigmoid(W2 relu(W1 s + b1) + b2) ; y = relu(gate*u + shortcut) */
+/* squeeze-and-excitation: s = mean_hw(u) ; gate = sigmoid(W2 relu(W1 s + b1) + b2) ; y = relu(gate*u + shortcut).
+ * w1 is [Cr][C]; w2 is passed TRANSPOSED, [Cr][C] (w2t[j][c] = W2[c][j]), so that the gate kernel reads it coalesced. */
 int xemo_op_se_squeeze(xemo_ctx* ctx, const void* u16, int N, int HW, int C, float* s);
 int xemo_op_se_gate(xemo_ctx* ctx, const float* s, int N, int C, int Cr, const float* w1, const float* b1,
                     const float* w2, const float* b2, float* gate);

@@ -198,23 +198,39 @@ inline bool conv_wgrad_plan(WgradPlan* plan, const ConvGeom& g, const __half* x,
   p.block_c = block_c;
   p.c_tiles = g.Cin / block_c;
   const int total_sub = g.R * g.S * p.c_tiles;
-  int T = 512 / block_c;
-  if (T > total_sub) T = total_sub;
-  // keep the stage small enough for >= 3 pipeline stages
-  while (T > 1 && wgrad_stage_bytes(T, block_c) * 3 > kSmemBudget - 2048) --T;
+  const int t_max = (512 / block_c) < total_sub ? (512 / block_c) : total_sub;
+  // Pixels per stage and sub-tiles per item: prefer the largest TMA boxes (128 / 64 / 32 pixels) that
+  // still leave >= 4 pipeline stages with at least two sub-tiles sharing each dY tile; short reductions
+  // (fc layers) stay at 32 pixels.
+  const int P_total = g.N * OH * OW;
+  const int budget = kSmemBudget - 2048;
+  int pix = 32, T = t_max;
+  while (T > 1 && wgrad_stage_bytes(T, block_c, 32) * 3 > budget) --T;
+  for (int cand = 128; cand >= 64; cand >>= 1) {
+    if (P_total < cand * 8) continue;
+    int tc = t_max;
+    while (tc > 1 && wgrad_stage_bytes(tc, block_c, cand) * 4 > budget) --tc;
+    if (wgrad_stage_bytes(tc, block_c, cand) * 4 > budget) continue;
+    if (tc < 2 && t_max >= 2 && block_c < 192) continue;  // a 192+-column sub-tile amortises the dY tile by itself
+    pix = cand;
+    T = tc;
+    break;
+  }
   p.T = T;
+  p.pix = pix;
   p.groups = (total_sub + T - 1) / T;
   p.m_tiles = (g.Kout + kWgBlockM - 1) / kWgBlockM;
-  const int pix_blocks = (p.P + kWgPix - 1) / kWgPix;
+  const int pix_blocks = (p.P + p.pix - 1) / p.pix;
   const int base_items = p.m_tiles * p.groups;
   // split the pixel reduction so that there are ~2 items per SM, each at least 8 pixel blocks long
-  int splits = (2 * num_sms + base_items - 1) / base_items;
+  // (rounded DOWN so that the item count stays within two full waves of the persistent grid)
+  int splits = (2 * num_sms) / base_items;
   const int max_splits = (pix_blocks + 7) / 8;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.pix_blocks_per_split = (pix_blocks + splits - 1) / splits;
   p.splits = (pix_blocks + p.pix_blocks_per_split - 1) / p.pix_blocks_per_split;
-  const int stage_bytes = wgrad_stage_bytes(T, block_c);
+  const int stage_bytes = wgrad_stage_bytes(T, block_c, p.pix);
   int stages = (kSmemBudget - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return false;
@@ -228,10 +244,10 @@ inline bool conv_wgrad_plan(WgradPlan* plan, const ConvGeom& g, const __half* x,
   const int upper_w = (OW - 1) * g.sw - g.pl - (g.W - 1);
   const int upper_h = (OH - 1) * g.sh - g.pt - (g.H - 1);
   if (!make_tmap_im2col_nhwc_f16(&plan->tmX, x, g.N, g.H, g.W, g.Cin, -g.pl, -g.pt, upper_w, upper_h, g.sw, g.sh,
-                                 uint32_t(p.chunk_b), uint32_t(kWgPix), swizzle_for_bytes(p.chunk_b * 2)))
+                                 uint32_t(p.chunk_b), uint32_t(p.pix), swizzle_for_bytes(p.chunk_b * 2)))
     return false;
   if (!make_tmap_2d_f16(&plan->tmY, dy, uint64_t(p.P), uint64_t(ldy), uint64_t(ldy), uint32_t(p.chunk_a),
-                        uint32_t(kWgPix), swizzle_for_bytes(p.chunk_a * 2)))
+                        uint32_t(p.pix), swizzle_for_bytes(p.chunk_a * 2)))
     return false;
   return true;
 }

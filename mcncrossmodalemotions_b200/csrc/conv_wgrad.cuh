@@ -15,7 +15,7 @@
 
 namespace xemo {
 
-constexpr int kWgPix = 32;        // pixels (GEMM-K) per pipeline stage
+constexpr int kWgPixMax = 128;    // pixels (GEMM-K) per pipeline stage: 32 / 64 / 128, chosen by the plan
 constexpr int kWgBlockM = 128;    // kout per item
 constexpr int kWgThreads = 192;
 
@@ -36,12 +36,13 @@ struct ConvWgradParams {
   int splits;
   int pix_blocks_per_split;
   int num_stages;
+  int pix;      // pixels per stage (multiple of 16)
   float* dF;    // [Kout][R][S][Cin] fp32, accumulated into (caller zeroes)
   float scale;  // applied to the accumulators before the atomic add (1/grad_scale)
 };
 
-__host__ __device__ inline int wgrad_stage_bytes(int T, int block_c) {
-  return kWgPix * kWgBlockM * 2 + T * kWgPix * block_c * 2;
+__host__ __device__ inline int wgrad_stage_bytes(int T, int block_c, int pix) {
+  return pix * kWgBlockM * 2 + T * pix * block_c * 2;
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -49,9 +50,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
                   const ConvWgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kWgPix = p.pix;
   const int a_bytes = kWgPix * kWgBlockM * 2;
   const int b_sub_bytes = kWgPix * p.block_c * 2;
-  const int stage_bytes = wgrad_stage_bytes(p.T, p.block_c);
+  const int stage_bytes = wgrad_stage_bytes(p.T, p.block_c, p.pix);
   const int num_stages = p.num_stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(num_stages) * stage_bytes);
   uint64_t* full_bar = bars;
@@ -157,7 +159,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + size_t(stage) * stage_bytes);
           const uint32_t sb = sa + a_bytes;
-#pragma unroll
           for (int k = 0; k < kWgPix / 16; ++k) {
             // 16 pixels (GEMM-K) = two 8-row groups: advance by 2*SBO
             const uint64_t a_desc = make_smem_desc(sa + k * 2 * sbo_a, lbo_a, sbo_a, swz_a);

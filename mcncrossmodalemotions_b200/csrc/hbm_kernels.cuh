@@ -212,13 +212,35 @@ struct PoolGeom {
   int OH, OW;
 };
 
-template <typename T, bool kAffineRelu>
+// Grid for kernels whose threads keep per-channel coefficients in registers: the total thread count is
+// a multiple of C8 (= C/8 channel groups), so that a grid-stride loop over (row, channel-group) items
+// always revisits the same channel group.
+inline int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
+inline int fixed_channel_grid(size_t items, int C8, int threads, int num_sms, int per_sm) {
+  size_t blocks = (items + threads - 1) / threads;
+  const size_t cap = size_t(num_sms) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const int m = C8 / gcd_int(C8, threads);
+  return int((blocks + m - 1) / m * m);
+}
+
+// PH / PW == 0 selects the run-time window of `g` (generic path); the 3x3 and 5x3 windows of the two
+// networks are compile-time so that the window loads are issued together.
+template <typename T, bool kAffineRelu, int PHc, int PWc>
 __global__ void maxpool_fwd_kernel(const T* __restrict__ x, PoolGeom g, const float* __restrict__ a,
                                    const float* __restrict__ b, T* __restrict__ y, uint8_t* __restrict__ idx) {
+  const int PH = PHc ? PHc : g.PH, PW = PWc ? PWc : g.PW;
   const int C8 = g.C >> 3;
   const size_t total = size_t(g.N) * g.OH * g.OW * C8;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int c8 = int(i % C8);
+  const size_t tid = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  const int c8 = int(tid % C8);  // constant along the grid-stride loop (fixed_channel_grid)
+  float av[8], bv[8];
+  if (kAffineRelu) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { av[k] = a[c8 * 8 + k]; bv[k] = b[c8 * 8 + k]; }
+  }
+  for (size_t i = tid; i < total; i += size_t(gridDim.x) * blockDim.x) {
     const int ow = int((i / C8) % g.OW);
     const int oh = int((i / (size_t(C8) * g.OW)) % g.OH);
     const int n = int(i / (size_t(C8) * g.OW * g.OH));
@@ -226,30 +248,26 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, PoolGeom g, const fl
     uint8_t arg[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; arg[k] = 0; }
-    float av[8], bv[8];
-    if (kAffineRelu) {
+    const T* xn = x + size_t(n) * g.H * g.W * g.C + c8 * 8;
+    const int h0 = oh * g.sh - g.pt, w0 = ow * g.sw - g.pl;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { av[k] = a[c8 * 8 + k]; bv[k] = b[c8 * 8 + k]; }
-    }
-    for (int dw = 0; dw < g.PW; ++dw) {
-      const int w = ow * g.sw + dw - g.pl;
-      if (w < 0 || w >= g.W) continue;
-      for (int dh = 0; dh < g.PH; ++dh) {
-        const int h = oh * g.sh + dh - g.pt;
-        if (h < 0 || h >= g.H) continue;
+    for (int dw = 0; dw < PW; ++dw) {
+      const int w = w0 + dw;
+#pragma unroll
+      for (int dh = 0; dh < PH; ++dh) {
+        const int h = h0 + dh;
+        if (w < 0 || w >= g.W || h < 0 || h >= g.H) continue;
         Vec8<T> v;
-        v.load(x + ((size_t(n) * g.H + h) * g.W + w) * g.C + c8 * 8);
+        v.load(xn + (size_t(h) * g.W + w) * g.C);
         float f[8];
         v.to_float(f);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           float z = f[k];
-          if (kAffineRelu) {
-            // round through fp16 so that the value compared here is exactly what a separate
-            // bn+relu pass would have stored
-            z = round_to<T>(fmaxf(fmaf(av[k], z, bv[k]), 0.f));
-          }
-          if (z > best[k]) { best[k] = z; arg[k] = uint8_t(dw * g.PH + dh); }
+          // round through the storage type so that the value compared here is exactly what a
+          // separate bn+relu pass would have stored
+          if (kAffineRelu) z = round_to<T>(fmaxf(fmaf(av[k], z, bv[k]), 0.f));
+          if (z > best[k]) { best[k] = z; arg[k] = uint8_t(dw * PH + dh); }
         }
       }
     }
@@ -267,12 +285,14 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, PoolGeom g, const fl
 }
 
 // Backward of max pooling as a gather: every input position collects dy from the windows whose
-// recorded arg-max points at it (no atomics, deterministic).
-template <typename T>
+// recorded arg-max points at it (no atomics, deterministic).  MH / MW = max windows covering one
+// input position along h / w (ceil(P/stride)); 0 selects run-time loops.
+template <typename T, int MH, int MW>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, PoolGeom g,
                                    T* __restrict__ dx) {
   const int C8 = g.C >> 3;
   const size_t total = size_t(g.N) * g.H * g.W * C8;
+  const int mh = MH ? MH : (g.PH + g.sh - 1) / g.sh, mw = MW ? MW : (g.PW + g.sw - 1) / g.sw;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
     const int c8 = int(i % C8);
     const int w = int((i / C8) % g.W);
@@ -282,14 +302,17 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __re
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
     // windows (oh, ow) covering (h, w): oh*sh - pt <= h < oh*sh - pt + PH
-    const int oh_hi = min((h + g.pt) / g.sh, g.OH - 1);
-    const int ow_hi = min((w + g.pl) / g.sw, g.OW - 1);
-    for (int oh = oh_hi; oh >= 0; --oh) {
+    const int oh_hi = (h + g.pt) / g.sh, ow_hi = (w + g.pl) / g.sw;
+#pragma unroll
+    for (int ia = 0; ia < (MH ? MH : mh); ++ia) {
+      const int oh = oh_hi - ia;
       const int dh = h + g.pt - oh * g.sh;
-      if (dh >= g.PH) break;
-      for (int ow = ow_hi; ow >= 0; --ow) {
+      if (oh < 0 || oh >= g.OH || dh >= g.PH) continue;
+#pragma unroll
+      for (int ib = 0; ib < (MW ? MW : mw); ++ib) {
+        const int ow = ow_hi - ib;
         const int dw = w + g.pl - ow * g.sw;
-        if (dw >= g.PW) break;
+        if (ow < 0 || ow >= g.OW || dw >= g.PW) continue;
         const size_t off = ((size_t(n) * g.OH + oh) * g.OW + ow) * g.C + c8 * 8;
         const uint2 pk = *reinterpret_cast<const uint2*>(idx + off);
         Vec8<T> v;
@@ -485,15 +508,19 @@ __global__ void affine_act_kernel(const T* __restrict__ x, size_t P, int C, cons
                                   const float* __restrict__ b, int relu, T* __restrict__ y) {
   const int C8 = C >> 3;
   const size_t total = P * C8;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int c8 = int(i % C8);
+  const size_t tid = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  const int c8 = int(tid % C8);  // constant along the loop (fixed_channel_grid)
+  float av[8], bv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { av[k] = a ? a[c8 * 8 + k] : 1.f; bv[k] = a ? b[c8 * 8 + k] : 0.f; }
+  for (size_t i = tid; i < total; i += size_t(gridDim.x) * blockDim.x) {
     Vec8<T> v;
     v.load(x + i * 8);
     float f[8];
     v.to_float(f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float z = a ? fmaf(a[c8 * 8 + k], f[k], b[c8 * 8 + k]) : f[k];
+      float z = fmaf(av[k], f[k], bv[k]);
       if (relu) z = fmaxf(z, 0.f);
       f[k] = z;
     }
@@ -557,7 +584,8 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
   }
 }
 
-// dx = a * (dz - db/P - xhat * dg/P); also emits dg, db (fp32, scaled by 1/grad_scale) once.
+// dx = a * (dz - db/P - xhat * dg/P) = A*dz - D*x + E with the per-channel constants
+//   A = a = g/sigma,  D = a*dg/(P*sigma),  E = mu*D - a*db/P     (held in registers per thread).
 template <typename T>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, size_t P, int C,
                                     const float* __restrict__ moments, const float* __restrict__ a,
@@ -565,9 +593,21 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
                                     T* __restrict__ dx) {
   const int C8 = C >> 3;
   const size_t total = P * C8;
-  const float invP = 1.f / float(P);
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int c8 = int(i % C8);
+  const size_t tid = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  const int c8 = int(tid % C8);  // constant along the loop (fixed_channel_grid)
+  float A[8], B[8], D[8], E[8];
+  const double invP = 1.0 / double(P);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = c8 * 8 + k;
+    const double av = double(a[c]), mu = double(moments[c]), sg = double(moments[C + c]);
+    const double d = av * acc[C + c] * invP / sg;
+    A[k] = float(av);
+    B[k] = b[c];
+    D[k] = float(d);
+    E[k] = float(mu * d - av * acc[c] * invP);
+  }
+  for (size_t i = tid; i < total; i += size_t(gridDim.x) * blockDim.x) {
     Vec8<T> vx, vd;
     vx.load(x + i * 8);
     vd.load(dy + i * 8);
@@ -576,12 +616,9 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
     vd.to_float(fd);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int c = c8 * 8 + k;
-      const float av = a[c], bv = b[c];
       float dz = fd[k];
-      if (relu_mask && !(fmaf(av, fx[k], bv) > 0.f)) dz = 0.f;
-      const float xhat = (fx[k] - moments[c]) / moments[C + c];
-      fd[k] = av * (dz - float(acc[c]) * invP - xhat * float(acc[C + c]) * invP);
+      if (relu_mask && !(fmaf(A[k], fx[k], B[k]) > 0.f)) dz = 0.f;
+      fd[k] = fmaf(A[k], dz, fmaf(-D[k], fx[k], E[k]));
     }
     vd.from_float(fd);
     vd.store(dx + i * 8);
@@ -622,17 +659,30 @@ __global__ void relu_bwd_kernel(const T* __restrict__ y, const T* __restrict__ d
 // ============================================================================================
 template <typename T>
 __global__ void se_squeeze_kernel(const T* __restrict__ u, int HW, int C, float* __restrict__ s) {
-  // grid: (C/8/32 chunks, N); block 32 x 8: lane -> channel group, y -> pixel stride
+  // grid: (ceil(C/8/32), N); block 32 x 32: lane -> channel group, y -> pixel stride (4 loads in flight)
   const int n = blockIdx.y;
   const int c8 = blockIdx.x * 32 + threadIdx.x;
-  __shared__ float part[8][32][8];
+  __shared__ float part[32][32][9];
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   if (c8 * 8 < C) {
-    for (int p = threadIdx.y; p < HW; p += 8) {
+    const T* base = u + size_t(n) * HW * C + c8 * 8;
+    int p = threadIdx.y;
+    for (; p + 96 < HW; p += 128) {
+      Vec8<T> v0, v1, v2, v3;
+      v0.load(base + size_t(p) * C);
+      v1.load(base + size_t(p + 32) * C);
+      v2.load(base + size_t(p + 64) * C);
+      v3.load(base + size_t(p + 96) * C);
+      float f0[8], f1[8], f2[8], f3[8];
+      v0.to_float(f0); v1.to_float(f1); v2.to_float(f2); v3.to_float(f3);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += (f0[k] + f1[k]) + (f2[k] + f3[k]);
+    }
+    for (; p < HW; p += 32) {
       Vec8<T> v;
-      v.load(u + (size_t(n) * HW + p) * C + c8 * 8);
+      v.load(base + size_t(p) * C);
       float f[8];
       v.to_float(f);
 #pragma unroll
@@ -642,19 +692,24 @@ __global__ void se_squeeze_kernel(const T* __restrict__ u, int HW, int C, float*
 #pragma unroll
   for (int k = 0; k < 8; ++k) part[threadIdx.y][threadIdx.x][k] = acc[k];
   __syncthreads();
-  if (threadIdx.y == 0 && c8 * 8 < C) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float t = 0.f;
-      for (int j = 0; j < 8; ++j) t += part[j][threadIdx.x][k];
-      s[size_t(n) * C + c8 * 8 + k] = t / float(HW);
+  // 32 x 8 (channel-group, k) outputs, each summed over the 32 pixel strides by one thread
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 256) {
+    const int cg = t >> 3, k = t & 7;
+    const int c = (blockIdx.x * 32 + cg) * 8 + k;
+    if (c < C) {
+      float tsum = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) tsum += part[j][cg][k];
+      s[size_t(n) * C + c] = tsum / float(HW);
     }
   }
 }
 
-// one block (256 threads) per sample.  w1: [Cr][C] fp32, w2: [C][Cr] fp32.
+// one block (256 threads) per sample.  w1: [Cr][C] fp32, w2t: [Cr][C] fp32 (the second FC transposed so
+// that consecutive threads read consecutive addresses).
 static __global__ void se_gate_kernel(const float* __restrict__ s, int C, int Cr, const float* __restrict__ w1,
-                               const float* __restrict__ b1, const float* __restrict__ w2,
+                               const float* __restrict__ b1, const float* __restrict__ w2t,
                                const float* __restrict__ b2, float* __restrict__ gate) {
   extern __shared__ float sm[];
   float* sv = sm;        // [C]
@@ -672,7 +727,7 @@ static __global__ void se_gate_kernel(const float* __restrict__ s, int C, int Cr
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float t = b2 ? b2[c] : 0.f;
-    for (int j = 0; j < Cr; ++j) t = fmaf(w2[size_t(c) * Cr + j], hid[j], t);
+    for (int j = 0; j < Cr; ++j) t = fmaf(w2t[size_t(j) * C + c], hid[j], t);
     gate[size_t(n) * C + c] = 1.f / (1.f + __expf(-t));
   }
 }

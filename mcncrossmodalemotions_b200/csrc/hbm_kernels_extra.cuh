@@ -271,8 +271,12 @@ __global__ void bn_bwd_test_kernel(const T* __restrict__ x, const T* __restrict_
                                    T* __restrict__ dx) {
   const int C8 = C >> 3;
   const size_t total = P * C8;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int c8 = int(i % C8);
+  const size_t tid = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  const int c8 = int(tid % C8);  // constant along the loop (fixed_channel_grid)
+  float av[8], bv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { av[k] = a[c8 * 8 + k]; bv[k] = b[c8 * 8 + k]; }
+  for (size_t i = tid; i < total; i += size_t(gridDim.x) * blockDim.x) {
     Vec8<T> vx, vd;
     vx.load(x + i * 8);
     vd.load(dy + i * 8);
@@ -281,10 +285,9 @@ __global__ void bn_bwd_test_kernel(const T* __restrict__ x, const T* __restrict_
     vd.to_float(fd);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float av = a[c8 * 8 + k], bv = b[c8 * 8 + k];
       float dz = fd[k];
-      if (relu_mask && !(fmaf(av, fx[k], bv) > 0.f)) dz = 0.f;
-      fd[k] = av * dz;
+      if (relu_mask && !(fmaf(av[k], fx[k], bv[k]) > 0.f)) dz = 0.f;
+      fd[k] = av[k] * dz;
     }
     vd.from_float(fd);
     vd.store(dx + i * 8);

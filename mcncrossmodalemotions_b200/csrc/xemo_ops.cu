@@ -355,13 +355,14 @@ extern "C" int xemo_op_maxpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H,
   PoolGeom g;
   XEMO_REQUIRE(ctx, x16 && y16 && pool_geom(&g, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr), "maxpool_fwd: bad geometry");
   const size_t total = size_t(N) * g.OH * g.OW * (C / 8);
-  const int grid = grid_for(total, 256, ctx->num_sms, 16);
-  if (a)
-    maxpool_fwd_kernel<__half, true><<<grid, 256, 0, ctx->stream>>>(static_cast<const __half*>(x16), g, a, b,
-                                                                  static_cast<__half*>(y16), argmax);
-  else
-    maxpool_fwd_kernel<__half, false><<<grid, 256, 0, ctx->stream>>>(static_cast<const __half*>(x16), g, nullptr, nullptr,
-                                                                   static_cast<__half*>(y16), argmax);
+  const int grid = fixed_channel_grid(total, C / 8, 256, ctx->num_sms, 8);
+  const __half* xp = static_cast<const __half*>(x16);
+  __half* yp = static_cast<__half*>(y16);
+#define XEMO_POOL_FWD(AFF, PHc, PWc) maxpool_fwd_kernel<__half, AFF, PHc, PWc><<<grid, 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax)
+  if (PH == 3 && PW == 3) { if (a) XEMO_POOL_FWD(true, 3, 3); else XEMO_POOL_FWD(false, 3, 3); }
+  else if (PH == 5 && PW == 3) { if (a) XEMO_POOL_FWD(true, 5, 3); else XEMO_POOL_FWD(false, 5, 3); }
+  else { if (a) XEMO_POOL_FWD(true, 0, 0); else XEMO_POOL_FWD(false, 0, 0); }
+#undef XEMO_POOL_FWD
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }
@@ -372,8 +373,11 @@ extern "C" int xemo_op_maxpool_bwd(xemo_ctx* ctx, const void* dy16, const uint8_
   XEMO_REQUIRE(ctx, dy16 && argmax && dx16 && pool_geom(&g, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr),
                "maxpool_bwd: bad geometry");
   const size_t total = size_t(N) * H * W * (C / 8);
-  maxpool_bwd_kernel<__half><<<grid_for(total, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
-      static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
+  const int grid = grid_for(total, 256, ctx->num_sms, 8);
+  if ((PH + sh - 1) / sh == 2 && (PW + sw - 1) / sw == 2)
+    maxpool_bwd_kernel<__half, 2, 2><<<grid, 256, 0, ctx->stream>>>(static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
+  else
+    maxpool_bwd_kernel<__half, 0, 0><<<grid, 256, 0, ctx->stream>>>(static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }
@@ -434,7 +438,7 @@ extern "C" int xemo_op_bn_test(xemo_ctx* ctx, const float* moments, int C, const
 extern "C" int xemo_op_affine_act(xemo_ctx* ctx, const void* x16, size_t P, int C, const float* a, const float* b, int relu,
                                   void* y16) {
   XEMO_REQUIRE(ctx, x16 && y16 && C % 8 == 0, "affine_act: bad arguments");
-  affine_act_kernel<__half><<<grid_for(P * (C / 8), 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
+  affine_act_kernel<__half><<<fixed_channel_grid(P * (C / 8), C / 8, 256, ctx->num_sms, 8), 256, 0, ctx->stream>>>(
       static_cast<const __half*>(x16), P, C, a, b, relu, static_cast<__half*>(y16));
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
@@ -452,7 +456,7 @@ extern "C" int xemo_op_bn_bwd(xemo_ctx* ctx, const void* x16, const void* dy16, 
   dim3 grid(bg.slabs_x, bg.slabs_y);
   bn_bwd_reduce_kernel<__half><<<grid, kBnThreads, 0, ctx->stream>>>(x, dy, P, C, bg.lanes, bg.rows_par, moments, a, b, relu_mask, ws);
   XEMO_LAUNCHED(ctx, 1);
-  const int egrid = grid_for(P * C8, 256, ctx->num_sms, 16);
+  const int egrid = fixed_channel_grid(P * C8, C8, 256, ctx->num_sms, 8);
   if (test_mode)
     bn_bwd_test_kernel<__half><<<egrid, 256, 0, ctx->stream>>>(x, dy, P, C, a, b, relu_mask, static_cast<__half*>(dx16));
   else
@@ -486,7 +490,7 @@ extern "C" int xemo_op_add_act(xemo_ctx* ctx, const void* a16, const void* b16, 
 // squeeze-and-excitation
 extern "C" int xemo_op_se_squeeze(xemo_ctx* ctx, const void* u16, int N, int HW, int C, float* s) {
   XEMO_REQUIRE(ctx, u16 && s && C % 8 == 0, "se_squeeze: bad arguments");
-  dim3 grid((C / 8 + 31) / 32, N), block(32, 8);
+  dim3 grid((C / 8 + 31) / 32, N), block(32, 32);
   se_squeeze_kernel<__half><<<grid, block, 0, ctx->stream>>>(static_cast<const __half*>(u16), HW, C, s);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;

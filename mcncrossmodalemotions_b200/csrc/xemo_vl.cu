@@ -212,7 +212,7 @@ extern "C" int xemo_vl_nnpool(xemo_ctx* ctx, const xemo_array* x, const int pool
   const size_t out8 = size_t(N) * OH * OW * (Cp / 8), in8 = size_t(N) * H * W * (Cp / 8);
   const bool backward = dzdy && dzdy->data;
   if (method == 0) {
-    maxpool_fwd_kernel<float, false><<<grid_for(out8, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(xn, g, nullptr, nullptr, yn, idx);
+    maxpool_fwd_kernel<float, false, 0, 0><<<fixed_channel_grid(out8, Cp / 8, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(xn, g, nullptr, nullptr, yn, idx);
     XEMO_LAUNCHED(ctx, 1);
   } else if (!backward) {
     avgpool_fwd_kernel<float><<<grid_for(out8, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(xn, g, yn);
@@ -242,7 +242,7 @@ extern "C" int xemo_vl_nnpool(xemo_ctx* ctx, const xemo_array* x, const int pool
   if (ar.failed) return ar.finish();
   if ((rc = xemo_op_hwcn_to_nhwc(ctx, dyd, OH, OW, C, N, dyn, Cp, 1))) return rc;
   if (method == 0)
-    maxpool_bwd_kernel<float><<<grid_for(in8, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(dyn, idx, g, dxn);
+    maxpool_bwd_kernel<float, 0, 0><<<grid_for(in8, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(dyn, idx, g, dxn);
   else
     avgpool_bwd_kernel<float><<<grid_for(in8, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(dyn, g, dxn);
   XEMO_LAUNCHED(ctx, 1);
@@ -288,7 +288,7 @@ extern "C" int xemo_vl_nnbnorm(xemo_ctx* ctx, const xemo_array* x, const float* 
     XEMO_LAUNCHED(ctx, 1);
   }
   const int C8 = Cp / 8;
-  const int egrid = grid_for(P * C8, 256, ctx->num_sms, 16);
+  const int egrid = fixed_channel_grid(P * C8, C8, 256, ctx->num_sms, 16);
   if (!dzdy || !dzdy->data) {
     affine_act_kernel<float><<<egrid, 256, 0, ctx->stream>>>(xn, P, Cp, av, bv, 0, outn);
     XEMO_LAUNCHED(ctx, 1);

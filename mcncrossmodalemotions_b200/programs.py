@@ -175,7 +175,7 @@ class TeacherProgram(_Base):
                 if self.arch == "senet50":
                     W[pre + "se1"] = self.upload(p[pre + "se1f"][0, 0].T)  # [Cr][C]
                     W[pre + "se1b"] = self.upload(p[pre + "se1b"])
-                    W[pre + "se2"] = self.upload(p[pre + "se2f"][0, 0].T)  # [C][Cr]
+                    W[pre + "se2"] = self.upload(p[pre + "se2f"][0, 0])  # [Cr][C]: W2 transposed (coalesced reads)
                     W[pre + "se2b"] = self.upload(p[pre + "se2b"])
                 self.blocks.append((pre, cin, mid, cout, stride if bi == 0 else 1, bi == 0))
                 cin = cout
