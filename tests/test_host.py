@@ -149,3 +149,18 @@ def test_two_rank_gradient_sum_gloo(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_mex_shims_compile_against_stub_header():
+    """The MEX shims are source-only (no MATLAB in the image): keep them syntactically valid against mex_stub.h."""
+    import glob
+    import shutil
+
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    shims = sorted(glob.glob(os.path.join(ROOT, "mex", "*_mex.c")))
+    assert len(shims) >= 3
+    for f in shims:
+        r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wno-unused-function", "-DXEMO_MEX_STUB", "-I" + os.path.join(ROOT, "include"),
+                            "-I" + os.path.join(ROOT, "mex"), f], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
