@@ -171,7 +171,11 @@ int xemo_op_avgpool_bwd(xemo_ctx* ctx, const void* dy16, int N, int H, int W, in
  * bn_train: batch statistics -> moments[2C] = [mu | sigma], a = g/sigma, b = beta - a*mu (ws: 2C doubles).
  * bn_test : a, b from given moments.  affine_act: y = a*x + b (+ReLU).
  * bn_bwd  : dz = dy*[a*x+b > 0] (relu_mask); dg = sum dz*xhat, db = sum dz (scaled by inv_grad_scale, fp32);
- *           dx = a*(dz - db/P - xhat*dg/P)  (train)  or  a*dz  (test_mode). */
+ *           dx = a*(dz - db/P - xhat*dg/P)  (train)  or  a*dz  (test_mode).  dconv_bias (optional, train mode,
+ *           C <= 8192) receives inv_grad_scale * sum_rows dx: the bias gradient of the convolution feeding the BN.
+ * bn_bwd_pool: the same for a BN+ReLU followed by a max pool whose windows overlap at most 2 x 2: dz is gathered
+ *           from the POOLED gradient dpool16 [N][OH][OW][C] through the recorded arg-max, so that the
+ *           full-resolution gradient is never materialised between the pooling and the BN backward. */
 int xemo_op_bn_train(xemo_ctx* ctx, const void* x16, size_t P, int C, const float* g, const float* beta, float eps,
                      double* ws, float* moments, float* a, float* b);
 int xemo_op_bn_test(xemo_ctx* ctx, const float* moments, int C, const float* g, const float* beta, float* a, float* b);
@@ -179,7 +183,11 @@ int xemo_op_affine_act(xemo_ctx* ctx, const void* x16, size_t P, int C, const fl
                        void* y16);
 int xemo_op_bn_bwd(xemo_ctx* ctx, const void* x16, const void* dy16, size_t P, int C, const float* moments,
                    const float* a, const float* b, int relu_mask, int test_mode, double* ws, void* dx16, float* dg,
-                   float* db, float inv_grad_scale);
+                   float* db, float* dconv_bias, float inv_grad_scale);
+int xemo_op_bn_bwd_pool(xemo_ctx* ctx, const void* x16, const void* dpool16, const uint8_t* argmax, int N, int H, int W,
+                        int C, int PH, int PW, int sh, int sw, int pt, int pb, int pl, int pr, const float* moments,
+                        const float* a, const float* b, double* ws, void* dx16, float* dg, float* db, float* dconv_bias,
+                        float inv_grad_scale);
 int xemo_op_relu_bwd(xemo_ctx* ctx, const void* y16, const void* dy16, size_t n, void* dx16);
 int xemo_op_add_act(xemo_ctx* ctx, const void* a16, const void* b16, size_t n, int relu, void* y16);
 

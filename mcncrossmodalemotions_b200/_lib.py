@@ -80,7 +80,8 @@ SIGNATURES = {
     "xemo_op_bn_test": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "xemo_op_affine_act": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "xemo_op_bn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
-                               c_void_p, c_void_p, c_void_p, c_float]),
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_float]),
+    "xemo_op_bn_bwd_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 12 + [c_void_p] * 8 + [c_float]),
     "xemo_op_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "xemo_op_add_act": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "xemo_op_se_squeeze": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

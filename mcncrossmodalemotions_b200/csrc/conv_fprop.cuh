@@ -14,20 +14,25 @@
 //   B (filters)     : [Kout][R][S][C] fp16 (K-major), fetched by tiled TMA, same swizzle.
 //   D (accumulator) : fp32 in TMEM, 128 lanes x block_n columns, double-buffered (2 x 256 columns) so
 //                     the epilogue of tile i overlaps the main loop of tile i+1.
-// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (320 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0   : TMA producer (one elected lane)
 //   warp 1   : tcgen05.mma issuer (one elected lane)
-//   warps 2-5: epilogue -- tcgen05.ld, per-channel scale/shift (folded test-mode BN or bias), optional
-//              residual add, optional ReLU; fp16 tile staged in swizzled smem and written with TMA
-//              stores (residual tiles prefetched with TMA loads), or stored directly (fp32 / strided
-//              outputs).  Warp 2 also owns TMEM alloc/free.
+//   warps 2-9: epilogue, as two independent groups of four warps (one warp per TMEM lane quadrant) that
+//              take alternate column chunks of the accumulator tiles: tcgen05.ld, per-channel
+//              scale/shift (folded test-mode BN or bias, staged in smem), optional residual add,
+//              optional ReLU; fp16 chunk staged in swizzled smem and written with a TMA store (residual
+//              chunks prefetched with TMA loads), or stored directly (fp32 / strided outputs).  While
+//              one group waits for its residual / drains its store the other one computes, which is
+//              what the HBM-bound 1x1 layers (K = 64: one MMA k-block per 128 x 256 tile) need.
+//              Warp 2 also owns TMEM alloc/free.
 #pragma once
 #include "xemo_ptx.cuh"
 
 namespace xemo {
 
 constexpr int kConvBlockM = 128;
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;
+constexpr int kEpiGroups = 2;
 constexpr int kConvTmemCols = 512;
 constexpr int kEpiStageBytes = kConvBlockM * 64 * 2;  // one [128 x 64] fp16 staging tile
 
@@ -81,7 +86,7 @@ __device__ __forceinline__ uint32_t swz_off(int row, int chunk, int pitch, uint3
   return off ^ (((off >> 7) & mask) << 4);
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 
 template <int BK>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -97,9 +102,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int stage_bytes = conv_stage_bytes(BK, p.block_n);
   const int num_stages = p.num_stages;
 
-  uint8_t* epi_store_buf = smem + size_t(num_stages) * stage_bytes;                  // 2 x 16 KB (if used)
-  uint8_t* epi_res_buf = epi_store_buf + (p.use_tma_store ? 2 * kEpiStageBytes : 0); // 2 x 16 KB (if used)
+  uint8_t* epi_store_buf = smem + size_t(num_stages) * stage_bytes;                  // one 16 KB buffer per group (if used)
+  uint8_t* epi_res_buf = epi_store_buf + (p.use_tma_store ? 2 * kEpiStageBytes : 0); // one 16 KB buffer per group (if used)
   uint8_t* after = epi_res_buf + (p.use_tma_residual ? 2 * kEpiStageBytes : 0);
+  float* epi_ss = reinterpret_cast<float*>(after);                                   // [group][scale | shift][64]
+  after += kEpiGroups * 2 * 64 * sizeof(float);
   uint64_t* bars = reinterpret_cast<uint64_t*>(after);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + num_stages;
@@ -122,7 +129,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], 4 * kEpiGroups);  // one arrive per epilogue warp
       mbar_init(&res_bar[a], 1);
     }
     fence_barrier_init();
@@ -208,29 +215,42 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps 2..5
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------------------------------------ epilogue warps 2..9 (two groups)
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int group = (warp - 2) >> 2;    // 0: warps 2-5, 1: warps 6-9
+    const int tg = int(threadIdx.x) - 64 - group * 128;  // thread index inside the group
     const int row_in_tile = quad * 32 + lane;
-    const bool leader = (threadIdx.x == 64);  // warp 2, lane 0
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    uint32_t chunk_ctr = 0;  // staging-chunk counter across tiles (buffer = ctr & 1)
+    const bool leader = (tg == 0);
     const int cw = p.epi_cw;
     const int chunks_per_tile = p.block_n / cw;
     const int pitch = cw * 2;
     const uint32_t swz_mask = (cw == 64) ? 7u : (cw == 32) ? 3u : 1u;
     const uint32_t chunk_bytes = uint32_t(kConvBlockM) * uint32_t(pitch);
     const int ohw = p.OH * p.OW;
+    uint8_t* sbuf = epi_store_buf + group * kEpiStageBytes;
+    uint8_t* rbuf = epi_res_buf + group * kEpiStageBytes;
+    float* ss_scale = epi_ss + group * 128;
+    float* ss_shift = ss_scale + 64;
+    uint64_t* rbar = &res_bar[group];
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t mine = 0;  // chunks this group has processed (phase of its residual barrier)
 
-    // prefetch the residual chunk for the first tile of this CTA
-    if (p.use_tma_residual && leader && int(blockIdx.x) < num_tiles) {
-      const int m_tile = blockIdx.x / p.num_n_tiles;
-      const int n_tile = blockIdx.x - m_tile * p.num_n_tiles;
-      mbar_arrive_expect_tx(&res_bar[0], chunk_bytes);
-      tma_load_2d(&tmRes, &res_bar[0], epi_res_buf, n_tile * p.block_n, m_tile * kConvBlockM);
-    }
+    // residual chunk `G` (global chunk index of this CTA: tile_iter * chunks_per_tile + q) -> TMA prefetch
+    auto prefetch_residual = [&](long long G) {
+      const long long titer = G / chunks_per_tile;
+      const int q = int(G - titer * chunks_per_tile);
+      const long long tile = (long long)blockIdx.x + titer * gridDim.x;
+      if (tile >= num_tiles) return;
+      const int nm = int(tile / p.num_n_tiles);
+      const int nn = int(tile - (long long)nm * p.num_n_tiles);
+      mbar_arrive_expect_tx(rbar, chunk_bytes);
+      tma_load_2d(&tmRes, rbar, rbuf, nn * p.block_n + q * cw, nm * kConvBlockM);
+    };
+    if (p.use_tma_residual && leader) prefetch_residual(group);
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    long long G0 = 0;  // global chunk index of chunk 0 of the current tile
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, G0 += chunks_per_tile) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int m0 = m_tile * kConvBlockM;
@@ -251,29 +271,15 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         row_off = size_t(row) * p.ldc + n0;
       }
 
-      for (int q = 0; q < chunks_per_tile; ++q, ++chunk_ctr) {
-        const uint32_t buf = chunk_ctr & 1u;
-        uint8_t* sbuf = epi_store_buf + buf * kEpiStageBytes;
-        uint8_t* rbuf = epi_res_buf + buf * kEpiStageBytes;
-        if (p.use_tma_store) {
-          // the TMA store that last read this staging buffer (two chunks ago) must have drained it
-          if (leader) tma_store_wait_read<1>();
+      for (int q = int((group + 2 - (G0 & 1)) & 1); q < chunks_per_tile; q += 2, ++mine) {
+        // the TMA store that last read this group's staging buffer must have drained it
+        if (p.use_tma_store && leader) tma_store_wait_read<0>();
+        if (tg < cw) {
+          ss_scale[tg] = p.scale ? __ldg(p.scale + n0 + q * cw + tg) : 1.f;
+          ss_shift[tg] = p.shift ? __ldg(p.shift + n0 + q * cw + tg) : 0.f;
         }
-        if (p.use_tma_residual && leader) {
-          // prefetch the next residual chunk (next chunk of this tile, or first chunk of the next tile)
-          int nq = q + 1, ntile = tile;
-          if (nq == chunks_per_tile) { nq = 0; ntile = tile + gridDim.x; }
-          if (ntile < num_tiles) {
-            const int nm = ntile / p.num_n_tiles;
-            const int nn = ntile - nm * p.num_n_tiles;
-            const uint32_t nbuf = (chunk_ctr + 1) & 1u;
-            mbar_arrive_expect_tx(&res_bar[nbuf], chunk_bytes);
-            tma_load_2d(&tmRes, &res_bar[nbuf], epi_res_buf + nbuf * kEpiStageBytes, nn * p.block_n + nq * cw,
-                        nm * kConvBlockM);
-          }
-        }
-        if (p.use_tma_store) epi_bar_sync();  // staging buffer `buf` is free for everyone
-        if (p.use_tma_residual) mbar_wait(&res_bar[buf], (chunk_ctr >> 1) & 1u);
+        epi_bar_sync(group);  // staging buffer free, scale/shift visible
+        if (p.use_tma_residual) mbar_wait(rbar, mine & 1u);
 
         for (int jj = 0; jj < cw; jj += 16) {
           const int j = q * cw + jj;  // column inside the tile
@@ -282,20 +288,13 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld_wait();
           float x[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
-          if (p.scale) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + j + i));
-              x[i] *= sc.x; x[i + 1] *= sc.y; x[i + 2] *= sc.z; x[i + 3] *= sc.w;
-            }
-          }
-          if (p.shift) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + j + i));
-              x[i] += sh.x; x[i + 1] += sh.y; x[i + 2] += sh.z; x[i + 3] += sh.w;
-            }
+          for (int i = 0; i < 16; i += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(ss_scale + jj + i);
+            const float4 sh = *reinterpret_cast<const float4*>(ss_shift + jj + i);
+            x[i] = fmaf(__uint_as_float(v[i]), sc.x, sh.x);
+            x[i + 1] = fmaf(__uint_as_float(v[i + 1]), sc.y, sh.y);
+            x[i + 2] = fmaf(__uint_as_float(v[i + 2]), sc.z, sh.z);
+            x[i + 3] = fmaf(__uint_as_float(v[i + 3]), sc.w, sh.w);
           }
           if (p.residual) {
 #pragma unroll
@@ -343,11 +342,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if (p.use_tma_store) {
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-          epi_bar_sync();
+          epi_bar_sync(group);       // chunk complete in sbuf; everyone is done with rbuf / scale / shift
           if (leader) {
             tma_store_2d(&tmOut, sbuf, n0 + q * cw, m0);  // rows beyond M are clipped by the tensor map
             tma_store_commit();
+            if (p.use_tma_residual) prefetch_residual(G0 + q + 2);
           }
+        } else {
+          epi_bar_sync(group);       // scale / shift may be overwritten by the next chunk
         }
       }
       tc_fence_before();

@@ -231,19 +231,22 @@ template <typename T, bool kAffineRelu, int PHc, int PWc>
 __global__ void maxpool_fwd_kernel(const T* __restrict__ x, PoolGeom g, const float* __restrict__ a,
                                    const float* __restrict__ b, T* __restrict__ y, uint8_t* __restrict__ idx) {
   const int PH = PHc ? PHc : g.PH, PW = PWc ? PWc : g.PW;
-  const int C8 = g.C >> 3;
-  const size_t total = size_t(g.N) * g.OH * g.OW * C8;
-  const size_t tid = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
-  const int c8 = int(tid % C8);  // constant along the grid-stride loop (fixed_channel_grid)
+  // 32-bit index arithmetic: thread -> fixed channel group c8, grid-stride loop over output pixels
+  const uint32_t C8 = uint32_t(g.C >> 3);
+  const uint32_t npix = uint32_t(g.N) * uint32_t(g.OH) * uint32_t(g.OW);
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c8 = tid % C8;  // constant along the loop (fixed_channel_grid)
+  const uint32_t pstride = (gridDim.x * blockDim.x) / C8;
   float av[8], bv[8];
   if (kAffineRelu) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) { av[k] = a[c8 * 8 + k]; bv[k] = b[c8 * 8 + k]; }
   }
-  for (size_t i = tid; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int ow = int((i / C8) % g.OW);
-    const int oh = int((i / (size_t(C8) * g.OW)) % g.OH);
-    const int n = int(i / (size_t(C8) * g.OW * g.OH));
+  for (uint32_t pp = tid / C8; pp < npix; pp += pstride) {
+    const uint32_t t1 = pp / uint32_t(g.OW);
+    const int ow = int(pp - t1 * uint32_t(g.OW));
+    const int n = int(t1 / uint32_t(g.OH));
+    const int oh = int(t1 - uint32_t(n) * uint32_t(g.OH));
     float best[8];
     uint8_t arg[8];
 #pragma unroll
@@ -264,9 +267,9 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, PoolGeom g, const fl
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           float z = f[k];
-          // round through the storage type so that the value compared here is exactly what a
-          // separate bn+relu pass would have stored
-          if (kAffineRelu) z = round_to<T>(fmaxf(fmaf(av[k], z, bv[k]), 0.f));
+          // the window maximum is taken over the fp32 normalised activations (as the CPU path does) and
+          // rounded once on store; ties -- the all-zero windows ReLU produces -- stay exact ties
+          if (kAffineRelu) z = fmaxf(fmaf(av[k], z, bv[k]), 0.f);
           if (z > best[k]) { best[k] = z; arg[k] = uint8_t(dw * PH + dh); }
         }
       }
@@ -290,14 +293,17 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, PoolGeom g, const fl
 template <typename T, int MH, int MW>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, PoolGeom g,
                                    T* __restrict__ dx) {
-  const int C8 = g.C >> 3;
-  const size_t total = size_t(g.N) * g.H * g.W * C8;
+  const uint32_t C8 = uint32_t(g.C >> 3);
+  const uint32_t npix = uint32_t(g.N) * uint32_t(g.H) * uint32_t(g.W);
   const int mh = MH ? MH : (g.PH + g.sh - 1) / g.sh, mw = MW ? MW : (g.PW + g.sw - 1) / g.sw;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int c8 = int(i % C8);
-    const int w = int((i / C8) % g.W);
-    const int h = int((i / (size_t(C8) * g.W)) % g.H);
-    const int n = int(i / (size_t(C8) * g.W * g.H));
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c8 = tid % C8;  // constant along the loop (fixed_channel_grid)
+  const uint32_t pstride = (gridDim.x * blockDim.x) / C8;
+  for (uint32_t pp = tid / C8; pp < npix; pp += pstride) {
+    const uint32_t t1 = pp / uint32_t(g.W);
+    const int w = int(pp - t1 * uint32_t(g.W));
+    const int n = int(t1 / uint32_t(g.H));
+    const int h = int(t1 - uint32_t(n) * uint32_t(g.H));
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
@@ -529,12 +535,50 @@ __global__ void affine_act_kernel(const T* __restrict__ x, size_t P, int C, cons
   }
 }
 
-// backward reduce: acc[0..C) += sum dz ; acc[C..2C) += sum dz * xhat, xhat = (x - mu)/sigma.
-// dz = dy * [a*x+b > 0] when relu_mask.  Same block layout as bn_stats_kernel.
+// dz of one (n, h, w, channel-group) position gathered through a max-pooling layer that follows the
+// BN+ReLU (the pooled tensor's gradient `dout` and the recorded arg-max): the sum over the (at most
+// 2 x 2) windows covering the position whose arg-max points at it.  Lets the BN backward read the
+// 4x smaller pooled gradient instead of a materialised full-resolution one.
 template <typename T>
+__device__ __forceinline__ void pool_gather8(const T* __restrict__ dout, const uint8_t* __restrict__ idx, const PoolGeom& g,
+                                             int n, int h, int w, int c8, float (&acc)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  const int oh_hi = (h + g.pt) / g.sh, ow_hi = (w + g.pl) / g.sw;
+#pragma unroll
+  for (int ia = 0; ia < 2; ++ia) {
+    const int oh = oh_hi - ia;
+    const int dh = h + g.pt - oh * g.sh;
+    if (oh < 0 || oh >= g.OH || dh >= g.PH) continue;
+#pragma unroll
+    for (int ib = 0; ib < 2; ++ib) {
+      const int ow = ow_hi - ib;
+      const int dw = w + g.pl - ow * g.sw;
+      if (ow < 0 || ow >= g.OW || dw >= g.PW) continue;
+      const size_t off = ((size_t(n) * g.OH + oh) * g.OW + ow) * g.C + c8 * 8;
+      const uint2 pk = *reinterpret_cast<const uint2*>(idx + off);
+      Vec8<T> v;
+      v.load(dout + off);
+      float f[8];
+      v.to_float(f);
+      const uint32_t me = uint32_t(dw * g.PH + dh);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t am = ((k < 4 ? pk.x : pk.y) >> (8 * (k & 3))) & 0xFF;
+        if (am == me) acc[k] += f[k];
+      }
+    }
+  }
+}
+
+// backward reduce: acc[0..C) += sum dz ; acc[C..2C) += sum dz * xhat, xhat = (x - mu)/sigma.
+// dz = dy * [a*x+b > 0] when relu_mask.  Same block layout as bn_stats_kernel.  kPool: dy is gathered
+// through the following max-pooling layer (dy = pooled gradient, idx = its arg-max, g = pool geometry).
+template <typename T, bool kPool>
 __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, size_t P, int C, int lanes,
                                      int rows_par, const float* __restrict__ moments, const float* __restrict__ a,
-                                     const float* __restrict__ b, int relu_mask, double* __restrict__ acc) {
+                                     const float* __restrict__ b, int relu_mask, double* __restrict__ acc,
+                                     const uint8_t* __restrict__ idx, PoolGeom g) {
   __shared__ float red[2][kBnThreads][8];
   const int C8 = C >> 3;
   const int rl = threadIdx.x / lanes;
@@ -555,12 +599,19 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
     }
     const size_t stride = size_t(gridDim.x) * rows_par;
     for (size_t r = size_t(blockIdx.x) * rows_par + rl; r < P; r += stride) {
-      Vec8<T> vx, vd;
+      Vec8<T> vx;
       vx.load(x + r * C + c8 * 8);
-      vd.load(dy + r * C + c8 * 8);
       float fx[8], fd[8];
       vx.to_float(fx);
-      vd.to_float(fd);
+      if (kPool) {
+        const uint32_t r32 = uint32_t(r);
+        const uint32_t t = r32 / uint32_t(g.W);
+        pool_gather8<T>(dy, idx, g, int(t / uint32_t(g.H)), int(t % uint32_t(g.H)), int(r32 - t * uint32_t(g.W)), c8, fd);
+      } else {
+        Vec8<T> vd;
+        vd.load(dy + r * C + c8 * 8);
+        vd.to_float(fd);
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float dz = fd[k];
@@ -586,16 +637,20 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
 
 // dx = a * (dz - db/P - xhat * dg/P) = A*dz - D*x + E with the per-channel constants
 //   A = a = g/sigma,  D = a*dg/(P*sigma),  E = mu*D - a*db/P     (held in registers per thread).
-template <typename T>
+// Optionally also accumulates colsum[c] += scale * sum_rows dx (the bias gradient of the convolution that
+// feeds this BN layer) so that no separate pass over dx is needed.
+template <typename T, bool kPool>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, size_t P, int C,
                                     const float* __restrict__ moments, const float* __restrict__ a,
                                     const float* __restrict__ b, int relu_mask, const double* __restrict__ acc,
-                                    T* __restrict__ dx) {
+                                    T* __restrict__ dx, const uint8_t* __restrict__ idx, PoolGeom g,
+                                    float* __restrict__ colsum, float colsum_scale) {
+  extern __shared__ float cs_smem[];  // [C] when colsum
   const int C8 = C >> 3;
   const size_t total = P * C8;
   const size_t tid = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   const int c8 = int(tid % C8);  // constant along the loop (fixed_channel_grid)
-  float A[8], B[8], D[8], E[8];
+  float A[8], B[8], D[8], E[8], cs[8];
   const double invP = 1.0 / double(P);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -606,14 +661,25 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
     B[k] = b[c];
     D[k] = float(d);
     E[k] = float(mu * d - av * acc[c] * invP);
+    cs[k] = 0.f;
+  }
+  if (colsum) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) cs_smem[c] = 0.f;
+    __syncthreads();
   }
   for (size_t i = tid; i < total; i += size_t(gridDim.x) * blockDim.x) {
     Vec8<T> vx, vd;
     vx.load(x + i * 8);
-    vd.load(dy + i * 8);
     float fx[8], fd[8];
     vx.to_float(fx);
-    vd.to_float(fd);
+    if (kPool) {
+      const uint32_t r32 = uint32_t(i / C8);
+      const uint32_t t = r32 / uint32_t(g.W);
+      pool_gather8<T>(dy, idx, g, int(t / uint32_t(g.H)), int(t % uint32_t(g.H)), int(r32 - t * uint32_t(g.W)), c8, fd);
+    } else {
+      vd.load(dy + i * 8);
+      vd.to_float(fd);
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float dz = fd[k];
@@ -622,6 +688,18 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
     }
     vd.from_float(fd);
     vd.store(dx + i * 8);
+    if (colsum) {
+      float fr[8];
+      vd.to_float(fr);  // sum what was actually stored
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[k] += fr[k];
+    }
+  }
+  if (colsum) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&cs_smem[c8 * 8 + k], cs[k]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(colsum + c, cs_smem[c] * colsum_scale);
   }
 }
 
@@ -720,6 +798,7 @@ static __global__ void se_gate_kernel(const float* __restrict__ s, int C, int Cr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int j = warp; j < Cr; j += nwarps) {
     float t = 0.f;
+#pragma unroll 8
     for (int c = lane; c < C; c += 32) t = fmaf(w1[size_t(j) * C + c], sv[c], t);
     t = warp_sum(t);
     if (lane == 0) hid[j] = fmaxf(t + (b1 ? b1[j] : 0.f), 0.f);
@@ -727,6 +806,7 @@ static __global__ void se_gate_kernel(const float* __restrict__ s, int C, int Cr
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float t = b2 ? b2[c] : 0.f;
+#pragma unroll 8
     for (int j = 0; j < Cr; ++j) t = fmaf(w2t[size_t(j) * C + c], hid[j], t);
     gate[size_t(n) * C + c] = 1.f / (1.f + __expf(-t));
   }

@@ -355,6 +355,7 @@ extern "C" int xemo_op_maxpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H,
   PoolGeom g;
   XEMO_REQUIRE(ctx, x16 && y16 && pool_geom(&g, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr), "maxpool_fwd: bad geometry");
   const size_t total = size_t(N) * g.OH * g.OW * (C / 8);
+  XEMO_REQUIRE(ctx, size_t(N) * g.OH * g.OW < (size_t(1) << 31), "maxpool_fwd: tensor too large for 32-bit pixel indices");
   const int grid = fixed_channel_grid(total, C / 8, 256, ctx->num_sms, 8);
   const __half* xp = static_cast<const __half*>(x16);
   __half* yp = static_cast<__half*>(y16);
@@ -373,7 +374,8 @@ extern "C" int xemo_op_maxpool_bwd(xemo_ctx* ctx, const void* dy16, const uint8_
   XEMO_REQUIRE(ctx, dy16 && argmax && dx16 && pool_geom(&g, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr),
                "maxpool_bwd: bad geometry");
   const size_t total = size_t(N) * H * W * (C / 8);
-  const int grid = grid_for(total, 256, ctx->num_sms, 8);
+  XEMO_REQUIRE(ctx, size_t(N) * H * W < (size_t(1) << 31), "maxpool_bwd: tensor too large for 32-bit pixel indices");
+  const int grid = fixed_channel_grid(total, C / 8, 256, ctx->num_sms, 8);
   if ((PH + sh - 1) / sh == 2 && (PW + sw - 1) / sw == 2)
     maxpool_bwd_kernel<__half, 2, 2><<<grid, 256, 0, ctx->stream>>>(static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
   else
@@ -444,30 +446,60 @@ extern "C" int xemo_op_affine_act(xemo_ctx* ctx, const void* x16, size_t P, int 
   return XEMO_OK;
 }
 
-extern "C" int xemo_op_bn_bwd(xemo_ctx* ctx, const void* x16, const void* dy16, size_t P, int C, const float* moments,
-                              const float* a, const float* b, int relu_mask, int test_mode, double* ws, void* dx16,
-                              float* dg, float* db, float inv_grad_scale) {
-  XEMO_REQUIRE(ctx, x16 && dy16 && moments && a && b && ws && dx16 && C % 8 == 0, "bn_bwd: bad arguments");
-  const __half* x = static_cast<const __half*>(x16);
-  const __half* dy = static_cast<const __half*>(dy16);
+// shared by xemo_op_bn_bwd (dy at the BN resolution) and xemo_op_bn_bwd_pool (dy gathered through a max pool)
+static int bn_bwd_impl(xemo_ctx* ctx, const __half* x, const __half* dy, size_t P, int C, const float* moments, const float* a,
+                       const float* b, int relu_mask, int test_mode, double* ws, __half* dx, float* dg, float* db,
+                       float* dconv_bias, float inv_grad_scale, const uint8_t* idx, const PoolGeom* pg) {
   XEMO_CUDA(ctx, cudaMemsetAsync(ws, 0, size_t(2) * C * sizeof(double), ctx->stream));
+  if (dconv_bias) XEMO_CUDA(ctx, cudaMemsetAsync(dconv_bias, 0, size_t(C) * 4, ctx->stream));
   const int C8 = C / 8;
   const BnGrid bg = bn_grid(P, C, ctx->num_sms);
   dim3 grid(bg.slabs_x, bg.slabs_y);
-  bn_bwd_reduce_kernel<__half><<<grid, kBnThreads, 0, ctx->stream>>>(x, dy, P, C, bg.lanes, bg.rows_par, moments, a, b, relu_mask, ws);
+  PoolGeom g0;
+  memset(&g0, 0, sizeof(g0));
+  if (pg)
+    bn_bwd_reduce_kernel<__half, true><<<grid, kBnThreads, 0, ctx->stream>>>(x, dy, P, C, bg.lanes, bg.rows_par, moments, a, b, relu_mask, ws, idx, *pg);
+  else
+    bn_bwd_reduce_kernel<__half, false><<<grid, kBnThreads, 0, ctx->stream>>>(x, dy, P, C, bg.lanes, bg.rows_par, moments, a, b, relu_mask, ws, nullptr, g0);
   XEMO_LAUNCHED(ctx, 1);
   const int egrid = fixed_channel_grid(P * C8, C8, 256, ctx->num_sms, 8);
-  if (test_mode)
-    bn_bwd_test_kernel<__half><<<egrid, 256, 0, ctx->stream>>>(x, dy, P, C, a, b, relu_mask, static_cast<__half*>(dx16));
-  else
-    bn_bwd_apply_kernel<__half><<<egrid, 256, 0, ctx->stream>>>(x, dy, P, C, moments, a, b, relu_mask, ws,
-                                                              static_cast<__half*>(dx16));
+  const size_t cs_smem = dconv_bias ? size_t(C) * 4 : 0;
+  if (test_mode) {
+    XEMO_REQUIRE(ctx, !pg && !dconv_bias, "bn_bwd: test mode does not support the fused pool / bias-gradient variants");
+    bn_bwd_test_kernel<__half><<<egrid, 256, 0, ctx->stream>>>(x, dy, P, C, a, b, relu_mask, dx);
+  } else if (pg) {
+    bn_bwd_apply_kernel<__half, true><<<egrid, 256, cs_smem, ctx->stream>>>(x, dy, P, C, moments, a, b, relu_mask, ws, dx, idx, *pg, dconv_bias, inv_grad_scale);
+  } else {
+    bn_bwd_apply_kernel<__half, false><<<egrid, 256, cs_smem, ctx->stream>>>(x, dy, P, C, moments, a, b, relu_mask, ws, dx, nullptr, g0, dconv_bias, inv_grad_scale);
+  }
   XEMO_LAUNCHED(ctx, 1);
   if (dg && db) {
     bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, ctx->stream>>>(ws, C, inv_grad_scale, dg, db);
     XEMO_LAUNCHED(ctx, 1);
   }
   return XEMO_OK;
+}
+
+extern "C" int xemo_op_bn_bwd(xemo_ctx* ctx, const void* x16, const void* dy16, size_t P, int C, const float* moments,
+                              const float* a, const float* b, int relu_mask, int test_mode, double* ws, void* dx16,
+                              float* dg, float* db, float* dconv_bias, float inv_grad_scale) {
+  XEMO_REQUIRE(ctx, x16 && dy16 && moments && a && b && ws && dx16 && C % 8 == 0 && C <= 8192, "bn_bwd: bad arguments");
+  return bn_bwd_impl(ctx, static_cast<const __half*>(x16), static_cast<const __half*>(dy16), P, C, moments, a, b, relu_mask,
+                     test_mode, ws, static_cast<__half*>(dx16), dg, db, dconv_bias, inv_grad_scale, nullptr, nullptr);
+}
+
+extern "C" int xemo_op_bn_bwd_pool(xemo_ctx* ctx, const void* x16, const void* dpool16, const uint8_t* argmax, int N, int H,
+                                   int W, int C, int PH, int PW, int sh, int sw, int pt, int pb, int pl, int pr,
+                                   const float* moments, const float* a, const float* b, double* ws, void* dx16, float* dg,
+                                   float* db, float* dconv_bias, float inv_grad_scale) {
+  PoolGeom g;
+  XEMO_REQUIRE(ctx, x16 && dpool16 && argmax && moments && a && b && ws && dx16 && C <= 8192 &&
+                        pool_geom(&g, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr),
+               "bn_bwd_pool: bad arguments");
+  XEMO_REQUIRE(ctx, (PH + sh - 1) / sh <= 2 && (PW + sw - 1) / sw <= 2 && size_t(N) * H * W < (size_t(1) << 31),
+               "bn_bwd_pool: at most 2 x 2 windows may cover one position (use maxpool_bwd + bn_bwd otherwise)");
+  return bn_bwd_impl(ctx, static_cast<const __half*>(x16), static_cast<const __half*>(dpool16), size_t(N) * H * W, C, moments, a, b,
+                     1, 0, ws, static_cast<__half*>(dx16), dg, db, dconv_bias, inv_grad_scale, argmax, &g);
 }
 
 extern "C" int xemo_op_relu_bwd(xemo_ctx* ctx, const void* y16, const void* dy16, size_t n, void* dx16) {

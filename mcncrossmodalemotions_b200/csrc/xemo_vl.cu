@@ -11,6 +11,8 @@
 // graph programs avoid the per-call layout conversions.
 #include "xemo_internal.h"
 
+#include <string.h>
+
 #include "hbm_kernels_extra.cuh"
 
 using namespace xemo;
@@ -242,7 +244,7 @@ extern "C" int xemo_vl_nnpool(xemo_ctx* ctx, const xemo_array* x, const int pool
   if (ar.failed) return ar.finish();
   if ((rc = xemo_op_hwcn_to_nhwc(ctx, dyd, OH, OW, C, N, dyn, Cp, 1))) return rc;
   if (method == 0)
-    maxpool_bwd_kernel<float, 0, 0><<<grid_for(in8, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(dyn, idx, g, dxn);
+    maxpool_bwd_kernel<float, 0, 0><<<fixed_channel_grid(in8, Cp / 8, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(dyn, idx, g, dxn);
   else
     avgpool_bwd_kernel<float><<<grid_for(in8, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(dyn, g, dxn);
   XEMO_LAUNCHED(ctx, 1);
@@ -301,12 +303,14 @@ extern "C" int xemo_vl_nnbnorm(xemo_ctx* ctx, const xemo_array* x, const float* 
     XEMO_CUDA(ctx, cudaMemsetAsync(ws, 0, size_t(2) * Cp * sizeof(double), ctx->stream));
     const BnGrid bg = bn_grid(P, Cp, ctx->num_sms);
     dim3 grid(bg.slabs_x, bg.slabs_y);
-    bn_bwd_reduce_kernel<float><<<grid, kBnThreads, 0, ctx->stream>>>(xn, dyn, P, Cp, bg.lanes, bg.rows_par, mom, av, bv, 0, ws);
+    PoolGeom g0;
+    memset(&g0, 0, sizeof(g0));
+    bn_bwd_reduce_kernel<float, false><<<grid, kBnThreads, 0, ctx->stream>>>(xn, dyn, P, Cp, bg.lanes, bg.rows_par, mom, av, bv, 0, ws, nullptr, g0);
     XEMO_LAUNCHED(ctx, 1);
     if (moments_in)
       bn_bwd_test_kernel<float><<<egrid, 256, 0, ctx->stream>>>(xn, dyn, P, Cp, av, bv, 0, outn);
     else
-      bn_bwd_apply_kernel<float><<<egrid, 256, 0, ctx->stream>>>(xn, dyn, P, Cp, mom, av, bv, 0, ws, outn);
+      bn_bwd_apply_kernel<float, false><<<egrid, 256, 0, ctx->stream>>>(xn, dyn, P, Cp, mom, av, bv, 0, ws, outn, nullptr, g0, nullptr, 1.f);
     XEMO_LAUNCHED(ctx, 1);
     if (dg || db) {
       float* dgp = ar.alloc_n<float>(Cp);

@@ -298,6 +298,7 @@ class StudentProgram(_Base):
         self.K = num_classes
         self.T = float(temperature)
         self.graphs = {}
+        self.fuse_pool_bwd = False
         self._geometry()
         self._load(params)
         self._alloc()
@@ -454,22 +455,34 @@ class StudentProgram(_Base):
             L = self.layers[i]
             n = L["name"]
             rows = N * L["oh"] * L["ow"]
+            fused_bias = False
             if L["bn"]:
                 bn = "bn" + n[-1]
                 P = L["pool"]
                 dcur = A[n + ":dout"]
-                if P and P["method"] == "max":
-                    # gradient w.r.t. the (never materialised) ReLU output, NHWC at the conv resolution
-                    ctx.op_maxpool_bwd(_p(dcur), _p(A[n + ":arg"]), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1],
-                                       P["stride"][0], P["stride"][1], 0, 0, 0, 0, _p(A[n + ":draw"]))
-                    dcur = A[n + ":draw"]
-                elif P:
-                    ctx.op_avgpool_bwd(_p(dcur), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1], P["stride"][0],
-                                       P["stride"][1], 0, 0, 0, 0, _p(A[n + ":dact"]))
-                    dcur = A[n + ":dact"]
-                ctx.op_bn_bwd(_p(A[n + ":raw"]), _p(dcur), rows, L["cout"], _p(self.batch_moments[bn]), _p(A[n + ":a"]),
-                              _p(A[n + ":b"]), 1, 0, _p(A[n + ":ws"]), _p(A[n + ":draw"]), _p(self.view(self.grad, bn + "m")),
-                              _p(self.view(self.grad, bn + "b")), inv)
+                gbias = self.view(self.grad, n + "b")
+                common = (_p(self.batch_moments[bn]), _p(A[n + ":a"]), _p(A[n + ":b"]))
+                outs = (_p(A[n + ":ws"]), _p(A[n + ":draw"]), _p(self.view(self.grad, bn + "m")), _p(self.view(self.grad, bn + "b")),
+                        _p(gbias), inv)
+                fused_bias = L["kp"] == L["cout"]
+                if not fused_bias:
+                    outs = outs[:4] + (None, inv)
+                if P and P["method"] == "max" and self.fuse_pool_bwd:
+                    # BN backward reads the pooled gradient through the arg-max (measured slower than the two-pass
+                    # form on B200 -- the gather is instruction-bound -- so off by default)
+                    ctx.op_bn_bwd_pool(_p(A[n + ":raw"]), _p(dcur), _p(A[n + ":arg"]), N, L["oh"], L["ow"], L["cout"], P["win"][0],
+                                       P["win"][1], P["stride"][0], P["stride"][1], 0, 0, 0, 0, *common, *outs)
+                else:
+                    if P and P["method"] == "max":
+                        # gradient w.r.t. the (never materialised) ReLU output, NHWC at the conv resolution
+                        ctx.op_maxpool_bwd(_p(dcur), _p(A[n + ":arg"]), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1],
+                                           P["stride"][0], P["stride"][1], 0, 0, 0, 0, _p(A[n + ":draw"]))
+                        dcur = A[n + ":draw"]
+                    elif P:
+                        ctx.op_avgpool_bwd(_p(dcur), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1], P["stride"][0],
+                                           P["stride"][1], 0, 0, 0, 0, _p(A[n + ":dact"]))
+                        dcur = A[n + ":dact"]
+                    ctx.op_bn_bwd(_p(A[n + ":raw"]), _p(dcur), rows, L["cout"], *common, 1, 0, *outs)
             dy = A[n + ":draw"]
             x = A["s2d"] if i == 0 else self._input_of(i)
             if n == "conv1":
@@ -484,7 +497,8 @@ class StudentProgram(_Base):
                 cp = _pad16(L["cin"])
                 ctx.op_conv_wgrad(_p(x), N, L["h"], L["w"], cp, _p(dy), L["kp"], L["kp"], L["fh"], L["fw"], L["stride"][0],
                                   L["stride"][1], *L["pad"], _p(self.view(self.grad, n + "f")), inv)
-            ctx.op_colsum(_p(dy), rows, L["kp"], L["kp"], inv, _p(self.view(self.grad, n + "b")))
+            if not fused_bias:
+                ctx.op_colsum(_p(dy), rows, L["kp"], L["kp"], inv, _p(self.view(self.grad, n + "b")))
             if i > 0:
                 cp = _pad16(L["cin"])
                 ctx.op_pack_dgrad_filters(_p(self.view(self.w16, n + "f")), L["kp"], L["fh"], L["fw"], cp, L["stride"][0],
@@ -496,12 +510,11 @@ class StudentProgram(_Base):
         return self.a[self.layers[i - 1]["name"] + ":out"]
 
     def _record_update(self):
+        """cnn_train_dag's accumulateGradients: every 'gradient' parameter has learningRate = weightDecay = 1 in
+        this graph (dag.initParams defaults), so the whole flat master buffer is updated by ONE launch that also
+        refreshes the fp16 mirror the tensor-core kernels read (alignment padding stays zero: g = w = m = 0)."""
         ctx = self.ctx
-        for name, (off, shape) in self.segs.items():
-            n = int(np.prod(shape))
-            is_filter = name.endswith("f") and not name.startswith("bn")
-            ctx.op_sgd_momentum(_p(self.view(self.master, name)), _p(self.view(self.momentum, name)), _p(self.view(self.grad, name)),
-                                n, _p(self.hyper), 1.0, 1.0, 1.0, _p(self.view(self.w16, name)) if is_filter else None)
+        ctx.op_sgd_momentum(_p(self.master), _p(self.momentum), _p(self.grad), self.nparam, _p(self.hyper), 1.0, 1.0, 1.0, _p(self.w16))
         for bn, m in self.moments.items():
             ctx.op_moments_average(_p(m), _p(self.batch_moments[bn]), m.numel(), 0.1)
 
