@@ -339,6 +339,204 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp16 fast paths of the two pooling kernels (the generic templates above are instruction-bound: ~700
+// instructions per 8-channel item).  Forward: z = relu(a*x + b) is monotone in x (increasing for a > 0,
+// decreasing for a < 0), so the window arg-max is found on sign-adjusted raw fp16 values with packed
+// half2 compares, the affine is applied once to the winner, and the ties ReLU creates (all-zero window)
+// resolve to the first in-bounds element as in MatConvNet's scan.  Backward: the uint8 arg-max bytes are
+// compared four at a time and the selected gradients accumulated in half2.
+template <bool kAffineRelu, int PH, int PW, bool kNoPad>
+__global__ void maxpool_fwd_h2_kernel(const __half* __restrict__ x, PoolGeom g, const float* __restrict__ a,
+                                      const float* __restrict__ b, __half* __restrict__ y, uint8_t* __restrict__ idx) {
+  const uint32_t C8 = uint32_t(g.C >> 3);
+  const uint32_t npix = uint32_t(g.N) * uint32_t(g.OH) * uint32_t(g.OW);
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c8 = tid % C8;  // constant along the loop (fixed_channel_grid)
+  const uint32_t pstride = (gridDim.x * blockDim.x) / C8;
+  float av[8], bv[8];
+  __half2 sgn[4];
+  if (kAffineRelu) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { av[k] = a[c8 * 8 + k]; bv[k] = b[c8 * 8 + k]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sgn[k] = __floats2half2_rn(av[2 * k] < 0.f ? -1.f : 1.f, av[2 * k + 1] < 0.f ? -1.f : 1.f);
+  }
+  const __half2 ninf = __floats2half2_rn(-INFINITY, -INFINITY);
+  for (uint32_t pp = tid / C8; pp < npix; pp += pstride) {
+    const uint32_t t1 = pp / uint32_t(g.OW);
+    const int ow = int(pp - t1 * uint32_t(g.OW));
+    const int n = int(t1 / uint32_t(g.OH));
+    const int oh = int(t1 - uint32_t(n) * uint32_t(g.OH));
+    const __half* xn = x + size_t(n) * g.H * g.W * g.C + c8 * 8;
+    const int h0 = oh * g.sh - g.pt, w0 = ow * g.sw - g.pl;
+    __half2 best[4] = {ninf, ninf, ninf, ninf};
+    uint32_t arg[4] = {0u, 0u, 0u, 0u};  // two 16-bit lanes per word
+    uint32_t first_valid = 0xFFFFu;
+#pragma unroll
+    for (int dw = 0; dw < PW; ++dw) {
+      const int w = w0 + dw;
+#pragma unroll
+      for (int dh = 0; dh < PH; ++dh) {
+        const int h = h0 + dh;
+        // kNoPad: every window lies inside the image (pad = 0 with vl_nnpool's floor output size), so the
+        // window loads carry no control dependence and are issued together
+        if (!kNoPad && (w < 0 || w >= g.W || h < 0 || h >= g.H)) continue;
+        const uint32_t pos = uint32_t(dw * PH + dh);
+        if (kNoPad) first_valid = 0u;
+        else if (first_valid == 0xFFFFu) first_valid = pos;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(xn + (size_t(h) * g.W + w) * g.C));
+        const __half2* v2 = reinterpret_cast<const __half2*>(&v);
+        const uint32_t pos2 = pos * 0x00010001u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const __half2 xv = kAffineRelu ? __hmul2(v2[k], sgn[k]) : v2[k];
+          const uint32_t m = __hgt2_mask(xv, best[k]);
+          arg[k] = (arg[k] & ~m) | (pos2 & m);
+          best[k] = __hmax2(best[k], xv);
+        }
+      }
+    }
+    uint4 o;
+    __half2* o2 = reinterpret_cast<__half2*>(&o);
+    uint32_t ab[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = __half22float2(kAffineRelu ? __hmul2(best[k], sgn[k]) : best[k]);
+      ab[2 * k] = arg[k] & 0xFFFFu;
+      ab[2 * k + 1] = arg[k] >> 16;
+      if (kAffineRelu) {
+        f.x = fmaxf(fmaf(av[2 * k], f.x, bv[2 * k]), 0.f);
+        f.y = fmaxf(fmaf(av[2 * k + 1], f.y, bv[2 * k + 1]), 0.f);
+        if (!(f.x > 0.f)) ab[2 * k] = first_valid;       // all-zero window: the first scanned element wins
+        if (!(f.y > 0.f)) ab[2 * k + 1] = first_valid;
+      }
+      o2[k] = __floats2half2_rn(f.x, f.y);
+    }
+    const size_t off = ((size_t(n) * g.OH + oh) * g.OW + ow) * g.C + c8 * 8;
+    *reinterpret_cast<uint4*>(y + off) = o;
+    if (idx) {
+      uint2 pk;
+      pk.x = ab[0] | (ab[1] << 8) | (ab[2] << 16) | (ab[3] << 24);
+      pk.y = ab[4] | (ab[5] << 8) | (ab[6] << 16) | (ab[7] << 24);
+      *reinterpret_cast<uint2*>(idx + off) = pk;
+    }
+  }
+}
+
+template <int MH, int MW>
+__global__ void maxpool_bwd_h2_kernel(const __half* __restrict__ dy, const uint8_t* __restrict__ idx, PoolGeom g,
+                                      __half* __restrict__ dx) {
+  const uint32_t C8 = uint32_t(g.C >> 3);
+  const uint32_t npix = uint32_t(g.N) * uint32_t(g.H) * uint32_t(g.W);
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c8 = tid % C8;
+  const uint32_t pstride = (gridDim.x * blockDim.x) / C8;
+  for (uint32_t pp = tid / C8; pp < npix; pp += pstride) {
+    const uint32_t t1 = pp / uint32_t(g.W);
+    const int w = int(pp - t1 * uint32_t(g.W));
+    const int n = int(t1 / uint32_t(g.H));
+    const int h = int(t1 - uint32_t(n) * uint32_t(g.H));
+    __half2 acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = __floats2half2_rn(0.f, 0.f);
+    const int oh_hi = (h + g.pt) / g.sh, ow_hi = (w + g.pl) / g.sw;
+#pragma unroll
+    for (int ia = 0; ia < MH; ++ia) {
+      const int oh = oh_hi - ia;
+      const int dh = h + g.pt - oh * g.sh;
+      if (oh < 0 || oh >= g.OH || dh >= g.PH) continue;
+#pragma unroll
+      for (int ib = 0; ib < MW; ++ib) {
+        const int ow = ow_hi - ib;
+        const int dw = w + g.pl - ow * g.sw;
+        if (ow < 0 || ow >= g.OW || dw >= g.PW) continue;
+        const size_t off = ((size_t(n) * g.OH + oh) * g.OW + ow) * g.C + c8 * 8;
+        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx + off));
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy + off));
+        const uint32_t me4 = uint32_t(dw * g.PH + dh) * 0x01010101u;
+        const uint32_t m0 = __vcmpeq4(pk.x, me4), m1 = __vcmpeq4(pk.y, me4);  // 0xFF per matching channel
+        // byte masks -> 16-bit lane masks, AND with the packed gradients, accumulate in half2
+        const uint32_t w0 = v.x & __byte_perm(m0, 0, 0x1100), w1 = v.y & __byte_perm(m0, 0, 0x3322);
+        const uint32_t w2 = v.z & __byte_perm(m1, 0, 0x1100), w3 = v.w & __byte_perm(m1, 0, 0x3322);
+        acc[0] = __hadd2(acc[0], *reinterpret_cast<const __half2*>(&w0));
+        acc[1] = __hadd2(acc[1], *reinterpret_cast<const __half2*>(&w1));
+        acc[2] = __hadd2(acc[2], *reinterpret_cast<const __half2*>(&w2));
+        acc[3] = __hadd2(acc[3], *reinterpret_cast<const __half2*>(&w3));
+      }
+    }
+    uint4 o;
+    __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o2[k] = acc[k];
+    *reinterpret_cast<uint4*>(dx + ((size_t(n) * g.H + h) * g.W + w) * g.C + c8 * 8) = o;
+  }
+}
+
+// 3x3 / stride 2 / pad 0 max-pool backward (both overlapping student pools): one thread owns the 2x2 input
+// cell (2i..2i+1, 2j..2j+1) of one channel group.  The cell is covered by exactly the four windows
+// (i-a, j-b), a, b in {0,1}; each window's (arg-max, gradient) pair is loaded once and routed to the (at
+// most) nine (position, window) combinations -- 24 bytes read per 16 bytes written, no redundant loads.
+static __global__ void maxpool_bwd_3x3s2_h2_kernel(const __half* __restrict__ dy, const uint8_t* __restrict__ idx, PoolGeom g,
+                                                   __half* __restrict__ dx) {
+  const uint32_t C8 = uint32_t(g.C >> 3);
+  const uint32_t HC = uint32_t(g.H + 1) >> 1, WC = uint32_t(g.W + 1) >> 1;
+  const uint32_t ncell = uint32_t(g.N) * HC * WC;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c8 = tid % C8;
+  const uint32_t pstride = (gridDim.x * blockDim.x) / C8;
+  for (uint32_t pp = tid / C8; pp < ncell; pp += pstride) {
+    const uint32_t t1 = pp / WC;
+    const int j = int(pp - t1 * WC);
+    const int n = int(t1 / HC);
+    const int i = int(t1 - uint32_t(n) * HC);
+    uint2 pk[2][2];
+    uint4 v[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int oh = i - a, ow = j - b;
+        const bool valid = oh >= 0 && oh < g.OH && ow >= 0 && ow < g.OW;
+        const size_t off = ((size_t(n) * g.OH + (valid ? oh : 0)) * g.OW + (valid ? ow : 0)) * g.C + c8 * 8;
+        pk[a][b] = __ldg(reinterpret_cast<const uint2*>(idx + off));
+        v[a][b] = __ldg(reinterpret_cast<const uint4*>(dy + off));
+        if (!valid) pk[a][b] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);  // matches no window-local index
+      }
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const int h = 2 * i + py, w = 2 * j + px;
+        if (h >= g.H || w >= g.W) continue;
+        __half2 acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          if (a == 1 && py == 1) continue;  // window i-1 reaches row 2i only (dh = 2)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            if (b == 1 && px == 1) continue;
+            const uint32_t me4 = uint32_t((px + 2 * b) * 3 + (py + 2 * a)) * 0x01010101u;  // dw * PH + dh
+            const uint32_t m0 = __vcmpeq4(pk[a][b].x, me4), m1 = __vcmpeq4(pk[a][b].y, me4);
+            const uint32_t w0 = v[a][b].x & __byte_perm(m0, 0, 0x1100), w1 = v[a][b].y & __byte_perm(m0, 0, 0x3322);
+            const uint32_t w2 = v[a][b].z & __byte_perm(m1, 0, 0x1100), w3 = v[a][b].w & __byte_perm(m1, 0, 0x3322);
+            acc[0] = __hadd2(acc[0], *reinterpret_cast<const __half2*>(&w0));
+            acc[1] = __hadd2(acc[1], *reinterpret_cast<const __half2*>(&w1));
+            acc[2] = __hadd2(acc[2], *reinterpret_cast<const __half2*>(&w2));
+            acc[3] = __hadd2(acc[3], *reinterpret_cast<const __half2*>(&w3));
+          }
+        }
+        uint4 o;
+        __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o2[k] = acc[k];
+        *reinterpret_cast<uint4*>(dx + ((size_t(n) * g.H + h) * g.W + w) * g.C + c8 * 8) = o;
+      }
+  }
+}
+
 // Average pooling (vl_nnpool 'avg'): divides by the number of in-bounds window elements.
 template <typename T>
 __global__ void avgpool_fwd_kernel(const T* __restrict__ x, PoolGeom g, T* __restrict__ y) {
@@ -459,7 +657,22 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, size_t P, int C, int la
   for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
   if (active) {
     const size_t stride = size_t(gridDim.x) * rows_par;
-    for (size_t r = size_t(blockIdx.x) * rows_par + rl; r < P; r += stride) {
+    size_t r = size_t(blockIdx.x) * rows_par + rl;
+    for (; r + 3 * stride < P; r += 4 * stride) {  // four independent 16-byte loads in flight per thread
+      Vec8<T> v0, v1, v2, v3;
+      v0.load(x + r * C + c8 * 8);
+      v1.load(x + (r + stride) * C + c8 * 8);
+      v2.load(x + (r + 2 * stride) * C + c8 * 8);
+      v3.load(x + (r + 3 * stride) * C + c8 * 8);
+      float f0[8], f1[8], f2[8], f3[8];
+      v0.to_float(f0); v1.to_float(f1); v2.to_float(f2); v3.to_float(f3);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s1[k] += (f0[k] + f1[k]) + (f2[k] + f3[k]);
+        s2[k] = fmaf(f0[k], f0[k], fmaf(f1[k], f1[k], fmaf(f2[k], f2[k], fmaf(f3[k], f3[k], s2[k]))));
+      }
+    }
+    for (; r < P; r += stride) {
       Vec8<T> v;
       v.load(x + r * C + c8 * 8);
       float f[8];
@@ -598,7 +811,27 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
       bv[k] = b[c8 * 8 + k];
     }
     const size_t stride = size_t(gridDim.x) * rows_par;
-    for (size_t r = size_t(blockIdx.x) * rows_par + rl; r < P; r += stride) {
+    size_t r = size_t(blockIdx.x) * rows_par + rl;
+    if (!kPool) {
+      for (; r + stride < P; r += 2 * stride) {  // two rows (four 16-byte loads) in flight per thread
+        Vec8<T> vx0, vd0, vx1, vd1;
+        vx0.load(x + r * C + c8 * 8);
+        vd0.load(dy + r * C + c8 * 8);
+        vx1.load(x + (r + stride) * C + c8 * 8);
+        vd1.load(dy + (r + stride) * C + c8 * 8);
+        float fx0[8], fd0[8], fx1[8], fd1[8];
+        vx0.to_float(fx0); vd0.to_float(fd0); vx1.to_float(fx1); vd1.to_float(fd1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float dz0 = fd0[k], dz1 = fd1[k];
+          if (relu_mask && !(fmaf(av[k], fx0[k], bv[k]) > 0.f)) dz0 = 0.f;
+          if (relu_mask && !(fmaf(av[k], fx1[k], bv[k]) > 0.f)) dz1 = 0.f;
+          s1[k] += dz0 + dz1;
+          s2[k] = fmaf(dz0, (fx0[k] - mu[k]) * isg[k], fmaf(dz1, (fx1[k] - mu[k]) * isg[k], s2[k]));
+        }
+      }
+    }
+    for (; r < P; r += stride) {
       Vec8<T> vx;
       vx.load(x + r * C + c8 * 8);
       float fx[8], fd[8];
@@ -667,7 +900,38 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
     for (int c = threadIdx.x; c < C; c += blockDim.x) cs_smem[c] = 0.f;
     __syncthreads();
   }
-  for (size_t i = tid; i < total; i += size_t(gridDim.x) * blockDim.x) {
+  const size_t gstride = size_t(gridDim.x) * blockDim.x;
+  size_t i = tid;
+  if (!kPool) {
+    for (; i + gstride < total; i += 2 * gstride) {  // two items (four 16-byte loads) in flight per thread
+      Vec8<T> vx0, vd0, vx1, vd1;
+      vx0.load(x + i * 8);
+      vd0.load(dy + i * 8);
+      vx1.load(x + (i + gstride) * 8);
+      vd1.load(dy + (i + gstride) * 8);
+      float fx0[8], fd0[8], fx1[8], fd1[8];
+      vx0.to_float(fx0); vd0.to_float(fd0); vx1.to_float(fx1); vd1.to_float(fd1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float dz0 = fd0[k], dz1 = fd1[k];
+        if (relu_mask && !(fmaf(A[k], fx0[k], B[k]) > 0.f)) dz0 = 0.f;
+        if (relu_mask && !(fmaf(A[k], fx1[k], B[k]) > 0.f)) dz1 = 0.f;
+        fd0[k] = fmaf(A[k], dz0, fmaf(-D[k], fx0[k], E[k]));
+        fd1[k] = fmaf(A[k], dz1, fmaf(-D[k], fx1[k], E[k]));
+      }
+      vd0.from_float(fd0);
+      vd1.from_float(fd1);
+      vd0.store(dx + i * 8);
+      vd1.store(dx + (i + gstride) * 8);
+      if (colsum) {
+        float fr0[8], fr1[8];
+        vd0.to_float(fr0); vd1.to_float(fr1);  // sum what was actually stored
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cs[k] += fr0[k] + fr1[k];
+      }
+    }
+  }
+  for (; i < total; i += gstride) {
     Vec8<T> vx, vd;
     vx.load(x + i * 8);
     float fx[8], fd[8];
@@ -784,31 +1048,57 @@ __global__ void se_squeeze_kernel(const T* __restrict__ u, int HW, int C, float*
   }
 }
 
-// one block (256 threads) per sample.  w1: [Cr][C] fp32, w2t: [Cr][C] fp32 (the second FC transposed so
-// that consecutive threads read consecutive addresses).
-static __global__ void se_gate_kernel(const float* __restrict__ s, int C, int Cr, const float* __restrict__ w1,
+// kSeSpb samples per block (256 threads) so that every weight element fetched from L2 feeds kSeSpb FMAs.
+// w1: [Cr][C] fp32, w2t: [Cr][C] fp32 (the second FC transposed: consecutive threads read consecutive
+// addresses).  Dynamic smem: kSeSpb * (C + Cr) floats.
+constexpr int kSeSpb = 2;
+static __global__ void se_gate_kernel(const float* __restrict__ s, int N, int C, int Cr, const float* __restrict__ w1,
                                const float* __restrict__ b1, const float* __restrict__ w2t,
                                const float* __restrict__ b2, float* __restrict__ gate) {
   extern __shared__ float sm[];
-  float* sv = sm;        // [C]
-  float* hid = sm + C;   // [Cr]
-  const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) sv[c] = s[size_t(n) * C + c];
+  float* sv = sm;                  // [kSeSpb][C]
+  float* hid = sm + kSeSpb * C;    // [kSeSpb][Cr]
+  const int n0 = blockIdx.x * kSeSpb;
+  for (int i = threadIdx.x; i < kSeSpb * C; i += blockDim.x) {
+    const int sidx = i / C, c = i - sidx * C;
+    sv[i] = (n0 + sidx < N) ? s[size_t(n0 + sidx) * C + c] : 0.f;
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int j = warp; j < Cr; j += nwarps) {
-    float t = 0.f;
-#pragma unroll 8
-    for (int c = lane; c < C; c += 32) t = fmaf(w1[size_t(j) * C + c], sv[c], t);
-    t = warp_sum(t);
-    if (lane == 0) hid[j] = fmaxf(t + (b1 ? b1[j] : 0.f), 0.f);
+    float t[kSeSpb];
+#pragma unroll
+    for (int q = 0; q < kSeSpb; ++q) t[q] = 0.f;
+    const float* wr = w1 + size_t(j) * C;
+#pragma unroll 4
+    for (int c = lane * 4; c < C; c += 128) {  // C is a multiple of 128 on this path (checked by the wrapper)
+      const float4 w = *reinterpret_cast<const float4*>(wr + c);
+#pragma unroll
+      for (int q = 0; q < kSeSpb; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(sv + q * C + c);
+        t[q] = fmaf(w.x, v.x, fmaf(w.y, v.y, fmaf(w.z, v.z, fmaf(w.w, v.w, t[q]))));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kSeSpb; ++q) {
+      const float r = warp_sum(t[q]);
+      if (lane == 0) hid[q * Cr + j] = fmaxf(r + (b1 ? b1[j] : 0.f), 0.f);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float t = b2 ? b2[c] : 0.f;
+    float t[kSeSpb];
+#pragma unroll
+    for (int q = 0; q < kSeSpb; ++q) t[q] = b2 ? b2[c] : 0.f;
 #pragma unroll 8
-    for (int j = 0; j < Cr; ++j) t = fmaf(w2t[size_t(j) * C + c], hid[j], t);
-    gate[size_t(n) * C + c] = 1.f / (1.f + __expf(-t));
+    for (int j = 0; j < Cr; ++j) {
+      const float w = w2t[size_t(j) * C + c];
+#pragma unroll
+      for (int q = 0; q < kSeSpb; ++q) t[q] = fmaf(w, hid[q * Cr + j], t[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < kSeSpb; ++q)
+      if (n0 + q < N) gate[size_t(n0 + q) * C + c] = 1.f / (1.f + __expf(-t[q]));
   }
 }
 

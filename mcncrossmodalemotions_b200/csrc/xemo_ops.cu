@@ -360,9 +360,16 @@ extern "C" int xemo_op_maxpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H,
   const __half* xp = static_cast<const __half*>(x16);
   __half* yp = static_cast<__half*>(y16);
 #define XEMO_POOL_FWD(AFF, PHc, PWc) maxpool_fwd_kernel<__half, AFF, PHc, PWc><<<grid, 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax)
-  if (PH == 3 && PW == 3) { if (a) XEMO_POOL_FWD(true, 3, 3); else XEMO_POOL_FWD(false, 3, 3); }
-  else if (PH == 5 && PW == 3) { if (a) XEMO_POOL_FWD(true, 5, 3); else XEMO_POOL_FWD(false, 5, 3); }
+#define XEMO_POOL_FWD_H2(AFF, PHc, PWc)                                                                                   \
+  do {                                                                                                                     \
+    if (nopad) maxpool_fwd_h2_kernel<AFF, PHc, PWc, true><<<grid, 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax);          \
+    else maxpool_fwd_h2_kernel<AFF, PHc, PWc, false><<<grid, 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax);               \
+  } while (0)
+  const bool nopad = (pt == 0 && pl == 0 && (g.OH - 1) * sh + PH <= H && (g.OW - 1) * sw + PW <= W);
+  if (PH == 3 && PW == 3) { if (a) XEMO_POOL_FWD_H2(true, 3, 3); else XEMO_POOL_FWD_H2(false, 3, 3); }
+  else if (PH == 5 && PW == 3) { if (a) XEMO_POOL_FWD_H2(true, 5, 3); else XEMO_POOL_FWD_H2(false, 5, 3); }
   else { if (a) XEMO_POOL_FWD(true, 0, 0); else XEMO_POOL_FWD(false, 0, 0); }
+#undef XEMO_POOL_FWD_H2
 #undef XEMO_POOL_FWD
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
@@ -376,8 +383,12 @@ extern "C" int xemo_op_maxpool_bwd(xemo_ctx* ctx, const void* dy16, const uint8_
   const size_t total = size_t(N) * H * W * (C / 8);
   XEMO_REQUIRE(ctx, size_t(N) * H * W < (size_t(1) << 31), "maxpool_bwd: tensor too large for 32-bit pixel indices");
   const int grid = fixed_channel_grid(total, C / 8, 256, ctx->num_sms, 8);
-  if ((PH + sh - 1) / sh == 2 && (PW + sw - 1) / sw == 2)
-    maxpool_bwd_kernel<__half, 2, 2><<<grid, 256, 0, ctx->stream>>>(static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
+  if (PH == 3 && PW == 3 && sh == 2 && sw == 2 && pt == 0 && pl == 0) {
+    const size_t cells = size_t(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+    maxpool_bwd_3x3s2_h2_kernel<<<fixed_channel_grid(cells, C / 8, 256, ctx->num_sms, 8), 256, 0, ctx->stream>>>(
+        static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
+  } else if ((PH + sh - 1) / sh == 2 && (PW + sw - 1) / sw == 2)
+    maxpool_bwd_h2_kernel<2, 2><<<grid, 256, 0, ctx->stream>>>(static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
   else
     maxpool_bwd_kernel<__half, 0, 0><<<grid, 256, 0, ctx->stream>>>(static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
   XEMO_LAUNCHED(ctx, 1);
@@ -530,8 +541,9 @@ extern "C" int xemo_op_se_squeeze(xemo_ctx* ctx, const void* u16, int N, int HW,
 
 extern "C" int xemo_op_se_gate(xemo_ctx* ctx, const float* s, int N, int C, int Cr, const float* w1, const float* b1,
                                const float* w2, const float* b2, float* gate) {
-  XEMO_REQUIRE(ctx, s && w1 && w2 && gate && (C + Cr) * 4 <= 48 * 1024, "se_gate: bad arguments");
-  se_gate_kernel<<<N, 256, size_t(C + Cr) * 4, ctx->stream>>>(s, C, Cr, w1, b1, w2, b2, gate);
+  XEMO_REQUIRE(ctx, s && w1 && w2 && gate && kSeSpb * (C + Cr) * 4 <= 48 * 1024 && C % 128 == 0, "se_gate: C must be a multiple of 128 and (C + Cr) <= 6144");
+  const int threads = C <= 512 ? 512 : 1024;  // latency-bound: many warps keep enough weight loads in flight
+  se_gate_kernel<<<(N + kSeSpb - 1) / kSeSpb, threads, size_t(kSeSpb) * (C + Cr) * 4, ctx->stream>>>(s, N, C, Cr, w1, b1, w2, b2, gate);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }

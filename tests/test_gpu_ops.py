@@ -1,0 +1,103 @@
+"""Device-native building blocks (xemo_op_*) against the oracle on exactly-representable data: the fp16
+fast-path pooling kernels (BN+ReLU folded into the read, packed compares) must reproduce MatConvNet's arg-max
+rule bit-exactly, and the optional pool-gather BN backward must agree with the two-pass form."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+
+    from mcncrossmodalemotions_b200 import _lib
+
+    stream = torch.cuda.Stream()
+    ctx = _lib.Context(0, stream.cuda_stream)
+    return torch, ctx, stream
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def nhwc(x):  # H x W x C x N  ->  N H W C
+    return np.ascontiguousarray(np.transpose(x, (3, 0, 1, 2)))
+
+
+def hwcn(x):
+    return np.transpose(x, (1, 2, 3, 0))
+
+
+@pytest.mark.parametrize("geom", [((3, 3), (2, 2), 21, 15), ((5, 3), (3, 2), 30, 17), ((2, 2), (2, 2), 10, 12)])
+@pytest.mark.parametrize("affine", [False, True])
+def test_fused_maxpool_forward_backward_bit_exact(env, geom, affine):
+    torch, ctx, stream = env
+    from oracle import mcn_ops as M
+
+    (ph, pw), (sh, sw), H, W = geom
+    Cc, N = 24, 3
+    rng = np.random.default_rng(ph * 100 + H + affine)
+    x = (np.round(rng.standard_normal((H, W, Cc, N)) * 4) / 2).astype(np.float32)        # multiples of 0.5: many exact ties
+    a = rng.choice([-2.0, -1.0, 0.5, 1.0, 2.0], Cc).astype(np.float32)                    # both signs
+    b = (np.round(rng.standard_normal(Cc) * 4) / 4).astype(np.float32)
+    z = np.maximum(a.reshape(1, 1, Cc, 1) * x + b.reshape(1, 1, Cc, 1), 0) if affine else x
+    yr, ir = M.vl_nnpool(z, (ph, pw), stride=(sh, sw), method="max", return_index=True)
+    OH, OW = yr.shape[:2]
+    with torch.cuda.stream(stream):
+        xd = torch.from_numpy(nhwc(x)).cuda().half()
+        ad, bd = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        yd = torch.zeros((N, OH, OW, Cc), dtype=torch.float16, device="cuda")
+        idd = torch.zeros((N, OH, OW, Cc), dtype=torch.uint8, device="cuda")
+        ctx.op_maxpool_fwd(_p(xd), N, H, W, Cc, ph, pw, sh, sw, 0, 0, 0, 0, _p(ad) if affine else None, _p(bd) if affine else None,
+                           _p(yd), _p(idd))
+        ctx.sync()
+        assert np.array_equal(hwcn(yd.float().cpu().numpy()), yr)
+        assert np.array_equal(hwcn(idd.cpu().numpy()), ir), "arg-max (first maximum in column-major scan order) must be bit-exact"
+        dy = (np.round(rng.standard_normal(yr.shape) * 8) / 8).astype(np.float32)
+        dxr = M.vl_nnpool(z, (ph, pw), dy, stride=(sh, sw), method="max")
+        dyd = torch.from_numpy(nhwc(dy)).cuda().half()
+        dxd = torch.zeros((N, H, W, Cc), dtype=torch.float16, device="cuda")
+        ctx.op_maxpool_bwd(_p(dyd), _p(idd), N, H, W, Cc, ph, pw, sh, sw, 0, 0, 0, 0, _p(dxd))
+        ctx.sync()
+        assert np.array_equal(hwcn(dxd.float().cpu().numpy()), dxr)
+
+
+def test_pool_gather_bn_backward_matches_two_pass(env):
+    torch, ctx, stream = env
+    N, H, W, Cc, ph, pw, sh, sw = 3, 21, 15, 32, 3, 3, 2, 2
+    OH, OW = (H - ph) // sh + 1, (W - pw) // sw + 1
+    rng = np.random.default_rng(0)
+    with torch.cuda.stream(stream):
+        x = torch.from_numpy(rng.standard_normal((N, H, W, Cc)).astype(np.float32)).cuda().half()
+        g = torch.from_numpy(rng.uniform(0.5, 1.5, Cc).astype(np.float32)).cuda()
+        beta = torch.from_numpy((0.1 * rng.standard_normal(Cc)).astype(np.float32)).cuda()
+        ws = torch.zeros(2 * Cc, dtype=torch.float64, device="cuda")
+        mom, a, b = (torch.zeros(n, device="cuda") for n in (2 * Cc, Cc, Cc))
+        ctx.op_bn_train(_p(x), N * H * W, Cc, _p(g), _p(beta), 1e-5, _p(ws), _p(mom), _p(a), _p(b))
+        y = torch.zeros((N, OH, OW, Cc), dtype=torch.float16, device="cuda")
+        arg = torch.zeros((N, OH, OW, Cc), dtype=torch.uint8, device="cuda")
+        ctx.op_maxpool_fwd(_p(x), N, H, W, Cc, ph, pw, sh, sw, 0, 0, 0, 0, _p(a), _p(b), _p(y), _p(arg))
+        dpool = torch.from_numpy(rng.standard_normal((N, OH, OW, Cc)).astype(np.float32)).cuda().half()
+        outs = []
+        for fused in (False, True):
+            dx = torch.zeros((N, H, W, Cc), dtype=torch.float16, device="cuda")
+            dg, db, dbias = (torch.zeros(Cc, device="cuda") for _ in range(3))
+            if fused:
+                ctx.op_bn_bwd_pool(_p(x), _p(dpool), _p(arg), N, H, W, Cc, ph, pw, sh, sw, 0, 0, 0, 0, _p(mom), _p(a), _p(b), _p(ws),
+                                   _p(dx), _p(dg), _p(db), _p(dbias), 1.0)
+            else:
+                full = torch.zeros((N, H, W, Cc), dtype=torch.float16, device="cuda")
+                ctx.op_maxpool_bwd(_p(dpool), _p(arg), N, H, W, Cc, ph, pw, sh, sw, 0, 0, 0, 0, _p(full))
+                ctx.op_bn_bwd(_p(x), _p(full), N * H * W, Cc, _p(mom), _p(a), _p(b), 1, 0, _p(ws), _p(dx), _p(dg), _p(db), _p(dbias), 1.0)
+            ctx.sync()
+            outs.append([t.float().cpu().numpy() for t in (dx, dg, db, dbias)])
+    for u, v in list(zip(*outs[:2]))[:3]:   # dx, dg, db
+        assert np.abs(u - v).max() <= 2e-3 * max(np.abs(v).max(), 1e-3)
+    # sum_rows dx (the bias gradient of a conv feeding train-mode BN) is identically zero in exact arithmetic:
+    # both forms must return only rounding noise
+    for o in outs:
+        assert np.abs(o[3]).max() <= 0.05 * np.abs(o[2]).max()
