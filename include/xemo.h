@@ -169,7 +169,8 @@ int xemo_op_avgpool_bwd(xemo_ctx* ctx, const void* dy16, int N, int H, int W, in
 
 /* batch normalisation over P = N*H*W rows of C channels.
  * bn_train: batch statistics -> moments[2C] = [mu | sigma], a = g/sigma, b = beta - a*mu (ws: 2C doubles).
- * bn_test : a, b from given moments.  affine_act: y = a*x + b (+ReLU).
+ * bn_test : a, b from given moments; conv_bias (optional) is folded into b (b += a*conv_bias) so that the BN of a
+ *           biased convolution can run as that convolution's scale/shift epilogue.  affine_act: y = a*x + b (+ReLU).
  * bn_bwd  : dz = dy*[a*x+b > 0] (relu_mask); dg = sum dz*xhat, db = sum dz (scaled by inv_grad_scale, fp32);
  *           dx = a*(dz - db/P - xhat*dg/P)  (train)  or  a*dz  (test_mode).  dconv_bias (optional, train mode,
  *           C <= 8192) receives inv_grad_scale * sum_rows dx: the bias gradient of the convolution feeding the BN.
@@ -178,7 +179,8 @@ int xemo_op_avgpool_bwd(xemo_ctx* ctx, const void* dy16, int N, int H, int W, in
  *           full-resolution gradient is never materialised between the pooling and the BN backward. */
 int xemo_op_bn_train(xemo_ctx* ctx, const void* x16, size_t P, int C, const float* g, const float* beta, float eps,
                      double* ws, float* moments, float* a, float* b);
-int xemo_op_bn_test(xemo_ctx* ctx, const float* moments, int C, const float* g, const float* beta, float* a, float* b);
+int xemo_op_bn_test(xemo_ctx* ctx, const float* moments, int C, const float* g, const float* beta, const float* conv_bias,
+                    float* a, float* b);
 int xemo_op_affine_act(xemo_ctx* ctx, const void* x16, size_t P, int C, const float* a, const float* b, int relu,
                        void* y16);
 int xemo_op_bn_bwd(xemo_ctx* ctx, const void* x16, const void* dy16, size_t P, int C, const float* moments,

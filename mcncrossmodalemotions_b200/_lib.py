@@ -77,7 +77,7 @@ SIGNATURES = {
     "xemo_op_avgpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]),
     "xemo_op_avgpool_bwd": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]),
     "xemo_op_bn_train": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "xemo_op_bn_test": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "xemo_op_bn_test": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "xemo_op_affine_act": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "xemo_op_bn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_float]),

@@ -62,6 +62,7 @@ struct ConvFpropParams {
   int use_tma_store;        // fp16 `out` written through tmOut
   int use_tma_residual;     // residual read through tmRes
   int epi_cw;               // staging chunk width in columns: 64 / 32 / 16
+  int epi_bufs;             // staging (and residual) buffers per epilogue group: 1 or 2
 };
 
 template <int BK>
@@ -102,9 +103,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int stage_bytes = conv_stage_bytes(BK, p.block_n);
   const int num_stages = p.num_stages;
 
-  uint8_t* epi_store_buf = smem + size_t(num_stages) * stage_bytes;                  // one 16 KB buffer per group (if used)
-  uint8_t* epi_res_buf = epi_store_buf + (p.use_tma_store ? 2 * kEpiStageBytes : 0); // one 16 KB buffer per group (if used)
-  uint8_t* after = epi_res_buf + (p.use_tma_residual ? 2 * kEpiStageBytes : 0);
+  const int epi_bufs = p.epi_bufs;
+  uint8_t* epi_store_buf = smem + size_t(num_stages) * stage_bytes;                  // epi_bufs x 16 KB per group (if used)
+  uint8_t* epi_res_buf = epi_store_buf + (p.use_tma_store ? kEpiGroups * epi_bufs * kEpiStageBytes : 0);
+  uint8_t* after = epi_res_buf + (p.use_tma_residual ? kEpiGroups * epi_bufs * kEpiStageBytes : 0);
   float* epi_ss = reinterpret_cast<float*>(after);                                   // [group][scale | shift][64]
   after += kEpiGroups * 2 * 64 * sizeof(float);
   uint64_t* bars = reinterpret_cast<uint64_t*>(after);
@@ -112,8 +114,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* empty_bar = bars + num_stages;
   uint64_t* tmem_full_bar = bars + 2 * num_stages;
   uint64_t* tmem_empty_bar = bars + 2 * num_stages + 2;
-  uint64_t* res_bar = bars + 2 * num_stages + 4;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * num_stages + 6);
+  uint64_t* res_bar = bars + 2 * num_stages + 4;  // [group][buf]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * num_stages + 8);
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
   const int lane = threadIdx.x & 31;
@@ -130,8 +132,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 4 * kEpiGroups);  // one arrive per epilogue warp
-      mbar_init(&res_bar[a], 1);
     }
+    for (int a = 0; a < 4; ++a) mbar_init(&res_bar[a], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -227,17 +229,20 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t swz_mask = (cw == 64) ? 7u : (cw == 32) ? 3u : 1u;
     const uint32_t chunk_bytes = uint32_t(kConvBlockM) * uint32_t(pitch);
     const int ohw = p.OH * p.OW;
-    uint8_t* sbuf = epi_store_buf + group * kEpiStageBytes;
-    uint8_t* rbuf = epi_res_buf + group * kEpiStageBytes;
+    uint8_t* sbuf0 = epi_store_buf + group * epi_bufs * kEpiStageBytes;
+    uint8_t* rbuf0 = epi_res_buf + group * epi_bufs * kEpiStageBytes;
     float* ss_scale = epi_ss + group * 128;
     float* ss_shift = ss_scale + 64;
-    uint64_t* rbar = &res_bar[group];
+    uint64_t* rbar0 = &res_bar[group * 2];
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t mine = 0;  // chunks this group has processed (phase of its residual barrier)
 
-    // residual chunk `G` (global chunk index of this CTA: tile_iter * chunks_per_tile + q) -> TMA prefetch
-    auto prefetch_residual = [&](long long G) {
+    // residual chunk `G` (global chunk index of this CTA: tile_iter * chunks_per_tile + q) -> TMA prefetch into
+    // buffer `buf` of this group
+    auto prefetch_residual = [&](long long G, int buf) {
+      uint64_t* rbar = rbar0 + buf;
+      uint8_t* rbuf = rbuf0 + buf * kEpiStageBytes;
       const long long titer = G / chunks_per_tile;
       const int q = int(G - titer * chunks_per_tile);
       const long long tile = (long long)blockIdx.x + titer * gridDim.x;
@@ -247,7 +252,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_arrive_expect_tx(rbar, chunk_bytes);
       tma_load_2d(&tmRes, rbar, rbuf, nn * p.block_n + q * cw, nm * kConvBlockM);
     };
-    if (p.use_tma_residual && leader) prefetch_residual(group);
+    if (p.use_tma_residual && leader)
+      for (int bq = 0; bq < epi_bufs; ++bq) prefetch_residual(group + 2 * bq, bq);
 
     long long G0 = 0;  // global chunk index of chunk 0 of the current tile
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, G0 += chunks_per_tile) {
@@ -272,14 +278,19 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
 
       for (int q = int((group + 2 - (G0 & 1)) & 1); q < chunks_per_tile; q += 2, ++mine) {
-        // the TMA store that last read this group's staging buffer must have drained it
-        if (p.use_tma_store && leader) tma_store_wait_read<0>();
+        const int buf = epi_bufs == 2 ? int(mine & 1u) : 0;
+        uint8_t* sbuf = sbuf0 + buf * kEpiStageBytes;
+        uint8_t* rbuf = rbuf0 + buf * kEpiStageBytes;
+        // the TMA store that last read this staging buffer (epi_bufs chunks ago) must have drained it
+        if (p.use_tma_store && leader) {
+          if (epi_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+        }
         if (tg < cw) {
           ss_scale[tg] = p.scale ? __ldg(p.scale + n0 + q * cw + tg) : 1.f;
           ss_shift[tg] = p.shift ? __ldg(p.shift + n0 + q * cw + tg) : 0.f;
         }
         epi_bar_sync(group);  // staging buffer free, scale/shift visible
-        if (p.use_tma_residual) mbar_wait(rbar, mine & 1u);
+        if (p.use_tma_residual) mbar_wait(rbar0 + buf, (epi_bufs == 2 ? (mine >> 1) : mine) & 1u);
 
         for (int jj = 0; jj < cw; jj += 16) {
           const int j = q * cw + jj;  // column inside the tile
@@ -346,7 +357,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (leader) {
             tma_store_2d(&tmOut, sbuf, n0 + q * cw, m0);  // rows beyond M are clipped by the tensor map
             tma_store_commit();
-            if (p.use_tma_residual) prefetch_residual(G0 + q + 2);
+            if (p.use_tma_residual) prefetch_residual(G0 + q + 2 * epi_bufs, buf);
           }
         } else {
           epi_bar_sync(group);       // scale / shift may be overwritten by the next chunk

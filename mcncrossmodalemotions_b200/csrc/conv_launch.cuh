@@ -96,13 +96,21 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   p.use_tma_store = (e.allow_tma_epilogue && e.out && !e.strided_out && (p.ldc % 8 == 0)) ? 1 : 0;
   p.use_tma_residual = (p.use_tma_store && e.residual) ? 1 : 0;
   p.epi_cw = (p.block_n % 64 == 0) ? 64 : (p.block_n % 32 == 0) ? 32 : 16;
-  const int epi_bytes = (p.use_tma_store ? 2 * kEpiStageBytes : 0) + (p.use_tma_residual ? 2 * kEpiStageBytes : 0);
-  int stages = (kSmemBudget - 1024 - 256 - 1024 - epi_bytes) / stage_bytes;
+  // staging buffers per epilogue group: two when the pipeline still keeps enough stages for the K loop
+  const int k_iters = g.R * g.S * p.kc_blocks;
+  const int want_stages = k_iters + 1 < 3 ? k_iters + 1 : 3;
+  int stages = 0, epi_bytes = 0;
+  for (int bufs = 2; bufs >= 1; --bufs) {
+    epi_bytes = (p.use_tma_store ? kEpiGroups * bufs * kEpiStageBytes : 0) + (p.use_tma_residual ? kEpiGroups * bufs * kEpiStageBytes : 0);
+    stages = (kSmemBudget - 1024 - 256 - 1024 - epi_bytes) / stage_bytes;
+    p.epi_bufs = bufs;
+    if (stages >= want_stages) break;
+  }
   if (stages > 12) stages = 12;
   if (stages < 2) return false;
   p.num_stages = stages;
   plan->bk = bk;
-  plan->smem = stages * stage_bytes + epi_bytes + 1024 + kEpiGroups * 2 * 64 * 4 + (2 * stages + 6) * 8 + 16;
+  plan->smem = stages * stage_bytes + epi_bytes + 1024 + kEpiGroups * 2 * 64 * 4 + (2 * stages + 8) * 8 + 16;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   plan->grid = tiles < num_sms ? tiles : num_sms;
   plan->flops = 2.0 * double(p.M) * g.Kout * g.R * g.S * g.Cin;

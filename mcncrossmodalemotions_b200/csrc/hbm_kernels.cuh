@@ -711,15 +711,16 @@ static __global__ void bn_finalize_kernel(const double* __restrict__ acc, size_t
   b[c] = float(double(beta[c]) - aa * mu);
 }
 
-// test mode: moments given (C x 2 = [mu sigma])
+// test mode: moments given (C x 2 = [mu sigma]).  conv_bias (optional) folds the bias of the convolution that
+// feeds the BN into the shift, so that y = a * conv_nobias(x) + b can run in the convolution's epilogue.
 static __global__ void bn_affine_from_moments_kernel(const float* __restrict__ moments, int C, const float* __restrict__ g,
-                                              const float* __restrict__ beta, float* __restrict__ a,
-                                              float* __restrict__ b) {
+                                              const float* __restrict__ beta, const float* __restrict__ conv_bias,
+                                              float* __restrict__ a, float* __restrict__ b) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float aa = g[c] / moments[C + c];
   a[c] = aa;
-  b[c] = beta[c] - aa * moments[c];
+  b[c] = beta[c] - aa * moments[c] + (conv_bias ? aa * conv_bias[c] : 0.f);
 }
 
 template <typename T>

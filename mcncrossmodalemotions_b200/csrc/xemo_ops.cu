@@ -440,10 +440,10 @@ extern "C" int xemo_op_bn_train(xemo_ctx* ctx, const void* x16, size_t P, int C,
   return XEMO_OK;
 }
 
-extern "C" int xemo_op_bn_test(xemo_ctx* ctx, const float* moments, int C, const float* g, const float* beta, float* a,
-                               float* b) {
+extern "C" int xemo_op_bn_test(xemo_ctx* ctx, const float* moments, int C, const float* g, const float* beta,
+                               const float* conv_bias, float* a, float* b) {
   XEMO_REQUIRE(ctx, moments && g && beta && a && b, "bn_test: null pointer");
-  bn_affine_from_moments_kernel<<<(C + 127) / 128, 128, 0, ctx->stream>>>(moments, C, g, beta, a, b);
+  bn_affine_from_moments_kernel<<<(C + 127) / 128, 128, 0, ctx->stream>>>(moments, C, g, beta, conv_bias, a, b);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }

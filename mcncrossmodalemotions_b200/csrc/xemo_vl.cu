@@ -282,7 +282,7 @@ extern "C" int xemo_vl_nnbnorm(xemo_ctx* ctx, const xemo_array* x, const float* 
     XEMO_LAUNCHED(ctx, 1);
     XEMO_CUDA(ctx, cudaMemcpyAsync(mom, moments_in, size_t(C) * 4, cudaMemcpyDefault, ctx->stream));
     XEMO_CUDA(ctx, cudaMemcpyAsync(mom + Cp, moments_in + C, size_t(C) * 4, cudaMemcpyDefault, ctx->stream));
-    bn_affine_from_moments_kernel<<<(Cp + 127) / 128, 128, 0, ctx->stream>>>(mom, Cp, gd, bd, av, bv);
+    bn_affine_from_moments_kernel<<<(Cp + 127) / 128, 128, 0, ctx->stream>>>(mom, Cp, gd, bd, nullptr, av, bv);
     XEMO_LAUNCHED(ctx, 1);
   } else {
     if ((rc = bn_stats_launch<float>(ctx, xn, P, Cp, ws))) return rc;

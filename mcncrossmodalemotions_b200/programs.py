@@ -406,6 +406,8 @@ class StudentProgram(_Base):
 
     # ---- forward
     def _record_forward(self, train):
+        if not train:
+            return self._record_forward_test()
         N, A, ctx = self.N, self.a, self.ctx
         ctx.op_spec_s2d(_p(A["spec"]), 512, self.W, N, 1, 1, self.s2d_hp, self.s2d_ow, _p(A["s2d"]))
         cur = A["s2d"]
@@ -424,11 +426,8 @@ class StudentProgram(_Base):
             bn = "bn" + n[-1]
             g, beta = self.view(self.master, bn + "m"), self.view(self.master, bn + "b")
             rows = N * L["oh"] * L["ow"]
-            if train:
-                ctx.op_bn_train(_p(cur), rows, L["cout"], _p(g), _p(beta), BN_EPS, _p(A[n + ":ws"]), _p(self.batch_moments[bn]),
-                                _p(A[n + ":a"]), _p(A[n + ":b"]))
-            else:
-                ctx.op_bn_test(_p(self.moments[bn]), L["cout"], _p(g), _p(beta), _p(A[n + ":a"]), _p(A[n + ":b"]))
+            ctx.op_bn_train(_p(cur), rows, L["cout"], _p(g), _p(beta), BN_EPS, _p(A[n + ":ws"]), _p(self.batch_moments[bn]),
+                            _p(A[n + ":a"]), _p(A[n + ":b"]))
             P = L["pool"]
             if P and P["method"] == "max":
                 ctx.op_maxpool_fwd(_p(cur), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1], P["stride"][0], P["stride"][1],
@@ -440,6 +439,40 @@ class StudentProgram(_Base):
             else:
                 ctx.op_affine_act(_p(cur), rows, L["cout"], _p(A[n + ":a"]), _p(A[n + ":b"]), 1, _p(A[n + ":out"]))
             cur = A[n + ":out"]
+
+    def _record_forward_test(self):
+        """dag.mode = 'test' (external/compute_audio_feats.m:106): BN uses the stored moments, so it folds -- together
+        with the conv bias -- into the convolution's scale/shift epilogue and the activation is rounded to fp16 once."""
+        N, A, ctx = self.N, self.a, self.ctx
+        ctx.op_spec_s2d(_p(A["spec"]), 512, self.W, N, 1, 1, self.s2d_hp, self.s2d_ow, _p(A["s2d"]))
+        cur = A["s2d"]
+        for L in self.layers:
+            n = L["name"]
+            wt, bias = self.view(self.w16, n + "f"), self.view(self.master, n + "b")
+            scale, shift, relu, out32 = None, bias, 0, None
+            if L["bn"]:
+                bn = "bn" + n[-1]
+                ctx.op_bn_test(_p(self.moments[bn]), L["cout"], _p(self.view(self.master, bn + "m")), _p(self.view(self.master, bn + "b")),
+                               _p(bias), _p(A[n + ":a"]), _p(A[n + ":b"]))
+                scale, shift, relu = A[n + ":a"], A[n + ":b"], 1
+            else:
+                out32 = A["pred32"]
+            P = L["pool"]
+            dst = A[n + ":raw"] if (P or not L["bn"]) else A[n + ":out"]
+            if n == "conv1":
+                self.conv(cur, N, self.s2d_hp, self.s2d_ow, 16, wt, L["kp"], 4, 1, (1, 1), (0, 0, 0, 0), scale, shift, None, relu, dst)
+            else:
+                self.conv(cur, N, L["h"], L["w"], _pad16(L["cin"]), wt, L["kp"], L["fh"], L["fw"], L["stride"], L["pad"], scale, shift,
+                          None, relu, dst, out32, L["kp"])
+            if P and P["method"] == "max":
+                ctx.op_maxpool_fwd(_p(dst), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1], P["stride"][0], P["stride"][1],
+                                   0, 0, 0, 0, None, None, _p(A[n + ":out"]), None)
+                dst = A[n + ":out"]
+            elif P:
+                ctx.op_avgpool_fwd(_p(dst), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1], P["stride"][0], P["stride"][1],
+                                   0, 0, 0, 0, _p(A[n + ":out"]))
+                dst = A[n + ":out"]
+            cur = dst
 
     # ---- loss + backward
     def _record_backward(self):
@@ -631,6 +664,24 @@ class StudentProgram(_Base):
                     o, shape = self.segs[bn + s]
                     out[bn + s] = flat[o : o + L["cout"]].copy()
         return out
+
+    def load_momentum(self, momentum):
+        """Restore the optimiser state exported by `_export(self.momentum)` (checkpoint resume)."""
+        flat = np.zeros(self.nparam, np.float32)
+        for L in self.layers:
+            n = L["name"]
+            o, shape = self.segs[n + "f"]
+            w = student_conv1_to_s2d(momentum[n + "f"]) if n == "conv1" else krsc(momentum[n + "f"])
+            flat[o : o + w.size] = w.reshape(-1)
+            o, _ = self.segs[n + "b"]
+            flat[o : o + L["cout"]] = momentum[n + "b"]
+            if L["bn"]:
+                bn = "bn" + n[-1]
+                for s_ in ("m", "b"):
+                    o, _ = self.segs[bn + s_]
+                    flat[o : o + L["cout"]] = momentum[bn + s_]
+        with torch.cuda.stream(self.stream):
+            self.momentum.copy_(torch.from_numpy(flat))
 
     def export_params(self):
         self.sync()

@@ -79,3 +79,62 @@ def pool6_window(width):
     if width not in POOL6_BUCKETS:
         raise ValueError("spectrogram width %d is not one of the buckets %s" % (width, sorted(POOL6_BUCKETS)))
     return (1, POOL6_BUCKETS[width])
+
+
+class Model:
+    """What `emoVoxZoo` / `ferPlusZoo` hand to the reference scripts, reduced to what they touch: the parameters
+    (MatConvNet layouts), `meta.normalization`, the layer names they look up (`pool6`), `mode`, `move` and `eval`."""
+
+    def __init__(self, name, params, kind, width=None):
+        self.name, self.params, self.kind = name, params, kind
+        self.mode = "test" if kind == "teacher" else "normal"
+        self.device = "cpu"
+        self.meta = {"normalization": {"imageSize": (224, 224, 3) if kind == "teacher" else (512, width, 1),
+                                       "averageImage": AVERAGE_IMAGE if kind == "teacher" else None}}
+        self.pool6 = pool6_window(width) if kind == "student" else None
+        self._prog = None
+
+    def move(self, device):
+        if device not in ("gpu", "cpu"):
+            raise ValueError("move: device must be 'gpu' or 'cpu'")
+        if device == "cpu":
+            raise RuntimeError("this back-end has no CPU path; the model stays on the GPU")
+        self.device = device
+
+    def eval(self, inputs):
+        """dag.eval({'data', x}) -> N x 8 (teacher: logits; student: predictions in the current mode's BN)."""
+        from .programs import StudentProgram, TeacherProgram
+
+        x = inputs["data"]
+        n = x.shape[-1]
+        if self._prog is None or self._prog.N != n:
+            if self.kind == "teacher":
+                self._prog = TeacherProgram(self.params, n, input_mode="u8" if x.ndim == 3 else "hwcn224",
+                                            face_size=x.shape[0] if x.ndim == 3 else 48)
+            else:
+                self._prog = StudentProgram(self.params, n, x.shape[1])
+        if self.kind == "teacher":
+            return self._prog.forward(x)
+        return self._prog.forward(x, "test" if self.mode == "test" else "train")
+
+
+def emoVoxZoo(modelName, scratch=False, lossType="hot-cross-ent", numSeconds=4, numOutputs=8, seed=3):
+    """emoVoxZoo(modelName, 'scratch', tf, 'lossType', ..., 'numSeconds', ..., 'numOutputs', ...) (emoVoxZoo.m:1,17-23).
+    Student names build the VGGVox graph re-initialised as dag.initParams() leaves it (:50-62); teacher names
+    (emoVoxZoo.m:28-31) return the FER+ teachers.  The released .mat weights are remote downloads (:95-97): with no
+    file at hand the parameters are seeded synthetic ones (scratch=True is what run_distillation uses anyway)."""
+    if modelName in TEACHERS:
+        return Model(modelName, teacher_init(modelName), "teacher")
+    if modelName not in STUDENTS:
+        raise ValueError("unrecognised model: %s" % modelName)
+    if lossType not in ("hot-cross-ent", "softmaxlog", "euclidean", "huber"):
+        raise ValueError("unrecognised loss type: %s" % lossType)
+    width = 100 * int(numSeconds)
+    return Model(modelName, student_init(seed, numOutputs), "student", width)
+
+
+def ferPlusZoo(modelName):
+    """ferPlusZoo (teacher/ferPlusZoo.m:95-114): the pretrained branch falls through to emoVoxZoo(modelName)."""
+    if modelName not in TEACHERS:
+        raise ValueError("unrecognised FER+ model: %s" % modelName)
+    return emoVoxZoo(modelName)

@@ -164,3 +164,49 @@ def test_mex_shims_compile_against_stub_header():
         r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wno-unused-function", "-DXEMO_MEX_STUB", "-I" + os.path.join(ROOT, "include"),
                             "-I" + os.path.join(ROOT, "mex"), f], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_batch_assembly_matches_reference_rules():
+    from mcncrossmodalemotions_b200 import batch as B
+    from oracle import nets
+
+    # time2idx: floor(max(25 t - 1, 0) / 6) + 1 (getBatchEmoVoxCeleb.m:210-214)
+    for t in (0.0, 0.03, 0.04, 0.27, 0.28, 1.0, 3.99, 4.0, 19.9):
+        assert B.time2idx(t) == nets.time2idx(t)
+    assert abs(B.audio_crop_seconds(400) - 4.024) < 1e-12           # 0.01*W + 0.001*Tw - 0.001
+    assert B.frame_window(20, 0.0, 4.024) == (0, 17)
+    assert B.frame_window(10, 1.0, 4.0) == (4, 10)                  # end clamped to the frames that exist
+    with pytest.raises(ValueError):
+        B.frame_window(3, 2.0, 3.0)
+    rng = np.random.default_rng(0)
+    lg = rng.standard_normal((17, 8)).astype(np.float32)
+    assert np.array_equal(B.aggregate(lg, "max"), nets.aggregate_logits(lg, "max"))
+    assert np.allclose(B.aggregate(lg, "mean", 6), nets.aggregate_logits(lg, "mean", 6))
+    with pytest.raises(FloatingPointError):
+        B.aggregate(np.full((2, 8), np.nan))
+    spec = rng.standard_normal((512, 300)) * 3 + 1
+    assert np.allclose(B.normalize_rows(spec), nets.normalize_spectrogram(spec), atol=1e-6)
+    inputs = B.get_batch([spec, spec[:, ::-1]], [lg, lg[::-1]], [(0.0, 3.0), (0.5, 3.5)])
+    assert inputs["data"].shape == (512, 300, 1, 2) and inputs["logitTarget"].shape == (1, 1, 8, 2)
+    assert inputs["maxLabel"][0, 0, 0, 0] == lg[0:13].max(axis=0).argmax() + 1
+    assert set(B.get_batch([spec], [lg], [(0, 1)], loss_type="softmaxlog")) == {"data", "maxLabel"}
+    with pytest.raises(ValueError):
+        B.get_batch([spec], [lg], [(0, 1)], loss_type="nope")
+    assert B.width_bucket(1234) == 1000 and B.width_bucket(399) == 300 and B.centre_crop(spec, 100).shape == (512, 100)
+    with pytest.raises(ValueError):
+        B.width_bucket(50)
+
+
+def test_training_driver_helpers():
+    from mcncrossmodalemotions_b200 import train as T
+
+    lr = T.learning_rate_schedule(300)
+    assert len(lr) == 300 and np.isclose(lr[0], 1e-4) and np.isclose(lr[-1], 1e-5)
+    assert T.exp_dir_name("senet50-ferplus", "emovoxceleb-student", "hot-cross-ent", 4, 8, "max", 2) == \
+        "voxceleb-senet50-ferplus-emovoxceleb-student-hot-cross-ent-scratch-4sec-8emo-agg-max-temp2"
+    st = T.extract_stats(dict(objective=20.0, classerror=5.0, correct=np.array([3, 0, 1, 0, 0, 0, 0, 0.]),
+                              count=np.array([4, 2, 2, 0, 0, 0, 0, 2.])), 10)
+    assert st["objective"] == 2.0 and st["classerror"] == 0.5 and st["neutral"] == 0.75 and st["neutralPop"] == 0.4
+    assert np.isclose(st["meanAcc"], (0.75 + 0.5) / 8)
+    with pytest.raises(ValueError):
+        T.run_distillation(None, None, notAnOption=1)
