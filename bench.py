@@ -304,6 +304,7 @@ def main():
     if rank == 0:
         prof = ConvProfiler(step.stream)
         step.use_graph = False
+        side, step.side, step.student.side_stream = step.side, None, None   # per-op timing needs one stream
         step.grad_step()  # warm
         step.sync()
         step.ctx.profiler = prof
@@ -311,6 +312,7 @@ def main():
             step.grad_step()
         step.ctx.profiler = None
         step.use_graph = True
+        step.side, step.student.side_stream = side, side
         fl, t, n_launch, by = prof.summary()
         peaks = measured_peaks()
         achieved = fl / t / 1e12

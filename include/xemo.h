@@ -70,7 +70,13 @@ int xemo_h2d(xemo_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int xemo_d2h(xemo_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 int xemo_memset(xemo_ctx* ctx, void* dst_dev, int byte, size_t bytes);
 
-/* CUDA-graph capture of a sequence of xemo_op_* calls on the context stream */
+/* Multi-stream programs.  xemo_set_stream redirects subsequent launches to `cuda_stream` (NULL = back to the
+ * primary stream the context was created on).  xemo_stream_wait(waiter, signal) makes `waiter` wait for the work
+ * enqueued so far on `signal` (NULL = primary); inside a capture this forks / joins the second stream. */
+int xemo_set_stream(xemo_ctx* ctx, void* cuda_stream);
+int xemo_stream_wait(xemo_ctx* ctx, void* waiter_stream, void* signal_stream);
+
+/* CUDA-graph capture of a sequence of xemo_op_* calls (begins / ends on the primary stream) */
 int xemo_capture_begin(xemo_ctx* ctx);
 int xemo_capture_end(xemo_ctx* ctx, xemo_graph** out);
 int xemo_graph_launch(xemo_ctx* ctx, xemo_graph* g);

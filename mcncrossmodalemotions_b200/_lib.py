@@ -41,6 +41,8 @@ SIGNATURES = {
     "xemo_h2d": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
     "xemo_d2h": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
     "xemo_memset": (c_int, [c_void_p, c_void_p, c_int, c_size_t]),
+    "xemo_set_stream": (c_int, [c_void_p, c_void_p]),
+    "xemo_stream_wait": (c_int, [c_void_p, c_void_p, c_void_p]),
     "xemo_capture_begin": (c_int, [c_void_p]),
     "xemo_capture_end": (c_int, [c_void_p, P(c_void_p)]),
     "xemo_graph_launch": (c_int, [c_void_p, c_void_p]),
@@ -158,7 +160,7 @@ class Context:
             raise XemoError(rc, self.lib.xemo_last_error(self.handle).decode())
 
     def __getattr__(self, name):
-        if name.startswith(("op_", "vl_")) or name in ("sync", "h2d", "d2h", "memset", "capture_begin", "graph_launch"):
+        if name.startswith(("op_", "vl_")) or name in ("sync", "h2d", "d2h", "memset", "capture_begin", "graph_launch", "set_stream", "stream_wait"):
             return lambda *a: self.call(name, *a)
         raise AttributeError(name)
 

@@ -12,7 +12,8 @@
 
 struct xemo_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // current launch stream (xemo_set_stream)
+  cudaStream_t primary = nullptr;  // the stream the context was created on: capture, graph launches, sync
   bool own_stream = false;
   int num_sms = 0;
   std::string err;

@@ -25,13 +25,14 @@ extern "C" int xemo_create(int device, void* cuda_stream, xemo_ctx** out) {
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   if (cuda_stream) {
-    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    ctx->stream = ctx->primary = reinterpret_cast<cudaStream_t>(cuda_stream);
   } else {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
       delete ctx;
       return XEMO_ERR_CUDA;
     }
     ctx->own_stream = true;
+    ctx->primary = ctx->stream;
   }
   *out = ctx;
   return XEMO_OK;
@@ -39,14 +40,14 @@ extern "C" int xemo_create(int device, void* cuda_stream, xemo_ctx** out) {
 
 extern "C" void xemo_destroy(xemo_ctx* ctx) {
   if (!ctx) return;
-  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->primary);
   delete ctx;
 }
 
 extern "C" const char* xemo_last_error(xemo_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 extern "C" int xemo_sync(xemo_ctx* ctx) {
-  XEMO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  XEMO_CUDA(ctx, cudaStreamSynchronize(ctx->primary));
   return XEMO_OK;
 }
 extern "C" int xemo_num_sms(xemo_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
@@ -65,11 +66,30 @@ extern "C" int xemo_memset(xemo_ctx* ctx, void* dst, int byte, size_t bytes) {
   return XEMO_OK;
 }
 
+// Multi-stream programs: launches go to the context's *current* stream; xemo_stream_wait makes `waiter` wait for
+// everything enqueued so far on `signal` (event record + wait), which also pulls `waiter` into an ongoing
+// capture of `signal` (fork) or joins it back.  NULL designates the context's primary stream.
+extern "C" int xemo_set_stream(xemo_ctx* ctx, void* cuda_stream) {
+  ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->primary;
+  return XEMO_OK;
+}
+extern "C" int xemo_stream_wait(xemo_ctx* ctx, void* waiter_stream, void* signal_stream) {
+  cudaStream_t w = waiter_stream ? reinterpret_cast<cudaStream_t>(waiter_stream) : ctx->primary;
+  cudaStream_t s = signal_stream ? reinterpret_cast<cudaStream_t>(signal_stream) : ctx->primary;
+  cudaEvent_t ev;
+  XEMO_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  XEMO_CUDA(ctx, cudaEventRecord(ev, s));
+  XEMO_CUDA(ctx, cudaStreamWaitEvent(w, ev, 0));
+  XEMO_CUDA(ctx, cudaEventDestroy(ev));  // released once the recorded work has completed
+  return XEMO_OK;
+}
+
 // ================================================================================================
 // CUDA-graph capture
 extern "C" int xemo_capture_begin(xemo_ctx* ctx) {
   XEMO_REQUIRE(ctx, !ctx->capturing, "capture already in progress");
-  XEMO_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  XEMO_REQUIRE(ctx, ctx->stream == ctx->primary, "capture must begin on the primary stream");
+  XEMO_CUDA(ctx, cudaStreamBeginCapture(ctx->primary, cudaStreamCaptureModeThreadLocal));
   ctx->capturing = true;
   ctx->capture_mark = ctx->launches;
   return XEMO_OK;
@@ -79,7 +99,8 @@ extern "C" int xemo_capture_end(xemo_ctx* ctx, xemo_graph** out) {
   XEMO_REQUIRE(ctx, ctx->capturing && out, "no capture in progress");
   ctx->capturing = false;
   cudaGraph_t graph = nullptr;
-  XEMO_CUDA(ctx, cudaStreamEndCapture(ctx->stream, &graph));
+  ctx->stream = ctx->primary;
+  XEMO_CUDA(ctx, cudaStreamEndCapture(ctx->primary, &graph));
   xemo_graph* g = new xemo_graph();
   g->graph = graph;
   g->num_kernels = int(ctx->launches - ctx->capture_mark);
@@ -96,7 +117,7 @@ extern "C" int xemo_capture_end(xemo_ctx* ctx, xemo_graph** out) {
 
 extern "C" int xemo_graph_launch(xemo_ctx* ctx, xemo_graph* g) {
   XEMO_REQUIRE(ctx, g && g->exec, "null graph");
-  XEMO_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+  XEMO_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->primary));
   ctx->launches += uint64_t(g->num_kernels);
   return XEMO_OK;
 }

@@ -8,6 +8,8 @@ headline config fuses them, keeping the coupling operator (`max` / `mean` over t
 first numPredEmotions classes, then softmax(. / T) inside the loss)."""
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -17,7 +19,7 @@ from .programs import StudentProgram, TeacherProgram, _p
 
 class DistillationStep:
     def __init__(self, teacher_params, student_params, batch, width=300, frames_per_clip=1, aggregator="max", device=0,
-                 face_input="u8", face_size=48, use_graph=True, grad_scale=1024.0, temperature=2.0):
+                 face_input="u8", face_size=48, use_graph=True, grad_scale=1024.0, temperature=2.0, overlap=False):
         self.N, self.F = batch, frames_per_clip
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
@@ -29,6 +31,11 @@ class DistillationStep:
         self.student = StudentProgram(student_params, batch, width, device, self.stream, use_graph=False, grad_scale=grad_scale,
                                       temperature=temperature, ctx=self.ctx)
         self.use_mean = 1 if aggregator == "mean" else 0
+        # optional second stream: the teacher forward beside the student forward (they only meet at the loss) and the
+        # student's filter gradients beside its data-gradient chain.  Measured on B200 (profiles/): no gain -- every
+        # kernel already fills the machine (persistent 1-CTA/SM convolutions, full-occupancy HBM kernels) -- so off by default
+        self.side = torch.cuda.Stream(self.device) if overlap else None
+        self.student.side_stream = self.side
         with torch.cuda.stream(self.stream):
             self.start = torch.arange(0, batch * frames_per_clip, frames_per_clip, dtype=torch.int32, device=self.device)
             self.end = self.start + frames_per_clip
@@ -46,11 +53,19 @@ class DistillationStep:
 
     # ---- phases
     def _record_grad(self):
-        t, s = self.teacher, self.student
+        t, s, ctx = self.teacher, self.student, self.ctx
+        side = C.c_void_p(self.side.cuda_stream) if self.side is not None else None
+        if side:
+            ctx.stream_wait(side, None)   # fork
+            ctx.set_stream(side)
         t._record()
-        self.ctx.op_logit_aggregate(_p(t.a["logits"]), t.a["logits"].shape[1], _p(self.start), _p(self.end), self.N, s.K, self.use_mean,
-                                    _p(s.a["target"]))
+        ctx.op_logit_aggregate(_p(t.a["logits"]), t.a["logits"].shape[1], _p(self.start), _p(self.end), self.N, s.K, self.use_mean,
+                               _p(s.a["target"]))
+        if side:
+            ctx.set_stream(None)
         s._record_forward(True)
+        if side:
+            ctx.stream_wait(None, side)   # join: the loss needs the aggregated teacher logits
         s._record_backward()
 
     def grad_step(self):

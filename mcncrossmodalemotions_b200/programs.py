@@ -299,6 +299,7 @@ class StudentProgram(_Base):
         self.T = float(temperature)
         self.graphs = {}
         self.fuse_pool_bwd = False
+        self.side_stream = None   # torch.cuda.Stream: filter gradients run there, off the dgrad critical path
         self._geometry()
         self._load(params)
         self._alloc()
@@ -518,6 +519,10 @@ class StudentProgram(_Base):
                     ctx.op_bn_bwd(_p(A[n + ":raw"]), _p(dcur), rows, L["cout"], *common, 1, 0, *outs)
             dy = A[n + ":draw"]
             x = A["s2d"] if i == 0 else self._input_of(i)
+            side = self.side_stream is not None
+            if side:  # fork: the filter gradient needs dy (just produced) but nothing downstream needs it before the update
+                ctx.stream_wait(VP(self.side_stream.cuda_stream), None)
+                ctx.set_stream(VP(self.side_stream.cuda_stream))
             if n == "conv1":
                 ctx.op_conv_wgrad(_p(x), N, self.s2d_hp, self.s2d_ow, 16, _p(dy), L["kp"], L["kp"], 4, 1, 1, 1, 0, 0, 0, 0,
                                   _p(self.view(self.grad, n + "f")), inv)
@@ -532,12 +537,17 @@ class StudentProgram(_Base):
                                   L["stride"][1], *L["pad"], _p(self.view(self.grad, n + "f")), inv)
             if not fused_bias:
                 ctx.op_colsum(_p(dy), rows, L["kp"], L["kp"], inv, _p(self.view(self.grad, n + "b")))
+            if side:
+                ctx.set_stream(None)
             if i > 0:
                 cp = _pad16(L["cin"])
                 ctx.op_pack_dgrad_filters(_p(self.view(self.w16, n + "f")), L["kp"], L["fh"], L["fw"], cp, L["stride"][0],
                                           L["stride"][1], L["pad"][0], L["pad"][2], _p(A[n + ":packed"]))
                 ctx.op_conv_dgrad(_p(dy), N, L["h"], L["w"], cp, _p(A[n + ":packed"]), L["kp"], L["fh"], L["fw"], L["stride"][0],
                                   L["stride"][1], *L["pad"], _p(A[self.layers[i - 1]["name"] + ":dout"]))
+
+        if self.side_stream is not None:
+            ctx.stream_wait(None, VP(self.side_stream.cuda_stream))  # join before the update / all-reduce
 
     def _input_of(self, i):
         return self.a[self.layers[i - 1]["name"] + ":out"]

@@ -31,7 +31,7 @@ class Prof:
 
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-step = DistillationStep(zoo.teacher_init("senet50"), zoo.student_init(), B, 300, use_graph=False)
+step = DistillationStep(zoo.teacher_init("senet50"), zoo.student_init(), B, 300, use_graph=False, overlap=False)
 step.grad_step(); step.update(); step.sync()
 prof = Prof(step.stream)
 step.ctx.profiler = prof
