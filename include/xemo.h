@@ -144,6 +144,14 @@ int xemo_op_face_u8_rows_im2col(xemo_ctx* ctx, const uint8_t* faces, int IH, int
 int xemo_op_spec_s2d(xemo_ctx* ctx, const float* spec, int H, int W, int N, int pad_t, int pad_l, int HP, int OW,
                      void* dst16);
 
+/* student front-end (VGGVox runSpec called at emoVoxCeleb/getBatchEmoVoxCeleb.m:162,
+ * external/compute_audio_feats.m:176; constants emoVoxCeleb/run_distillation.m:109-117): wav [N][L] fp32 ->
+ * pre-emphasis (alpha) -> W frames of Nw samples every Ns -> Hamming -> |FFT_nfft| -> spec nfft x W x 1 x N
+ * column-major fp32; spec_rownorm = per-row (x - mean)/std over time, N-1 normalised (getBatchEmoVoxCeleb.m:164-169) */
+int xemo_op_spectrogram(xemo_ctx* ctx, const float* wav, int N, int L, int Nw, int Ns, int nfft, float alpha, float scale,
+                        int W, float* spec);
+int xemo_op_spec_rownorm(xemo_ctx* ctx, float* spec, int H, int W, int N);
+
 /* implicit-GEMM convolution on tcgen05: out = act(scale[k]*conv(x,w) + shift[k] + residual).
  * out16 (fp16) and/or out32 (fp32) receive [N*OH*OW][ldc]; scale/shift/residual may be NULL. */
 int xemo_op_conv_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int Cin, const void* w16, int Kout, int R,

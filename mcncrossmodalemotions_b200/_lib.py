@@ -65,6 +65,8 @@ SIGNATURES = {
     "xemo_op_face_rows_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "xemo_op_face_u8_rows_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "xemo_op_spec_s2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "xemo_op_spectrogram": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
+    "xemo_op_spec_rownorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int]),
     "xemo_op_conv_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int]),
     "xemo_dgrad_pack_elems": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),

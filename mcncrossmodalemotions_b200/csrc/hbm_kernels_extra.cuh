@@ -248,6 +248,63 @@ static __global__ void face_u8_rows_im2col_kernel(const uint8_t* __restrict__ sr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Spectrogram front-end (VGGVox `runSpec`, called at emoVoxCeleb/getBatchEmoVoxCeleb.m:162 and
+// external/compute_audio_feats.m:176 with the constants of emoVoxCeleb/run_distillation.m:109-117):
+//   y[n] = x[n] - alpha * x[n-1]  (pre-emphasis, y[0] = x[0]) ; frames of Nw samples every Ns samples, no padding ;
+//   symmetric Hamming window ; |FFT_nfft| with nfft = 2^nextpow2(Nw) -> nfft rows (the full spectrum).
+// One block per (frame, clip): the windowed frame is zero-padded to nfft in shared memory and transformed by an
+// in-place radix-2 FFT (fp32).  Output layout: nfft x W x 1 x N column-major (what the student graph consumes).
+static __global__ void spectrogram_kernel(const float* __restrict__ wav, int L, int Nw, int Ns, int nfft, int log2n,
+                                          float alpha, float scale, int W, float* __restrict__ spec) {
+  extern __shared__ float2 fft_buf[];  // [nfft]
+  const int t = blockIdx.x, n = blockIdx.y;
+  const float* x = wav + size_t(n) * L + size_t(t) * Ns;
+  for (int i = threadIdx.x; i < nfft; i += blockDim.x) {
+    float v = 0.f;
+    if (i < Nw) {
+      const size_t g = size_t(t) * Ns + i;  // index into the clip
+      const float cur = x[i] * scale;
+      const float prev = g > 0 ? x[i - 1] * scale : 0.f;
+      const float wgt = 0.54f - 0.46f * cospif(2.f * float(i) / float(Nw - 1));
+      v = (cur - alpha * prev) * wgt;
+    }
+    fft_buf[__brev(unsigned(i)) >> (32 - log2n)] = make_float2(v, 0.f);  // bit-reversed order for the DIT butterflies
+  }
+  __syncthreads();
+  for (int s = 1; s <= log2n; ++s) {
+    const int half = 1 << (s - 1);
+    for (int k = threadIdx.x; k < nfft / 2; k += blockDim.x) {
+      const int j = k & (half - 1);
+      const int i0 = ((k >> (s - 1)) << s) + j, i1 = i0 + half;
+      float sn, cs;
+      sincospif(-float(j) / float(half), &sn, &cs);  // exp(-2 pi i j / 2^s)
+      const float2 a = fft_buf[i0], b = fft_buf[i1];
+      const float2 tw = make_float2(b.x * cs - b.y * sn, b.x * sn + b.y * cs);
+      fft_buf[i0] = make_float2(a.x + tw.x, a.y + tw.y);
+      fft_buf[i1] = make_float2(a.x - tw.x, a.y - tw.y);
+    }
+    __syncthreads();
+  }
+  float* out = spec + (size_t(n) * W + t) * nfft;
+  for (int i = threadIdx.x; i < nfft; i += blockDim.x) out[i] = sqrtf(fft_buf[i].x * fft_buf[i].x + fft_buf[i].y * fft_buf[i].y);
+}
+
+// per frequency row (x - mean) / std over time, std with the N-1 normalisation (getBatchEmoVoxCeleb.m:164-169).
+// One block per clip, one thread per row (coalesced across rows), two-pass variance.  In place.
+static __global__ void spec_rownorm_kernel(float* __restrict__ spec, int H, int W) {
+  float* s = spec + size_t(blockIdx.x) * H * W;
+  for (int f = threadIdx.x; f < H; f += blockDim.x) {
+    float sum = 0.f;
+    for (int t = 0; t < W; ++t) sum += s[f + size_t(t) * H];
+    const float mu = sum / float(W);
+    float ss = 0.f;
+    for (int t = 0; t < W; ++t) { const float d = s[f + size_t(t) * H] - mu; ss = fmaf(d, d, ss); }
+    const float inv = rsqrtf(ss / float(W - 1));
+    for (int t = 0; t < W; ++t) s[f + size_t(t) * H] = (s[f + size_t(t) * H] - mu) * inv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // cnn_train_dag update with the hyper-parameters in device memory (hyper = {lr, momentum, wd, 1/B}),
 // so that a captured CUDA graph follows the learning-rate schedule without re-capture.
 static __global__ void sgd_momentum_dev_kernel(float* __restrict__ w, float* __restrict__ m, const float* __restrict__ g,

@@ -211,6 +211,27 @@ extern "C" int xemo_op_spec_s2d(xemo_ctx* ctx, const float* spec, int H, int W, 
   return XEMO_OK;
 }
 
+extern "C" int xemo_op_spectrogram(xemo_ctx* ctx, const float* wav, int N, int L, int Nw, int Ns, int nfft, float alpha,
+                                   float scale, int W, float* spec) {
+  XEMO_REQUIRE(ctx, wav && spec && N > 0 && Nw > 1 && Ns > 0 && nfft >= Nw && nfft <= 4096 && (nfft & (nfft - 1)) == 0,
+               "spectrogram: nfft must be a power of two in [Nw, 4096]");
+  XEMO_REQUIRE(ctx, W > 0 && W <= 65535 * 4 && size_t(W - 1) * Ns + Nw <= size_t(L), "spectrogram: %d frames need %zu samples, clip has %d", W,
+               size_t(W - 1) * Ns + Nw, L);
+  int log2n = 0;
+  while ((1 << log2n) < nfft) ++log2n;
+  dim3 grid(W, N);
+  spectrogram_kernel<<<grid, 256, size_t(nfft) * sizeof(float2), ctx->stream>>>(wav, L, Nw, Ns, nfft, log2n, alpha, scale, W, spec);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_spec_rownorm(xemo_ctx* ctx, float* spec, int H, int W, int N) {
+  XEMO_REQUIRE(ctx, spec && H > 0 && W > 1 && N > 0, "spec_rownorm: bad arguments");
+  spec_rownorm_kernel<<<N, 512, 0, ctx->stream>>>(spec, H, W);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
 // ================================================================================================
 // convolution
 static int run_fprop(xemo_ctx* ctx, const ConvGeom& g, const __half* x, const __half* w, const ConvEpilogue& e) {

@@ -19,7 +19,7 @@ from .programs import StudentProgram, TeacherProgram, _p
 
 class DistillationStep:
     def __init__(self, teacher_params, student_params, batch, width=300, frames_per_clip=1, aggregator="max", device=0,
-                 face_input="u8", face_size=48, use_graph=True, grad_scale=1024.0, temperature=2.0, overlap=False):
+                 face_input="u8", face_size=48, use_graph=True, grad_scale=1024.0, temperature=2.0, overlap=False, audio_input="spectrogram"):
         self.N, self.F = batch, frames_per_clip
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
@@ -29,7 +29,8 @@ class DistillationStep:
         self.teacher = TeacherProgram(teacher_params, batch * frames_per_clip, device, self.stream, use_graph=False, ctx=self.ctx,
                                       input_mode=face_input, face_size=face_size)
         self.student = StudentProgram(student_params, batch, width, device, self.stream, use_graph=False, grad_scale=grad_scale,
-                                      temperature=temperature, ctx=self.ctx)
+                                      temperature=temperature, ctx=self.ctx, audio_input=audio_input)
+        self.audio_key = "wav" if audio_input == "wav" else "spec"
         self.use_mean = 1 if aggregator == "mean" else 0
         # optional second stream: the teacher forward beside the student forward (they only meet at the loss) and the
         # student's filter gradients beside its data-gradient chain.  Measured on B200 (profiles/): no gain -- every
@@ -41,7 +42,7 @@ class DistillationStep:
             self.end = self.start + frames_per_clip
             # staging buffers the copy stream fills while the previous step computes
             self.stage_faces = torch.empty_like(self.teacher.a["faces"])
-            self.stage_spec = torch.empty_like(self.student.a["spec"])
+            self.stage_spec = torch.empty_like(self.student.a[self.audio_key]).view(-1)
             self.loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
         self.use_graph = use_graph
         self.g_grad = self.g_update = None
@@ -113,7 +114,7 @@ class DistillationStep:
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self.h2d_done)
             self.teacher.a["faces"].copy_(self.stage_faces, non_blocking=True)
-            self.student.a["spec"].copy_(self.stage_spec, non_blocking=True)
+            self.student.a[self.audio_key].view(-1).copy_(self.stage_spec, non_blocking=True)
             self.stage_free.record(self.stream)
         self.step_resident(allreduce)
         with torch.cuda.stream(self.stream):

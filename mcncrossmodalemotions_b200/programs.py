@@ -289,9 +289,18 @@ class TeacherProgram(_Base):
 class StudentProgram(_Base):
     """VGGVox student: forward (train / test mode BN), backward, loss + metrics, SGD-momentum."""
 
+    AUDIO = dict(fs=16000, Tw=25, Ts=10, alpha=0.97)   # emoVoxCeleb/run_distillation.m:109-117
+
     def __init__(self, params, batch, width=300, device=0, stream=None, use_graph=True, grad_scale=1024.0, num_classes=8,
-                 temperature=2.0, ctx=None):
+                 temperature=2.0, ctx=None, audio_input="spectrogram"):
+        """audio_input 'spectrogram': 512 x W x 1 x N row-normalised spectrograms (what getBatchEmoVoxCeleb hands to
+        dag.eval); 'wav': N x L waveform crops of L = (0.01 W + 0.024) * fs samples -- runSpec + the row normalisation
+        (getBatchEmoVoxCeleb.m:162-169) then run on the device ahead of the graph."""
         super().__init__(device, stream, ctx)
+        self.audio_input = audio_input
+        a = self.AUDIO
+        self.Nw, self.Ns = int(round(1e-3 * a["Tw"] * a["fs"])), int(round(1e-3 * a["Ts"] * a["fs"]))
+        self.wav_len = (width - 1) * self.Ns + self.Nw + (a["fs"] * 24 // 1000 - self.Nw + self.Ns)  # = (0.01 W + 0.024) fs
         self.N, self.W = batch, width
         self.use_graph = use_graph
         self.grad_scale = float(grad_scale)
@@ -376,6 +385,8 @@ class StudentProgram(_Base):
         N = self.N
         A = self.a = {}
         A["spec"] = self.f32(N * 512 * self.W)                   # 512 x W x 1 x N column-major fp32
+        if self.audio_input == "wav":
+            A["wav"] = self.f32(N, self.wav_len)
         A["s2d"] = self.f16(N, self.s2d_hp, self.s2d_ow, 16)
         A["target"] = self.f32(N, self.K)                        # aggregated teacher logits
         for L in self.layers:
@@ -410,6 +421,7 @@ class StudentProgram(_Base):
         if not train:
             return self._record_forward_test()
         N, A, ctx = self.N, self.a, self.ctx
+        self._record_frontend()
         ctx.op_spec_s2d(_p(A["spec"]), 512, self.W, N, 1, 1, self.s2d_hp, self.s2d_ow, _p(A["s2d"]))
         cur = A["s2d"]
         for L in self.layers:
@@ -445,6 +457,7 @@ class StudentProgram(_Base):
         """dag.mode = 'test' (external/compute_audio_feats.m:106): BN uses the stored moments, so it folds -- together
         with the conv bias -- into the convolution's scale/shift epilogue and the activation is rounded to fp16 once."""
         N, A, ctx = self.N, self.a, self.ctx
+        self._record_frontend()
         ctx.op_spec_s2d(_p(A["spec"]), 512, self.W, N, 1, 1, self.s2d_hp, self.s2d_ow, _p(A["s2d"]))
         cur = A["s2d"]
         for L in self.layers:
@@ -474,6 +487,15 @@ class StudentProgram(_Base):
                                    0, 0, 0, 0, _p(A[n + ":out"]))
                 dst = A[n + ":out"]
             cur = dst
+
+    def _record_frontend(self):
+        """runSpec + row normalisation on the device (audio_input == 'wav'); samples are scaled by 2^15 as runSpec does
+        for [-1, 1] audio (the row normalisation makes the result scale-free)."""
+        if self.audio_input != "wav":
+            return
+        A, ctx = self.a, self.ctx
+        ctx.op_spectrogram(_p(A["wav"]), self.N, self.wav_len, self.Nw, self.Ns, 512, self.AUDIO["alpha"], 32768.0, self.W, _p(A["spec"]))
+        ctx.op_spec_rownorm(_p(A["spec"]), 512, self.W, self.N)
 
     # ---- loss + backward
     def _record_backward(self):
@@ -585,10 +607,15 @@ class StudentProgram(_Base):
             self.hyper.copy_(torch.from_numpy(h))
 
     def set_input(self, spec, target=None):
+        """spec: 512 x W x 1 x N spectrograms, or N x L waveforms when audio_input == 'wav'."""
+        key = "wav" if self.audio_input == "wav" else "spec"
         if isinstance(spec, np.ndarray):
-            spec = torch.from_numpy(np.ascontiguousarray(spec.astype(np.float32).transpose(3, 2, 1, 0)).reshape(-1))
+            if key == "wav":
+                spec = torch.from_numpy(np.ascontiguousarray(spec, dtype=np.float32).reshape(-1))
+            else:
+                spec = torch.from_numpy(np.ascontiguousarray(spec.astype(np.float32).transpose(3, 2, 1, 0)).reshape(-1))
         with torch.cuda.stream(self.stream):
-            self.a["spec"].copy_(spec.reshape(-1), non_blocking=True)
+            self.a[key].view(-1).copy_(spec.reshape(-1), non_blocking=True)
             if target is not None:
                 if isinstance(target, np.ndarray):
                     target = torch.from_numpy(np.ascontiguousarray(target.astype(np.float32).reshape(self.K, self.N).T))

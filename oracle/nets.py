@@ -408,3 +408,20 @@ def faces48_to_input(u8, dtype=np.float32):
     g = u8.astype(dtype)[:, :, None, :]
     x = np.repeat(g, 3, axis=2) - AVERAGE_IMAGE.reshape(1, 1, 3, 1).astype(dtype)
     return bilinear_resize_hw(x, 224, 224)
+
+
+def run_spec(speech, fs=16000, Tw=25, Ts=10, alpha=0.97):
+    """VGGVox `runSpec` [UPSTREAM, restated from the public VGGVox / HTK-MFCC code it derives from; not in
+    /root/reference]: called at emoVoxCeleb/getBatchEmoVoxCeleb.m:162 with the constants of
+    emoVoxCeleb/run_distillation.m:109-117.  speech * 2^15 when max|speech| <= 1; pre-emphasis filter([1 -alpha], 1, .);
+    vec2frames(Nw, Ns, hamming, no padding); abs(fft(frames, 2^nextpow2(Nw))) -> nfft x M (full spectrum: 512 rows)."""
+    z = np.asarray(speech, np.float64).reshape(-1)
+    if np.abs(z).max() <= 1:
+        z = z * 2.0 ** 15
+    Nw, Ns = int(round(1e-3 * Tw * fs)), int(round(1e-3 * Ts * fs))
+    nfft = 1 << int(np.ceil(np.log2(Nw)))
+    y = np.concatenate([z[:1], z[1:] - alpha * z[:-1]])
+    M_ = (len(y) - Nw) // Ns + 1
+    idx = np.arange(Nw)[:, None] + Ns * np.arange(M_)[None, :]
+    win = 0.54 - 0.46 * np.cos(2 * np.pi * np.arange(Nw) / (Nw - 1))  # MATLAB hamming(Nw), symmetric
+    return np.abs(np.fft.fft(y[idx] * win[:, None], nfft, axis=0))

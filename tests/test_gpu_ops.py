@@ -101,3 +101,45 @@ def test_pool_gather_bn_backward_matches_two_pass(env):
     # both forms must return only rounding noise
     for o in outs:
         assert np.abs(o[3]).max() <= 0.05 * np.abs(o[2]).max()
+
+
+def test_spectrogram_front_end_matches_runspec_oracle(env):
+    """runSpec + row normalisation on the device vs the numpy restatement."""
+    torch, ctx, stream = env
+    from oracle import nets
+
+    N, W = 3, 300
+    L = int(round((0.01 * W + 0.024) * 16000))
+    rng = np.random.default_rng(0)
+    t = np.arange(L) / 16000.0
+    wav = np.stack([0.3 * np.sin(2 * np.pi * (300 + 500 * i) * t) + 0.05 * rng.standard_normal(L) for i in range(N)]).astype(np.float32)
+    ref = np.stack([nets.run_spec(w) for w in wav], axis=2)[:, :, None, :]        # 512 x W x 1 x N
+    assert ref.shape == (512, W, 1, N)
+    with torch.cuda.stream(stream):
+        wd = torch.from_numpy(wav).cuda()
+        sd = torch.zeros(N * W * 512, device="cuda")
+        ctx.op_spectrogram(_p(wd), N, L, 400, 160, 512, 0.97, 32768.0, W, _p(sd))
+        ctx.sync()
+        got = sd.cpu().numpy().reshape(N, W, 512).transpose(2, 1, 0)[:, :, None, :]
+        assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()
+        ctx.op_spec_rownorm(_p(sd), 512, W, N)
+        ctx.sync()
+        gotn = sd.cpu().numpy().reshape(N, W, 512).transpose(2, 1, 0)
+        refn = np.stack([nets.normalize_spectrogram(ref[:, :, 0, i]) for i in range(N)], axis=2)
+        assert np.abs(gotn - refn).max() <= 1e-3 * np.abs(refn).max()
+
+
+def test_student_from_waveforms(env):
+    from mcncrossmodalemotions_b200 import zoo
+    from mcncrossmodalemotions_b200.programs import StudentProgram
+    from oracle import nets
+
+    n, W = 4, 100
+    p = nets.student_randomize_bn(zoo.student_init())
+    prog = StudentProgram(p, n, W, audio_input="wav")
+    rng = np.random.default_rng(1)
+    wav = (0.1 * rng.standard_normal((n, prog.wav_len))).astype(np.float32)
+    spec = np.stack([nets.normalize_spectrogram(nets.run_spec(w)) for w in wav], axis=2)[:, :, None, :]
+    ref, _ = nets.student_forward({k: v.astype(np.float64) for k, v in p.items()}, spec, "test", nets.TorchOps)
+    got = prog.forward(wav, "test")
+    assert np.abs(got - ref.reshape(8, n).T).max() <= 1e-3 * np.abs(ref).max()
