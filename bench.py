@@ -316,8 +316,15 @@ def main():
         fl, t, n_launch, by = prof.summary()
         peaks = measured_peaks()
         achieved = fl / t / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+        if os.path.exists(tpath):   # dram__bytes_read+write of the same launches from the committed ncu capture
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get("per_gpu_batch") == B:
+                traffic = tj["dram_bytes"]
         roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tflops_sustained"], "traffic": None, "kernel": "conv_fprop_kernel / conv_wgrad_kernel (tcgen05)",
+                "frac": achieved / peaks["tflops_sustained"], "traffic": traffic, "traffic_unit": "bytes per step (all conv launches)", "kernel": "conv_fprop_kernel / conv_wgrad_kernel (tcgen05)",
                 "launches_per_step": n_launch, "conv_ms_per_step": t * 1e3, "by_op": by, "peak_source": peaks["source"] + ", sustained bf16",
                 "operand_dtype": "fp16 x fp16 -> fp32 (TMEM)"}
     barrier()
