@@ -210,3 +210,28 @@ def test_training_driver_helpers():
     assert np.isclose(st["meanAcc"], (0.75 + 0.5) / 8)
     with pytest.raises(ValueError):
         T.run_distillation(None, None, notAnOption=1)
+
+
+def test_dagnn_mat_files_round_trip(tmp_path):
+    from scipy.io import loadmat
+
+    from mcncrossmodalemotions_b200 import matfile, zoo
+    from oracle import nets
+
+    sp = nets.student_randomize_bn(zoo.student_init())
+    path = str(tmp_path / "emovoxceleb-student.mat")
+    matfile.save_dagnn(path, sp, "student")
+    raw = loadmat(path, squeeze_me=True)
+    assert {"layers", "params", "meta"} <= set(raw) and raw["layers"]["type"][0] == "dagnn.Conv" and len(raw["layers"]) == 8 + 2 * 7
+    back = matfile.load_dagnn(path, "student")
+    assert back.keys() == sp.keys() and all(np.array_equal(back[k], sp[k]) for k in sp)
+    tp = zoo.teacher_init("senet50-ferplus")
+    path = str(tmp_path / "senet50-ferplus.mat")
+    matfile.save_dagnn(path, tp, "teacher")
+    back = matfile.load_dagnn(path, "teacher")
+    assert back["arch"] == "senet50" and all(np.array_equal(back[k], tp[k]) for k in tp if k != "arch")
+    # a file with the wrong shapes is rejected instead of being silently mis-mapped
+    bad = dict(sp); bad["conv3f"] = bad["conv3f"][:, :, :, :100]
+    matfile.save_dagnn(str(tmp_path / "bad.mat"), bad, "student")
+    with pytest.raises(ValueError):
+        matfile.load_dagnn(str(tmp_path / "bad.mat"), "student")
