@@ -65,5 +65,20 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+def build_selftest(force=False):
+    """The standalone convolution bring-up harness (tools/conv_selftest.cu -> build/conv_selftest)."""
+    src = os.path.join(HERE, "..", "tools", "conv_selftest.cu")
+    out = os.path.join(HERE, "..", "build", "conv_selftest")
+    deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    if force or _stale(out, deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        r = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", src, "-o", out],
+                           capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed on conv_selftest.cu")
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))
