@@ -285,6 +285,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (p.use_tma_store && leader) {
           if (epi_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
         }
+        uint32_t va[16], vb[16];
+        tmem_ld16(taddr + uint32_t(q * cw), va);  // in flight across the waits below
         if (tg < cw) {
           ss_scale[tg] = p.scale ? __ldg(p.scale + n0 + q * cw + tg) : 1.f;
           ss_shift[tg] = p.shift ? __ldg(p.shift + n0 + q * cw + tg) : 0.f;
@@ -292,11 +294,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         epi_bar_sync(group);  // staging buffer free, scale/shift visible
         if (p.use_tma_residual) mbar_wait(rbar0 + buf, (epi_bufs == 2 ? (mine >> 1) : mine) & 1u);
 
-        for (int jj = 0; jj < cw; jj += 16) {
+        // 16 accumulator columns -> scale/shift (+residual, ReLU) -> fp16 staging / direct stores
+        auto process = [&](const uint32_t (&v)[16], int jj) {
           const int j = q * cw + jj;  // column inside the tile
-          uint32_t v[16];
-          tmem_ld16(taddr + uint32_t(j), v);
-          tmem_ld_wait();
           float x[16];
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
@@ -349,6 +349,19 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             float4* fp = reinterpret_cast<float4*>(p.out_f32 + row_off + j);
 #pragma unroll
             for (int i = 0; i < 4; ++i) fp[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+          }
+        };
+        // software pipeline over the chunk: the tcgen05.ld of the next 16 columns is in flight while the current
+        // 16 are processed (the first load was issued before the barrier / residual waits above)
+        for (int jj = 0; jj < cw; jj += 32) {
+          tmem_ld_wait();
+          const bool second = jj + 16 < cw;
+          if (second) tmem_ld16(taddr + uint32_t(q * cw + jj + 16), vb);
+          process(va, jj);
+          if (second) {
+            tmem_ld_wait();
+            if (jj + 32 < cw) tmem_ld16(taddr + uint32_t(q * cw + jj + 32), va);
+            process(vb, jj + 16);
           }
         }
         if (p.use_tma_store) {

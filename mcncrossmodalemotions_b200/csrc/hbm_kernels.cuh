@@ -1002,28 +1002,30 @@ __global__ void relu_bwd_kernel(const T* __restrict__ y, const T* __restrict__ d
 // ============================================================================================
 template <typename T>
 __global__ void se_squeeze_kernel(const T* __restrict__ u, int HW, int C, float* __restrict__ s) {
-  // grid: (ceil(C/8/32), N); block 32 x 32: lane -> channel group, y -> pixel stride (4 loads in flight)
+  // grid: (ceil(C/8/LX), N); block LX x LY (= 1024 threads): x -> channel group, y -> pixel stride, four 16-byte
+  // loads in flight per thread.  LX = min(32, C/8) so that narrow tensors still fill the block.
+  const int LX = blockDim.x, LY = blockDim.y;
   const int n = blockIdx.y;
-  const int c8 = blockIdx.x * 32 + threadIdx.x;
-  __shared__ float part[32][32][9];
+  const int c8 = blockIdx.x * LX + threadIdx.x;
+  __shared__ float part[1024 * 9];
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   if (c8 * 8 < C) {
     const T* base = u + size_t(n) * HW * C + c8 * 8;
     int p = threadIdx.y;
-    for (; p + 96 < HW; p += 128) {
+    for (; p + 3 * LY < HW; p += 4 * LY) {
       Vec8<T> v0, v1, v2, v3;
       v0.load(base + size_t(p) * C);
-      v1.load(base + size_t(p + 32) * C);
-      v2.load(base + size_t(p + 64) * C);
-      v3.load(base + size_t(p + 96) * C);
+      v1.load(base + size_t(p + LY) * C);
+      v2.load(base + size_t(p + 2 * LY) * C);
+      v3.load(base + size_t(p + 3 * LY) * C);
       float f0[8], f1[8], f2[8], f3[8];
       v0.to_float(f0); v1.to_float(f1); v2.to_float(f2); v3.to_float(f3);
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] += (f0[k] + f1[k]) + (f2[k] + f3[k]);
     }
-    for (; p < HW; p += 32) {
+    for (; p < HW; p += LY) {
       Vec8<T> v;
       v.load(base + size_t(p) * C);
       float f[8];
@@ -1032,18 +1034,18 @@ __global__ void se_squeeze_kernel(const T* __restrict__ u, int HW, int C, float*
       for (int k = 0; k < 8; ++k) acc[k] += f[k];
     }
   }
+  float* mine = part + (threadIdx.y * LX + threadIdx.x) * 9;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) part[threadIdx.y][threadIdx.x][k] = acc[k];
+  for (int k = 0; k < 8; ++k) mine[k] = acc[k];
   __syncthreads();
-  // 32 x 8 (channel-group, k) outputs, each summed over the 32 pixel strides by one thread
-  const int t = threadIdx.y * 32 + threadIdx.x;
-  if (t < 256) {
+  // LX x 8 (channel-group, k) outputs, each summed over the LY pixel strides by one thread
+  const int t = threadIdx.y * LX + threadIdx.x;
+  if (t < LX * 8) {
     const int cg = t >> 3, k = t & 7;
-    const int c = (blockIdx.x * 32 + cg) * 8 + k;
+    const int c = (blockIdx.x * LX + cg) * 8 + k;
     if (c < C) {
       float tsum = 0.f;
-#pragma unroll 8
-      for (int j = 0; j < 32; ++j) tsum += part[j][cg][k];
+      for (int j = 0; j < LY; ++j) tsum += part[(j * LX + cg) * 9 + k];
       s[size_t(n) * C + c] = tsum / float(HW);
     }
   }

@@ -575,7 +575,10 @@ extern "C" int xemo_op_add_act(xemo_ctx* ctx, const void* a16, const void* b16, 
 // squeeze-and-excitation
 extern "C" int xemo_op_se_squeeze(xemo_ctx* ctx, const void* u16, int N, int HW, int C, float* s) {
   XEMO_REQUIRE(ctx, u16 && s && C % 8 == 0, "se_squeeze: bad arguments");
-  dim3 grid((C / 8 + 31) / 32, N), block(32, 32);
+  const int C8 = C / 8;
+  int lx = 1;
+  while (lx < 32 && lx * 2 <= C8) lx *= 2;   // min(32, largest power of two <= C/8)
+  dim3 grid((C8 + lx - 1) / lx, N), block(lx, 1024 / lx);
   se_squeeze_kernel<__half><<<grid, block, 0, ctx->stream>>>(static_cast<const __half*>(u16), HW, C, s);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;

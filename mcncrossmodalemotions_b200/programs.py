@@ -240,6 +240,8 @@ class TeacherProgram(_Base):
             a, b = W[pre + "bn3"]
             if se:
                 self.conv(A[pre + "t2"], N, ohw, ohw, mid, W[pre + "c3"], cout, 1, 1, (1, 1), (0, 0, 0, 0), a, b, None, 0, A[pre + "u"])
+                # (computing the squeeze by linearity from mean_hw(t2) -- 4x fewer bytes -- was measured: the extra tiny
+                # launches cost what the narrower read saves, so the direct form stays)
                 ctx.op_se_squeeze(_p(A[pre + "u"]), N, ohw * ohw, cout, _p(A[pre + "s"]))
                 ctx.op_se_gate(_p(A[pre + "s"]), N, cout, cout // 16, _p(W[pre + "se1"]), _p(W[pre + "se1b"]), _p(W[pre + "se2"]),
                                _p(W[pre + "se2b"]), _p(A[pre + "g"]))
