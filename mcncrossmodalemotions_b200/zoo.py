@@ -81,18 +81,126 @@ def pool6_window(width):
     return (1, POOL6_BUCKETS[width])
 
 
-class Model:
-    """What `emoVoxZoo` / `ferPlusZoo` hand to the reference scripts, reduced to what they touch: the parameters
-    (MatConvNet layouts), `meta.normalization`, the layer names they look up (`pool6`), `mode`, `move` and `eval`."""
+class _Block:
+    """dagnn block stand-in: `type` (e.g. 'dagnn.Pooling') plus the attributes the reference scripts touch
+    (`poolSize`, emoVoxCeleb/emoVoxZoo.m:269, external/compute_audio_feats.m:125)."""
 
-    def __init__(self, name, params, kind, width=None):
+    def __init__(self, type_, **attrs):
+        self.type = type_
+        self.__dict__.update(attrs)
+
+    def isa(self, cls):
+        loss_family = ("dagnn.Loss", "dagnn.SoftmaxCELoss", "dagnn.VerboseLoss", "dagnn.ErrorStats")
+        return self.type == cls or (cls == "dagnn.Loss" and self.type in loss_family)
+
+
+class _Layer:
+    def __init__(self, name, block, inputs, outputs, params=()):
+        self.name, self.block, self.inputs, self.outputs, self.params = name, block, list(inputs), list(outputs), list(params)
+
+
+class _Var:
+    def __init__(self, name):
+        self.name, self.value = name, None
+
+
+class Model:
+    """The dagnn.DagNN object `emoVoxZoo` / `ferPlusZoo` hand to the reference scripts, reduced to what those scripts
+    touch: `layers(i).{name,block}`, `removeLayer`, `getLayerIndex`, `getInputs`, `renameVar`,
+    `mode`, `move`, `meta.normalization`, `layers(pool6).block.poolSize`, `eval({'data', x})`, `vars(end).value`,
+    `params`.  `eval` runs the fused device program of the graph; there is no layer-by-layer interpreter."""
+
+    def __init__(self, name, params, kind, width=None, loss_type=None):
         self.name, self.params, self.kind = name, params, kind
         self.mode = "test" if kind == "teacher" else "normal"
         self.device = "cpu"
         self.meta = {"normalization": {"imageSize": (224, 224, 3) if kind == "teacher" else (512, width, 1),
-                                       "averageImage": AVERAGE_IMAGE if kind == "teacher" else None}}
-        self.pool6 = pool6_window(width) if kind == "student" else None
+                                       "averageImage": AVERAGE_IMAGE if kind == "teacher" else None},
+                     "classes": {"name": ["neutral", "happiness", "surprise", "sadness", "anger", "disgust", "fear", "contempt"]}}
+        self.layers, self.vars = [], [_Var("data")]
+        self._build_layers(loss_type)
         self._prog = None
+
+    # ---- graph description
+    def _add(self, name, block, inputs, outputs, params=()):
+        self.layers.append(_Layer(name, block, inputs, outputs, params))
+        for o in outputs:
+            if o not in [v.name for v in self.vars]:
+                self.vars.append(_Var(o))
+
+    def _build_layers(self, loss_type):
+        prev = "data"
+        if self.kind == "student":
+            width = self.meta["normalization"]["imageSize"][1]
+            for name, fh, fw, cin, cout, stride, pad, has_bn in STUDENT_CONVS:
+                out = "prediction" if name == "fc8" else "x_" + name
+                self._add(name, _Block("dagnn.Conv", size=(fh, fw, cin, cout), stride=stride, pad=pad), [prev], [out], [name + "f", name + "b"])
+                prev = out
+                if has_bn:
+                    i = name[-1]
+                    self._add("bn" + i, _Block("dagnn.BatchNorm", epsilon=1e-5), [prev], ["x_bn" + i], ["bn%sm" % i, "bn%sb" % i, "bn%sx" % i])
+                    self._add("relu" + i, _Block("dagnn.ReLU"), ["x_bn" + i], ["x_relu" + i])
+                    prev = "x_relu" + i
+                pool = {"conv1": ("pool1", "max", (3, 3), (2, 2)), "conv2": ("pool2", "max", (3, 3), (2, 2)),
+                        "conv5": ("pool5", "max", (5, 3), (3, 2)), "fc6": ("pool6", "avg", pool6_window(width), (1, 1))}.get(name)
+                if pool:
+                    self._add(pool[0], _Block("dagnn.Pooling", method=pool[1], poolSize=tuple(pool[2]), stride=pool[3], pad=(0, 0, 0, 0)),
+                              [prev], ["x_" + pool[0]])
+                    prev = "x_" + pool[0]
+            if loss_type == "hot-cross-ent":   # configureForRegression, emoVoxZoo.m:151-169
+                self._add("loss", _Block("dagnn.SoftmaxCELoss", temperature=2, logitTargets=True), ["prediction", "logitTarget"], ["objective"])
+                self._add("error", _Block("dagnn.VerboseLoss", loss="classerror"), ["prediction", "maxLabel"], ["classerror"])
+                self._add("errorStats", _Block("dagnn.ErrorStats", numClasses=8), ["prediction", "maxLabel"], ["errorStats"])
+        else:
+            self._add("conv1", _Block("dagnn.Conv", size=(7, 7, 3, 64), stride=(2, 2), pad=(3, 3, 3, 3)), ["data"], ["conv1"], ["conv1f"])
+            self._add("pool1", _Block("dagnn.Pooling", method="max", poolSize=(3, 3), stride=(2, 2), pad=(0, 1, 0, 1)), ["conv1"], ["pool1"])
+            prev = "pool1"
+            for si, (blocks, mid, cout, stride) in enumerate(TEACHER_STAGES):
+                for bi in range(blocks):
+                    pre = "s%db%d" % (si + 2, bi + 1)
+                    self._add(pre, _Block("bottleneck", mid=mid, out=cout, stride=stride if bi == 0 else 1, se=self.params["arch"] == "senet50"),
+                              [prev], [pre])
+                    prev = pre
+            self._add("pool5", _Block("dagnn.Pooling", method="avg", poolSize=(7, 7), stride=(1, 1), pad=(0, 0, 0, 0)), [prev], ["pool5"])
+            self._add("classifier", _Block("dagnn.Conv", size=(1, 1, 2048, 8), stride=(1, 1), pad=(0, 0, 0, 0)), ["pool5"], ["prediction"],
+                      ["classifierf", "classifierb"])
+
+    # ---- the DagNN methods the scripts call
+    def getLayerIndex(self, name):
+        for i, l in enumerate(self.layers):
+            if l.name == name:
+                return i
+        raise KeyError("no layer named %s" % name)
+
+    def removeLayer(self, name):
+        i = self.getLayerIndex(name)
+        if not self.layers[i].block.isa("dagnn.Loss"):
+            raise ValueError("only loss / metric layers can be removed from the fused graphs")
+        del self.layers[i]
+        used = {v for l in self.layers for v in l.inputs + l.outputs}
+        self.vars = [v for v in self.vars if v.name in used]
+
+    def getInputs(self):
+        produced = {o for l in self.layers for o in l.outputs}
+        seen, out = set(), []
+        for l in self.layers:
+            for v in l.inputs:
+                if v not in produced and v not in seen:
+                    seen.add(v)
+                    out.append(v)
+        return out
+
+    def renameVar(self, old, new):
+        for l in self.layers:
+            l.inputs = [new if v == old else v for v in l.inputs]
+            l.outputs = [new if v == old else v for v in l.outputs]
+        for v in self.vars:
+            if v.name == old:
+                v.name = new
+
+    @property
+    def pool6(self):
+        return self.layers[self.getLayerIndex("pool6")].block.poolSize if self.kind == "student" else None
 
     def move(self, device):
         if device not in ("gpu", "cpu"):
@@ -102,20 +210,31 @@ class Model:
         self.device = device
 
     def eval(self, inputs):
-        """dag.eval({'data', x}) -> N x 8 (teacher: logits; student: predictions in the current mode's BN)."""
+        """dag.eval({'data', x}): runs the fused program, stores `prediction` (1 x 1 x K x N) in vars(end).value when it
+        is the last variable (losses removed), and returns it as N x K (`gather(squeeze(dag.vars(end).value))'`)."""
         from .programs import StudentProgram, TeacherProgram
 
-        x = inputs["data"]
+        if isinstance(inputs, (list, tuple)):   # MATLAB-style {'data', x}
+            inputs = dict(zip(inputs[0::2], inputs[1::2]))
+        x = inputs[self.getInputs()[0]]
         n = x.shape[-1]
-        if self._prog is None or self._prog.N != n:
-            if self.kind == "teacher":
+        if self.kind == "teacher":
+            if self._prog is None or self._prog.N != n:
                 self._prog = TeacherProgram(self.params, n, input_mode="u8" if x.ndim == 3 else "hwcn224",
                                             face_size=x.shape[0] if x.ndim == 3 else 48)
-            else:
-                self._prog = StudentProgram(self.params, n, x.shape[1])
-        if self.kind == "teacher":
-            return self._prog.forward(x)
-        return self._prog.forward(x, "test" if self.mode == "test" else "train")
+            out = self._prog.forward(x)
+        else:
+            width = x.shape[1]
+            if self.pool6 != pool6_window(width):
+                raise ValueError("pool6.poolSize = %s does not match a %d-column input (expected %s): set it from the width bucket "
+                                 "as compute_audio_feats.m:121-125 does" % (self.pool6, width, pool6_window(width)))
+            if self._prog is None or self._prog.N != n or self._prog.W != width:
+                self._prog = StudentProgram(self.params, n, width)
+            out = self._prog.forward(x, "test" if self.mode == "test" else "train")
+        for v in self.vars:
+            if v.name == "prediction":
+                v.value = out.T.reshape(1, 1, out.shape[1], n)
+        return out
 
 
 def emoVoxZoo(modelName, scratch=False, lossType="hot-cross-ent", numSeconds=4, numOutputs=8, seed=3):
@@ -130,7 +249,7 @@ def emoVoxZoo(modelName, scratch=False, lossType="hot-cross-ent", numSeconds=4, 
     if lossType not in ("hot-cross-ent", "softmaxlog", "euclidean", "huber"):
         raise ValueError("unrecognised loss type: %s" % lossType)
     width = 100 * int(numSeconds)
-    return Model(modelName, student_init(seed, numOutputs), "student", width)
+    return Model(modelName, student_init(seed, numOutputs), "student", width, loss_type=lossType if scratch else None)
 
 
 def ferPlusZoo(modelName):

@@ -235,3 +235,29 @@ def test_dagnn_mat_files_round_trip(tmp_path):
     matfile.save_dagnn(str(tmp_path / "bad.mat"), bad, "student")
     with pytest.raises(ValueError):
         matfile.load_dagnn(str(tmp_path / "bad.mat"), "student")
+
+
+def test_zoo_model_mirrors_the_dagnn_calls_of_the_reference_scripts():
+    from mcncrossmodalemotions_b200 import zoo
+
+    dag = zoo.emoVoxZoo("emovoxceleb-student", scratch=True, lossType="hot-cross-ent", numSeconds=4)
+    assert dag.getInputs() == ["data", "logitTarget", "maxLabel"]          # emoVoxZoo.m:151-169 wiring
+    assert dag.layers[dag.getLayerIndex("loss")].block.temperature == 2 and dag.layers[dag.getLayerIndex("loss")].block.logitTargets
+    assert dag.layers[dag.getLayerIndex("pool6")].block.poolSize == (1, 11)
+    # compute_audio_feats.m:101-110: strip the losses, test mode, single input, `prediction` is the last variable
+    for name in [l.name for l in dag.layers if l.block.isa("dagnn.Loss")]:
+        dag.removeLayer(name)
+    dag.mode = "test"
+    assert dag.getInputs() == ["data"] and dag.vars[-1].name == "prediction"
+    with pytest.raises(ValueError):
+        dag.removeLayer("conv3")
+    with pytest.raises(KeyError):
+        dag.getLayerIndex("pool7")
+    dag.layers[dag.getLayerIndex("pool6")].block.poolSize = (1, 8)          # compute_audio_feats.m:125
+    assert dag.pool6 == (1, 8)
+    dag.renameVar("data", "input")
+    assert dag.getInputs() == ["input"]
+    teacher = zoo.ferPlusZoo("senet50-ferplus")
+    assert teacher.mode == "test" and teacher.getInputs() == ["data"] and teacher.vars[-1].name == "prediction"
+    assert teacher.meta["normalization"]["imageSize"] == (224, 224, 3) and len(teacher.meta["classes"]["name"]) == 8
+    assert sum(l.block.type == "bottleneck" for l in teacher.layers) == 16
