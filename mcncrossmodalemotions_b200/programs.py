@@ -500,16 +500,21 @@ class StudentProgram(_Base):
         ctx.op_spec_rownorm(_p(A["spec"]), 512, self.W, self.N)
 
     # ---- loss + backward
-    def _record_backward(self):
+    def _record_backward(self, lo=0, hi=None, loss=True):
+        """Loss (when `loss`) and the backward sweep over layers [lo, hi) in reverse order.  The split form lets the
+        data-parallel step all-reduce the gradients of the late layers (fc6-fc8: 82 % of the bytes) while the early
+        layers are still being differentiated."""
         N, A, ctx, gs = self.N, self.a, self.ctx, self.grad_scale
         inv = 1.0 / gs
         last = self.layers[-1]
-        ctx.memset(_p(self.grad), 0, self.nparam * 4)
-        ctx.memset(_p(A["fc8:draw"]), 0, A["fc8:draw"].numel() * 2)
-        ctx.memset(_p(A["scalars"]), 0, 8)  # objective / classerror of THIS batch (class_stats keep accumulating)
-        ctx.op_softmaxce(_p(A["fc8:raw"]), last["kp"], _p(A["target"]), self.K, None, N, self.K, self.T, 1, 1.0, gs,
-                         _p(A["fc8:draw"]), _p(A["scalars"]), _p(A["class_stats"]), _p(A["max_label"]))
-        for i in range(len(self.layers) - 1, -1, -1):
+        hi = len(self.layers) if hi is None else hi
+        if loss:
+            ctx.memset(_p(self.grad), 0, self.nparam * 4)
+            ctx.memset(_p(A["fc8:draw"]), 0, A["fc8:draw"].numel() * 2)
+            ctx.memset(_p(A["scalars"]), 0, 8)  # objective / classerror of THIS batch (class_stats keep accumulating)
+            ctx.op_softmaxce(_p(A["fc8:raw"]), last["kp"], _p(A["target"]), self.K, None, N, self.K, self.T, 1, 1.0, gs,
+                             _p(A["fc8:draw"]), _p(A["scalars"]), _p(A["class_stats"]), _p(A["max_label"]))
+        for i in range(hi - 1, lo - 1, -1):
             L = self.layers[i]
             n = L["name"]
             rows = N * L["oh"] * L["ow"]
