@@ -174,6 +174,10 @@ int xemo_op_colsum(xemo_ctx* ctx, const void* dy16, size_t P, int ld, int C, flo
  * the pooling read) and emits the uint8 window-local arg-max dw*PH + dh that maxpool_bwd consumes. */
 int xemo_op_maxpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
                         int pt, int pb, int pl, int pr, const float* a, const float* b, void* y16, uint8_t* argmax);
+/* the same, also recording the raw (pre-affine) value of each window's winner in xwin16 [N][OH][OW][C] (3x3 / 5x3 windows) */
+int xemo_op_maxpool_fwd_win(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
+                            int pt, int pb, int pl, int pr, const float* a, const float* b, void* y16, uint8_t* argmax,
+                            void* xwin16);
 int xemo_op_maxpool_bwd(xemo_ctx* ctx, const void* dy16, const uint8_t* argmax, int N, int H, int W, int C, int PH,
                         int PW, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16);
 int xemo_op_avgpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
@@ -206,6 +210,29 @@ int xemo_op_bn_bwd_pool(xemo_ctx* ctx, const void* x16, const void* dpool16, con
                         float inv_grad_scale);
 int xemo_op_relu_bwd(xemo_ctx* ctx, const void* y16, const void* dy16, size_t n, void* dx16);
 int xemo_op_add_act(xemo_ctx* ctx, const void* a16, const void* b16, size_t n, int relu, void* y16);
+
+/* student stem (conv1 of the VGGVox graph built at emoVoxCeleb/emoVoxZoo.m:50-62 on the 512 x W x 1 batch of
+ * getBatchEmoVoxCeleb.m:197, followed by train-mode BN + ReLU + 3x3/2 max pool under cnn_train_dag,
+ * run_distillation.m:170).  With one input channel the layer is linear in the 64-entry space-to-depth patch, so
+ * the BN statistics and the BN / filter gradients follow from the patch autocorrelation R (64 x 64) and patch sum S
+ * instead of passes over the 1.85 GB conv1 activation (csrc/stem_kernels.cuh).
+ * stem_autocorr      : s2d16 [N][HP][OW][16] (xemo_op_spec_s2d), HP == OH + 3 -> ws (xemo_stem_ws_doubles() doubles):
+ *                      row-pair products then the assembled [R | S]
+ * stem_bn_train      : as bn_train for x = conv(s2d, w16 [C][64]) + bias, from ws
+ * stem_pool_bn_reduce: xwin16 / dpool16 [P][C] at the POOLED resolution (xemo_op_maxpool_fwd_win); masks dpool16
+ *                      in place with [a*xwin+b > 0] and accumulates acc[2C] = {sum dz, sum dz*xhat} (doubles)
+ * stem_wgrad_finalize: dW [C][64] holds G1 = inv_grad_scale * sum_p dz[p,.] patch[p] (xemo_op_conv_wgrad on the dz
+ *                      that xemo_op_maxpool_bwd scatters from the masked dpool16) and is overwritten with the
+ *                      filter gradient A*G1 - D*(R w + bias*S) + E*S; dgamma/dbeta = inv_grad_scale*acc; dbias = 0 */
+size_t xemo_stem_ws_doubles(void);
+int xemo_op_stem_autocorr(xemo_ctx* ctx, const void* s2d16, int N, int HP, int OW, int OH, double* ws);
+int xemo_op_stem_bn_train(xemo_ctx* ctx, const double* ws, const void* w16, const float* bias, size_t P, int C,
+                          const float* g, const float* beta, float eps, float* moments, float* a, float* b);
+int xemo_op_stem_pool_bn_reduce(xemo_ctx* ctx, const void* xwin16, void* dpool16, size_t P, int C, const float* moments,
+                                const float* a, const float* b, double* acc);
+int xemo_op_stem_wgrad_finalize(xemo_ctx* ctx, const double* ws, const void* w16, const float* bias, const double* acc,
+                                size_t P, int C, const float* moments, const float* a, float inv_grad_scale, float* dW,
+                                float* dbias, float* dgamma, float* dbeta);
 
 /* squeeze-and-excitation: s = mean_hw(u) ; gate = sigmoid(W2 relu(W1 s + b1) + b2) ; y = relu(gate*u + shortcut).
  * w1 is [Cr][C]; w2 is passed TRANSPOSED, [Cr][C] (w2t[j][c] = W2[c][j]), so that the gate kernel reads it coalesced. */

@@ -348,7 +348,8 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __re
 // compared four at a time and the selected gradients accumulated in half2.
 template <bool kAffineRelu, int PH, int PW, bool kNoPad>
 __global__ void maxpool_fwd_h2_kernel(const __half* __restrict__ x, PoolGeom g, const float* __restrict__ a,
-                                      const float* __restrict__ b, __half* __restrict__ y, uint8_t* __restrict__ idx) {
+                                      const float* __restrict__ b, __half* __restrict__ y, uint8_t* __restrict__ idx,
+                                      __half* __restrict__ xwin) {
   const uint32_t C8 = uint32_t(g.C >> 3);
   const uint32_t npix = uint32_t(g.N) * uint32_t(g.OH) * uint32_t(g.OW);
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -397,12 +398,14 @@ __global__ void maxpool_fwd_h2_kernel(const __half* __restrict__ x, PoolGeom g, 
         }
       }
     }
-    uint4 o;
+    uint4 o, xo;
     __half2* o2 = reinterpret_cast<__half2*>(&o);
+    __half2* xo2 = reinterpret_cast<__half2*>(&xo);
     uint32_t ab[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float2 f = __half22float2(kAffineRelu ? __hmul2(best[k], sgn[k]) : best[k]);
+      xo2[k] = kAffineRelu ? __hmul2(best[k], sgn[k]) : best[k];   // the raw (pre-affine) value of the winner
+      float2 f = __half22float2(xo2[k]);
       ab[2 * k] = arg[k] & 0xFFFFu;
       ab[2 * k + 1] = arg[k] >> 16;
       if (kAffineRelu) {
@@ -415,6 +418,7 @@ __global__ void maxpool_fwd_h2_kernel(const __half* __restrict__ x, PoolGeom g, 
     }
     const size_t off = ((size_t(n) * g.OH + oh) * g.OW + ow) * g.C + c8 * 8;
     *reinterpret_cast<uint4*>(y + off) = o;
+    if (xwin) *reinterpret_cast<uint4*>(xwin + off) = xo;   // consumed by stem_pool_bn_reduce_kernel
     if (idx) {
       uint2 pk;
       pk.x = ab[0] | (ab[1] << 8) | (ab[2] << 16) | (ab[3] << 24);

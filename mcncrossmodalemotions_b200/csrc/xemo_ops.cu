@@ -4,6 +4,7 @@
 
 #include "conv_launch.cuh"
 #include "hbm_kernels_extra.cuh"
+#include "stem_kernels.cuh"
 
 using namespace xemo;
 
@@ -391,9 +392,9 @@ static bool pool_geom(PoolGeom* g, int N, int H, int W, int C, int PH, int PW, i
   return g->OH > 0 && g->OW > 0 && C % 8 == 0 && PH * PW <= 255;
 }
 
-extern "C" int xemo_op_maxpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
-                                   int pt, int pb, int pl, int pr, const float* a, const float* b, void* y16,
-                                   uint8_t* argmax) {
+static int maxpool_fwd_impl(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
+                            int pt, int pb, int pl, int pr, const float* a, const float* b, void* y16, uint8_t* argmax,
+                            __half* xwin) {
   PoolGeom g;
   XEMO_REQUIRE(ctx, x16 && y16 && pool_geom(&g, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr), "maxpool_fwd: bad geometry");
   const size_t total = size_t(N) * g.OH * g.OW * (C / 8);
@@ -404,10 +405,11 @@ extern "C" int xemo_op_maxpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H,
 #define XEMO_POOL_FWD(AFF, PHc, PWc) maxpool_fwd_kernel<__half, AFF, PHc, PWc><<<grid, 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax)
 #define XEMO_POOL_FWD_H2(AFF, PHc, PWc)                                                                                   \
   do {                                                                                                                     \
-    if (nopad) maxpool_fwd_h2_kernel<AFF, PHc, PWc, true><<<grid, 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax);          \
-    else maxpool_fwd_h2_kernel<AFF, PHc, PWc, false><<<grid, 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax);               \
+    if (nopad) maxpool_fwd_h2_kernel<AFF, PHc, PWc, true><<<grid, 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax, xwin);    \
+    else maxpool_fwd_h2_kernel<AFF, PHc, PWc, false><<<grid, 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax, xwin);         \
   } while (0)
   const bool nopad = (pt == 0 && pl == 0 && (g.OH - 1) * sh + PH <= H && (g.OW - 1) * sw + PW <= W);
+  XEMO_REQUIRE(ctx, !xwin || (PH == 3 && PW == 3) || (PH == 5 && PW == 3), "maxpool_fwd_win: only the 3x3 and 5x3 windows record the winner");
   if (PH == 3 && PW == 3) { if (a) XEMO_POOL_FWD_H2(true, 3, 3); else XEMO_POOL_FWD_H2(false, 3, 3); }
   else if (PH == 5 && PW == 3) { if (a) XEMO_POOL_FWD_H2(true, 5, 3); else XEMO_POOL_FWD_H2(false, 5, 3); }
   else { if (a) XEMO_POOL_FWD(true, 0, 0); else XEMO_POOL_FWD(false, 0, 0); }
@@ -415,6 +417,19 @@ extern "C" int xemo_op_maxpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H,
 #undef XEMO_POOL_FWD
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
+}
+
+extern "C" int xemo_op_maxpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
+                                   int pt, int pb, int pl, int pr, const float* a, const float* b, void* y16,
+                                   uint8_t* argmax) {
+  return maxpool_fwd_impl(ctx, x16, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr, a, b, y16, argmax, nullptr);
+}
+
+extern "C" int xemo_op_maxpool_fwd_win(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh,
+                                       int sw, int pt, int pb, int pl, int pr, const float* a, const float* b, void* y16,
+                                       uint8_t* argmax, void* xwin16) {
+  XEMO_REQUIRE(ctx, xwin16, "maxpool_fwd_win: null winner buffer");
+  return maxpool_fwd_impl(ctx, x16, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr, a, b, y16, argmax, static_cast<__half*>(xwin16));
 }
 
 extern "C" int xemo_op_maxpool_bwd(xemo_ctx* ctx, const void* dy16, const uint8_t* argmax, int N, int H, int W, int C, int PH,
@@ -600,6 +615,59 @@ extern "C" int xemo_op_se_excite(xemo_ctx* ctx, const void* u16, const float* ga
   se_excite_kernel<__half><<<grid_for(total8, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
       static_cast<const __half*>(u16), gate, static_cast<const __half*>(shortcut16), HW, C, total8, relu,
       static_cast<__half*>(y16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+// ================================================================================================
+// student stem (conv1 on the one-channel spectrogram): BN statistics and BN/filter gradients by linearity
+extern "C" size_t xemo_stem_ws_doubles(void) { return size_t(kAcAccDoubles) + size_t(kStemRS); }
+
+extern "C" int xemo_op_stem_autocorr(xemo_ctx* ctx, const void* s2d16, int N, int HP, int OW, int OH, double* ws) {
+  XEMO_REQUIRE(ctx, s2d16 && ws && N > 0 && OW > 0 && OH >= 3 && HP == OH + 3, "stem_autocorr: needs HP == OH + 3 (4 x 1 taps) and OH >= 3");
+  static bool attr = false;
+  if (!attr) {
+    XEMO_CUDA(ctx, cudaFuncSetAttribute(stem_autocorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAcSmemBytes));
+    attr = true;
+  }
+  XEMO_CUDA(ctx, cudaMemsetAsync(ws, 0, size_t(kAcAccDoubles) * sizeof(double), ctx->stream));
+  const int strips = (HP + kAcRows - 1) / kAcRows, chunks = (OW + kAcOw - 1) / kAcOw;
+  const long units = long(N) * strips * chunks;
+  const int grid = int(units < 2L * ctx->num_sms ? units : 2L * ctx->num_sms);
+  stem_autocorr_kernel<<<grid, kAcThreads, kAcSmemBytes, ctx->stream>>>(static_cast<const __half*>(s2d16), N, HP, OW, OH, ws);
+  XEMO_LAUNCHED(ctx, 1);
+  stem_assemble_kernel<<<1, 1024, 0, ctx->stream>>>(ws, ws + kAcAccDoubles);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_stem_bn_train(xemo_ctx* ctx, const double* ws, const void* w16, const float* bias, size_t P, int C,
+                                     const float* g, const float* beta, float eps, float* moments, float* a, float* b) {
+  XEMO_REQUIRE(ctx, ws && w16 && bias && g && beta && moments && a && b && C > 0 && P > 0, "stem_bn_train: bad arguments");
+  stem_bn_stats_kernel<<<C, kStemT, 0, ctx->stream>>>(ws + kAcAccDoubles, static_cast<const __half*>(w16), bias, double(P), C, g,
+                                                     beta, eps, moments, a, b);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_stem_pool_bn_reduce(xemo_ctx* ctx, const void* xwin16, void* dpool16, size_t P, int C,
+                                           const float* moments, const float* a, const float* b, double* acc) {
+  XEMO_REQUIRE(ctx, xwin16 && dpool16 && moments && a && b && acc && C % 8 == 0 && P > 0, "stem_pool_bn_reduce: bad arguments");
+  XEMO_CUDA(ctx, cudaMemsetAsync(acc, 0, size_t(2) * C * sizeof(double), ctx->stream));
+  const BnGrid bg = bn_grid(P, C, ctx->num_sms);
+  dim3 grid(bg.slabs_x, bg.slabs_y);
+  stem_pool_bn_reduce_kernel<<<grid, kBnThreads, 0, ctx->stream>>>(static_cast<const __half*>(xwin16), static_cast<__half*>(dpool16),
+                                                                  P, C, bg.lanes, bg.rows_par, moments, a, b, acc);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_stem_wgrad_finalize(xemo_ctx* ctx, const double* ws, const void* w16, const float* bias,
+                                           const double* acc, size_t P, int C, const float* moments, const float* a,
+                                           float inv_grad_scale, float* dW, float* dbias, float* dgamma, float* dbeta) {
+  XEMO_REQUIRE(ctx, ws && w16 && bias && acc && moments && a && dW && dgamma && dbeta && C > 0 && P > 0, "stem_wgrad_finalize: bad arguments");
+  stem_wgrad_finalize_kernel<<<C, kStemT, 0, ctx->stream>>>(ws + kAcAccDoubles, static_cast<const __half*>(w16), bias, acc,
+                                                           double(P), C, moments, a, inv_grad_scale, dW, dbias, dgamma, dbeta);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }

@@ -16,6 +16,7 @@ key names of the zoo (`<layer>f`, `<layer>b`, `bnNm`, `bnNb`, `bnNx`).
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -294,7 +295,7 @@ class StudentProgram(_Base):
     AUDIO = dict(fs=16000, Tw=25, Ts=10, alpha=0.97)   # emoVoxCeleb/run_distillation.m:109-117
 
     def __init__(self, params, batch, width=300, device=0, stream=None, use_graph=True, grad_scale=1024.0, num_classes=8,
-                 temperature=2.0, ctx=None, audio_input="spectrogram"):
+                 temperature=2.0, ctx=None, audio_input="spectrogram", stem_algebra=None):
         """audio_input 'spectrogram': 512 x W x 1 x N row-normalised spectrograms (what getBatchEmoVoxCeleb hands to
         dag.eval); 'wav': N x L waveform crops of L = (0.01 W + 0.024) * fs samples -- runSpec + the row normalisation
         (getBatchEmoVoxCeleb.m:162-169) then run on the device ahead of the graph."""
@@ -310,6 +311,10 @@ class StudentProgram(_Base):
         self.T = float(temperature)
         self.graphs = {}
         self.fuse_pool_bwd = False
+        # conv1 + bn1 + pool1 by linearity in the one-channel input (csrc/stem_kernels.cuh): BN statistics from the patch
+        # autocorrelation, BN reductions at the pooled resolution, filter gradient without materialising dY.
+        # XEMO_STEM_ALGEBRA=0 selects the generic per-layer path (A/B measurements, parity tests of both).
+        self.stem_algebra = os.environ.get("XEMO_STEM_ALGEBRA", "1") != "0" if stem_algebra is None else bool(stem_algebra)
         self.side_stream = None   # torch.cuda.Stream: filter gradients run there, off the dgrad critical path
         self._geometry()
         self._load(params)
@@ -390,6 +395,8 @@ class StudentProgram(_Base):
         if self.audio_input == "wav":
             A["wav"] = self.f32(N, self.wav_len)
         A["s2d"] = self.f16(N, self.s2d_hp, self.s2d_ow, 16)
+        if self.stem_algebra:
+            A["stem:ws"] = torch.zeros(int(self.ctx.lib.xemo_stem_ws_doubles()), dtype=torch.float64, device=self.device)
         A["target"] = self.f32(N, self.K)                        # aggregated teacher logits
         for L in self.layers:
             n = L["name"]
@@ -404,6 +411,8 @@ class StudentProgram(_Base):
                 A[n + ":dout"] = self.f16(N, P["oh"], P["ow"], L["cout"])
                 if P["method"] == "max":
                     A[n + ":arg"] = torch.zeros((N, P["oh"], P["ow"], L["cout"]), dtype=torch.uint8, device=self.device)
+                    if n == "conv1" and self.stem_algebra:
+                        A[n + ":xwin"] = self.f16(N, P["oh"], P["ow"], L["cout"])
                 else:
                     A[n + ":act"] = self.f16(N, L["oh"], L["ow"], L["cout"])
                     A[n + ":dact"] = self.f16(N, L["oh"], L["ow"], L["cout"])
@@ -425,6 +434,8 @@ class StudentProgram(_Base):
         N, A, ctx = self.N, self.a, self.ctx
         self._record_frontend()
         ctx.op_spec_s2d(_p(A["spec"]), 512, self.W, N, 1, 1, self.s2d_hp, self.s2d_ow, _p(A["s2d"]))
+        if self.stem_algebra:
+            ctx.op_stem_autocorr(_p(A["s2d"]), N, self.s2d_hp, self.s2d_ow, self.layers[0]["oh"], _p(A["stem:ws"]))
         cur = A["s2d"]
         for L in self.layers:
             n = L["name"]
@@ -441,10 +452,19 @@ class StudentProgram(_Base):
             bn = "bn" + n[-1]
             g, beta = self.view(self.master, bn + "m"), self.view(self.master, bn + "b")
             rows = N * L["oh"] * L["ow"]
-            ctx.op_bn_train(_p(cur), rows, L["cout"], _p(g), _p(beta), BN_EPS, _p(A[n + ":ws"]), _p(self.batch_moments[bn]),
-                            _p(A[n + ":a"]), _p(A[n + ":b"]))
+            stem = n == "conv1" and self.stem_algebra
+            if stem:   # batch statistics of w.patch + b from the patch autocorrelation: no pass over the activation
+                ctx.op_stem_bn_train(_p(A["stem:ws"]), _p(wt), _p(bias), rows, L["cout"], _p(g), _p(beta), BN_EPS,
+                                     _p(self.batch_moments[bn]), _p(A[n + ":a"]), _p(A[n + ":b"]))
+            else:
+                ctx.op_bn_train(_p(cur), rows, L["cout"], _p(g), _p(beta), BN_EPS, _p(A[n + ":ws"]), _p(self.batch_moments[bn]),
+                                _p(A[n + ":a"]), _p(A[n + ":b"]))
             P = L["pool"]
-            if P and P["method"] == "max":
+            if P and P["method"] == "max" and stem:
+                ctx.op_maxpool_fwd_win(_p(cur), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1], P["stride"][0],
+                                       P["stride"][1], 0, 0, 0, 0, _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":out"]),
+                                       _p(A[n + ":arg"]), _p(A[n + ":xwin"]))
+            elif P and P["method"] == "max":
                 ctx.op_maxpool_fwd(_p(cur), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1], P["stride"][0], P["stride"][1],
                                    0, 0, 0, 0, _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":out"]), _p(A[n + ":arg"]))
             elif P:
@@ -519,7 +539,18 @@ class StudentProgram(_Base):
             n = L["name"]
             rows = N * L["oh"] * L["ow"]
             fused_bias = False
-            if L["bn"]:
+            stem = n == "conv1" and self.stem_algebra
+            if stem:
+                bn, P = "bn1", L["pool"]
+                prow = N * P["oh"] * P["ow"]
+                # ReLU mask + the two BN reductions at the pooled resolution, then the (masked) gradient w.r.t. the
+                # never-materialised ReLU output at the conv resolution: dz, which the filter gradient consumes directly
+                ctx.op_stem_pool_bn_reduce(_p(A[n + ":xwin"]), _p(A[n + ":dout"]), prow, L["cout"], _p(self.batch_moments[bn]),
+                                           _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":ws"]))
+                ctx.op_maxpool_bwd(_p(A[n + ":dout"]), _p(A[n + ":arg"]), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1],
+                                   P["stride"][0], P["stride"][1], 0, 0, 0, 0, _p(A[n + ":draw"]))
+                fused_bias = True
+            elif L["bn"]:
                 bn = "bn" + n[-1]
                 P = L["pool"]
                 dcur = A[n + ":dout"]
@@ -552,7 +583,14 @@ class StudentProgram(_Base):
             if side:  # fork: the filter gradient needs dy (just produced) but nothing downstream needs it before the update
                 ctx.stream_wait(VP(self.side_stream.cuda_stream), None)
                 ctx.set_stream(VP(self.side_stream.cuda_stream))
-            if n == "conv1":
+            if stem:
+                gf = self.view(self.grad, n + "f")
+                ctx.op_conv_wgrad(_p(x), N, self.s2d_hp, self.s2d_ow, 16, _p(dy), L["kp"], L["kp"], 4, 1, 1, 1, 0, 0, 0, 0, _p(gf), inv)
+                ctx.op_stem_wgrad_finalize(_p(A["stem:ws"]), _p(self.view(self.w16, n + "f")), _p(self.view(self.master, n + "b")),
+                                           _p(A[n + ":ws"]), rows, L["cout"], _p(self.batch_moments["bn1"]), _p(A[n + ":a"]), inv,
+                                           _p(gf), _p(self.view(self.grad, n + "b")), _p(self.view(self.grad, "bn1m")),
+                                           _p(self.view(self.grad, "bn1b")))
+            elif n == "conv1":
                 ctx.op_conv_wgrad(_p(x), N, self.s2d_hp, self.s2d_ow, 16, _p(dy), L["kp"], L["kp"], 4, 1, 1, 1, 0, 0, 0, 0,
                                   _p(self.view(self.grad, n + "f")), inv)
                 # structurally-zero slots of the space-to-depth filter: column 7 / 15 of every tap, and tap 3 rows 8..15
