@@ -223,8 +223,13 @@ int xemo_op_add_act(xemo_ctx* ctx, const void* a16, const void* b16, size_t n, i
  *                      in place with [a*xwin+b > 0] and accumulates acc[2C] = {sum dz, sum dz*xhat} (doubles)
  * stem_wgrad_finalize: dW [C][64] holds G1 = inv_grad_scale * sum_p dz[p,.] patch[p] (xemo_op_conv_wgrad on the dz
  *                      that xemo_op_maxpool_bwd scatters from the masked dpool16) and is overwritten with the
- *                      filter gradient A*G1 - D*(R w + bias*S) + E*S; dgamma/dbeta = inv_grad_scale*acc; dbias = 0 */
+ *                      filter gradient A*G1 - D*(R w + bias*S) + E*S; dgamma/dbeta = inv_grad_scale*acc; dbias = 0
+ * stem_pair_filter   : w16 [C][4][1][16] -> w2 [2C][4][1][32], w2[(e,k)][j][e'*16+c] = [e==e'] w[k][j][c]: the filter
+ *                      of the pixel-pair form (s2d viewed as [N][HP][OW/2][32], output as [N][OH][OW/2][2C]; OW even)
+ * tile_f32           : dst[r*C + c] = src[c] (or `fill` when src is NULL), r < reps */
 size_t xemo_stem_ws_doubles(void);
+int xemo_op_stem_pair_filter(xemo_ctx* ctx, const void* w16, int C, void* w2_16);
+int xemo_op_tile_f32(xemo_ctx* ctx, const float* src, int C, int reps, float fill, float* dst);
 int xemo_op_stem_autocorr(xemo_ctx* ctx, const void* s2d16, int N, int HP, int OW, int OH, double* ws);
 int xemo_op_stem_bn_train(xemo_ctx* ctx, const double* ws, const void* w16, const float* bias, size_t P, int C,
                           const float* g, const float* beta, float eps, float* moments, float* a, float* b);

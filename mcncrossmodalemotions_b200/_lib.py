@@ -79,6 +79,8 @@ SIGNATURES = {
     "xemo_op_maxpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p, c_void_p, c_void_p, c_void_p]),
     "xemo_op_maxpool_fwd_win": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "xemo_stem_ws_doubles": (c_size_t, []),
+    "xemo_op_stem_pair_filter": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "xemo_op_tile_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "xemo_op_stem_autocorr": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "xemo_op_stem_bn_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_float,
                                       c_void_p, c_void_p, c_void_p]),

@@ -63,6 +63,10 @@ struct ConvFpropParams {
   int use_tma_residual;     // residual read through tmRes
   int epi_cw;               // staging chunk width in columns: 64 / 32 / 16
   int epi_bufs;             // staging (and residual) buffers per epilogue group: 1 or 2
+  // resident filter: when the whole [Kout x R*S*Cin] filter is one N tile and fits beside the pipeline, it is loaded
+  // ONCE per CTA (k_iters slots) instead of once per tile -- for the K = 64..576 layers at 56 x 56 and the stems the
+  // per-tile filter re-fetch is 40-65 % of the L2->smem traffic and of the TMA row requests
+  int b_resident;
 };
 
 template <int BK>
@@ -74,10 +78,10 @@ struct ConvSwizzle<32> { static constexpr uint32_t mode = 4; };  // 64B
 template <>
 struct ConvSwizzle<16> { static constexpr uint32_t mode = 6; };  // 32B
 
-__host__ __device__ inline int conv_stage_bytes(int bk, int block_n) {
+__host__ __device__ inline int conv_b_slot_bytes(int bk, int block_n) { return ((block_n * bk * 2) + 1023) & ~1023; }
+__host__ __device__ inline int conv_stage_bytes(int bk, int block_n, int b_resident = 0) {
   const int a_bytes = kConvBlockM * bk * 2;
-  const int b_bytes = ((block_n * bk * 2) + 1023) & ~1023;
-  return a_bytes + b_bytes;
+  return a_bytes + (b_resident ? 0 : conv_b_slot_bytes(bk, block_n));
 }
 
 // byte offset of 16-byte chunk `chunk` of row `row` inside a TMA-swizzled staging tile with row pitch
@@ -100,11 +104,15 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   constexpr int kABytes = kConvBlockM * BK * 2;
   const int b_bytes = p.block_n * BK * 2;
-  const int stage_bytes = conv_stage_bytes(BK, p.block_n);
+  const int b_res = p.b_resident;
+  const int stage_bytes = conv_stage_bytes(BK, p.block_n, b_res);
+  const int b_slot = conv_b_slot_bytes(BK, p.block_n);
   const int num_stages = p.num_stages;
+  const int k_iters = p.R * p.S * p.kc_blocks;
 
   const int epi_bufs = p.epi_bufs;
-  uint8_t* epi_store_buf = smem + size_t(num_stages) * stage_bytes;                  // epi_bufs x 16 KB per group (if used)
+  uint8_t* b_res_buf = smem + size_t(num_stages) * stage_bytes;                      // k_iters filter slots (if resident)
+  uint8_t* epi_store_buf = b_res_buf + (b_res ? size_t(k_iters) * b_slot : 0);       // epi_bufs x 16 KB per group (if used)
   uint8_t* epi_res_buf = epi_store_buf + (p.use_tma_store ? kEpiGroups * epi_bufs * kEpiStageBytes : 0);
   uint8_t* after = epi_res_buf + (p.use_tma_residual ? kEpiGroups * epi_bufs * kEpiStageBytes : 0);
   float* epi_ss = reinterpret_cast<float*>(after);                                   // [group][scale | shift][64]
@@ -115,7 +123,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_full_bar = bars + 2 * num_stages;
   uint64_t* tmem_empty_bar = bars + 2 * num_stages + 2;
   uint64_t* res_bar = bars + 2 * num_stages + 4;  // [group][buf]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * num_stages + 8);
+  uint64_t* b_res_bar = bars + 2 * num_stages + 8;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * num_stages + 9);
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
   const int lane = threadIdx.x & 31;
@@ -134,6 +143,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tmem_empty_bar[a], 4 * kEpiGroups);  // one arrive per epilogue warp
     }
     for (int a = 0; a < 4; ++a) mbar_init(&res_bar[a], 1);
+    mbar_init(b_res_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -146,7 +156,6 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int k_iters = p.R * p.S * p.kc_blocks;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -154,6 +163,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const int ohw = p.OH * p.OW;
+      if (b_res && int(blockIdx.x) < num_tiles) {  // the whole filter, once (num_n_tiles == 1)
+        mbar_arrive_expect_tx(b_res_bar, uint32_t(k_iters) * uint32_t(b_bytes));
+        for (int it = 0; it < k_iters; ++it) tma_load_2d(&tmB, b_res_bar, b_res_buf + size_t(it) * b_slot, it * BK, 0);
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.num_n_tiles;
         const int n_tile = tile - m_tile * p.num_n_tiles;
@@ -172,10 +185,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = smem + size_t(stage) * stage_bytes;
               uint8_t* sb = sa + kABytes;
-              mbar_arrive_expect_tx(&full_bar[stage], uint32_t(kABytes + b_bytes));
+              mbar_arrive_expect_tx(&full_bar[stage], uint32_t(kABytes + (b_res ? 0 : b_bytes)));
               tma_load_im2col_4d(&tmA, &full_bar[stage], sa, kc * BK, w_base, h_base, n_img, uint16_t(s),
                                  uint16_t(r));
-              tma_load_2d(&tmB, &full_bar[stage], sb, kbase + kc * BK, n0);
+              if (!b_res) tma_load_2d(&tmB, &full_bar[stage], sb, kbase + kc * BK, n0);
               if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -191,6 +204,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (b_res && int(blockIdx.x) < num_tiles) mbar_wait(b_res_bar, 0);
+      const uint32_t sb_res = smem_u32(b_res_buf);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -199,7 +214,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + size_t(stage) * stage_bytes);
-          const uint32_t sb = sa + kABytes;
+          const uint32_t sb = b_res ? sb_res + uint32_t(it) * uint32_t(b_slot) : sa + kABytes;
           const uint64_t a_desc = make_smem_desc(sa, 16, kSbo, ConvSwizzle<BK>::mode);
           const uint64_t b_desc = make_smem_desc(sb, 16, kSbo, ConvSwizzle<BK>::mode);
 #pragma unroll

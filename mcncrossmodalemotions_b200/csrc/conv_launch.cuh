@@ -3,6 +3,7 @@
 #pragma once
 #include "conv_fprop.cuh"
 #include "conv_wgrad.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 #include "tma_host.h"
@@ -88,7 +89,6 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   if (p.block_n <= 0 || g.Kout % p.block_n) return false;
   p.num_m_tiles = (p.M + kConvBlockM - 1) / kConvBlockM;
   p.num_n_tiles = g.Kout / p.block_n;
-  const int stage_bytes = conv_stage_bytes(bk, p.block_n);
   p.scale = e.scale; p.shift = e.shift; p.residual = e.residual; p.relu = e.relu;
   p.out = e.out; p.out_f32 = e.out_f32;
   p.ldc = e.ldc ? e.ldc : g.Kout;
@@ -99,10 +99,18 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   // staging buffers per epilogue group: two when the pipeline still keeps enough stages for the K loop
   const int k_iters = g.R * g.S * p.kc_blocks;
   const int want_stages = k_iters + 1 < 3 ? k_iters + 1 : 3;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  // resident filter (one load per CTA instead of one per tile): a single N tile, at most 80 KB, and enough tiles per
+  // CTA to amortise it.  XEMO_CONV_BRES=0 disables (A/B measurements).
+  static const bool bres_enabled = [] { const char* e = getenv("XEMO_CONV_BRES"); return !(e && e[0] == '0'); }();
+  const int bres_bytes = k_iters * conv_b_slot_bytes(bk, p.block_n);
+  p.b_resident = (bres_enabled && p.num_n_tiles == 1 && bres_bytes <= 80 * 1024 && tiles >= num_sms) ? 1 : 0;
+  const int stage_bytes = conv_stage_bytes(bk, p.block_n, p.b_resident);
+  const int fixed_bytes = p.b_resident ? bres_bytes : 0;
   int stages = 0, epi_bytes = 0;
   for (int bufs = 2; bufs >= 1; --bufs) {
     epi_bytes = (p.use_tma_store ? kEpiGroups * bufs * kEpiStageBytes : 0) + (p.use_tma_residual ? kEpiGroups * bufs * kEpiStageBytes : 0);
-    stages = (kSmemBudget - 1024 - 256 - 1024 - epi_bytes) / stage_bytes;
+    stages = (kSmemBudget - 1024 - 256 - 1024 - epi_bytes - fixed_bytes) / stage_bytes;
     p.epi_bufs = bufs;
     if (stages >= want_stages) break;
   }
@@ -110,8 +118,7 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   if (stages < 2) return false;
   p.num_stages = stages;
   plan->bk = bk;
-  plan->smem = stages * stage_bytes + epi_bytes + 1024 + kEpiGroups * 2 * 64 * 4 + (2 * stages + 8) * 8 + 16;
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  plan->smem = stages * stage_bytes + fixed_bytes + epi_bytes + 1024 + kEpiGroups * 2 * 64 * 4 + (2 * stages + 9) * 8 + 16;
   plan->grid = tiles < num_sms ? tiles : num_sms;
   plan->flops = 2.0 * double(p.M) * g.Kout * g.R * g.S * g.Cin;
 

@@ -80,6 +80,7 @@ stem_autocorr_kernel(const __half* __restrict__ x, int N, int HP, int OW, int OH
     const int h0 = strip * kAcRows, ow0 = chunk * kAcOw;
     __syncthreads();  // the previous unit's fragments have been read
     // ---- stage rows h0 .. h0+18 (zero outside the tensor) : 16-byte pieces, coalesced along (ow, half)
+#pragma unroll 4
     for (int i = threadIdx.x; i < (kAcRows + 3) * kAcOw * 2; i += kAcThreads) {
       const int half = i & 1;
       const int ow = (i >> 1) % kAcOw;
@@ -345,6 +346,24 @@ static __global__ void stem_wgrad_finalize_kernel(const double* __restrict__ rs,
     dbeta[k] = float(db);
     if (dbias) dbias[k] = 0.f;   // a bias ahead of train-mode BN has an identically zero gradient
   }
+}
+
+// Pixel-pair form of the stem convolution: the s2d tensor [N][HP][OW][16] viewed as [N][HP][OW/2][32] and the
+// output [N][OH][OW][C] viewed as [N][OH][OW/2][2C] make conv1 a 4 x 1 convolution with 32 input channels and a
+// block-diagonal filter  w2[(e,k)][j][e'*16 + c] = [e == e'] w[k][j][c]  -- same bytes in HBM, half the TMA row
+// requests per output pixel (64-byte instead of 32-byte rows), at the price of 2x (free) tensor-core work.
+static __global__ void stem_pair_filter_kernel(const __half* __restrict__ w16, int C, __half* __restrict__ w2) {
+  const int total = 2 * C * 4 * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cc = i & 31, j = (i >> 5) & 3, ek = i >> 7;
+    const int e = ek / C, k = ek - e * C;
+    w2[i] = (cc >> 4) == e ? w16[(k * 4 + j) * 16 + (cc & 15)] : __float2half_rn(0.f);
+  }
+}
+
+// dst[r*C + c] = src[c] (NULL src -> fill) for r < reps: per-channel epilogue vectors of the pixel-pair form
+static __global__ void tile_f32_kernel(const float* __restrict__ src, int C, int reps, float fill, float* __restrict__ dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * reps; i += gridDim.x * blockDim.x) dst[i] = src ? src[i % C] : fill;
 }
 
 }  // namespace xemo

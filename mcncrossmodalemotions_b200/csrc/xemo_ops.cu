@@ -641,6 +641,21 @@ extern "C" int xemo_op_stem_autocorr(xemo_ctx* ctx, const void* s2d16, int N, in
   return XEMO_OK;
 }
 
+extern "C" int xemo_op_stem_pair_filter(xemo_ctx* ctx, const void* w16, int C, void* w2_16) {
+  XEMO_REQUIRE(ctx, w16 && w2_16 && C > 0, "stem_pair_filter: bad arguments");
+  stem_pair_filter_kernel<<<grid_for(size_t(2) * C * 128, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+      static_cast<const __half*>(w16), C, static_cast<__half*>(w2_16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_tile_f32(xemo_ctx* ctx, const float* src, int C, int reps, float fill, float* dst) {
+  XEMO_REQUIRE(ctx, dst && C > 0 && reps > 0, "tile_f32: bad arguments");
+  tile_f32_kernel<<<grid_for(size_t(C) * reps, 256, ctx->num_sms), 256, 0, ctx->stream>>>(src, C, reps, fill, dst);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
 extern "C" int xemo_op_stem_bn_train(xemo_ctx* ctx, const double* ws, const void* w16, const float* bias, size_t P, int C,
                                      const float* g, const float* beta, float eps, float* moments, float* a, float* b) {
   XEMO_REQUIRE(ctx, ws && w16 && bias && g && beta && moments && a && b && C > 0 && P > 0, "stem_bn_train: bad arguments");

@@ -295,7 +295,7 @@ class StudentProgram(_Base):
     AUDIO = dict(fs=16000, Tw=25, Ts=10, alpha=0.97)   # emoVoxCeleb/run_distillation.m:109-117
 
     def __init__(self, params, batch, width=300, device=0, stream=None, use_graph=True, grad_scale=1024.0, num_classes=8,
-                 temperature=2.0, ctx=None, audio_input="spectrogram", stem_algebra=None):
+                 temperature=2.0, ctx=None, audio_input="spectrogram", stem_algebra=None, stem_pairs=None):
         """audio_input 'spectrogram': 512 x W x 1 x N row-normalised spectrograms (what getBatchEmoVoxCeleb hands to
         dag.eval); 'wav': N x L waveform crops of L = (0.01 W + 0.024) * fs samples -- runSpec + the row normalisation
         (getBatchEmoVoxCeleb.m:162-169) then run on the device ahead of the graph."""
@@ -315,6 +315,9 @@ class StudentProgram(_Base):
         # autocorrelation, BN reductions at the pooled resolution, filter gradient without materialising dY.
         # XEMO_STEM_ALGEBRA=0 selects the generic per-layer path (A/B measurements, parity tests of both).
         self.stem_algebra = os.environ.get("XEMO_STEM_ALGEBRA", "1") != "0" if stem_algebra is None else bool(stem_algebra)
+        # conv1 forward in pixel-pair form (32-channel view of the s2d tensor, block-diagonal filter): half the TMA row
+        # requests per output pixel.  Needs an even conv1 output width (true for every width bucket 100..1000).
+        self.stem_pairs = os.environ.get("XEMO_STEM_PAIRS", "1") != "0" if stem_pairs is None else bool(stem_pairs)
         self.side_stream = None   # torch.cuda.Stream: filter gradients run there, off the dgrad critical path
         self._geometry()
         self._load(params)
@@ -342,6 +345,7 @@ class StudentProgram(_Base):
         assert (h, w) == (1, 1), "student graph must reduce to 1 x 1 (got %d x %d)" % (h, w)
         L1 = self.layers[0]
         self.s2d_hp, self.s2d_ow = L1["oh"] + 3, L1["ow"]
+        self.stem_pairs = self.stem_pairs and L1["ow"] % 2 == 0
 
     # ---- parameters: one flat fp32 master / momentum / gradient buffer (single all-reduce payload)
     def _load(self, p):
@@ -395,6 +399,10 @@ class StudentProgram(_Base):
         if self.audio_input == "wav":
             A["wav"] = self.f32(N, self.wav_len)
         A["s2d"] = self.f16(N, self.s2d_hp, self.s2d_ow, 16)
+        if self.stem_pairs:
+            c1 = self.layers[0]["kp"]
+            A["stem:w2"] = self.f16(2 * c1 * 4 * 32)
+            A["stem:shift2"], A["stem:scale2"] = self.f32(2 * c1), self.f32(2 * c1)
         if self.stem_algebra:
             A["stem:ws"] = torch.zeros(int(self.ctx.lib.xemo_stem_ws_doubles()), dtype=torch.float64, device=self.device)
         A["target"] = self.f32(N, self.K)                        # aggregated teacher logits
@@ -442,7 +450,7 @@ class StudentProgram(_Base):
             wt, bias = self.view(self.w16, n + "f"), self.view(self.master, n + "b")
             last = n == "fc8"
             if n == "conv1":
-                self.conv(cur, N, self.s2d_hp, self.s2d_ow, 16, wt, L["kp"], 4, 1, (1, 1), (0, 0, 0, 0), None, bias, None, 0, A[n + ":raw"])
+                self._stem_conv(wt, None, bias, 0, A[n + ":raw"])
             else:
                 self.conv(cur, N, L["h"], L["w"], _pad16(L["cin"]), wt, L["kp"], L["fh"], L["fw"], L["stride"], L["pad"], None, bias,
                           None, 0, A[n + ":raw"], A["pred32"] if last else None, L["kp"])
@@ -475,6 +483,20 @@ class StudentProgram(_Base):
                 ctx.op_affine_act(_p(cur), rows, L["cout"], _p(A[n + ":a"]), _p(A[n + ":b"]), 1, _p(A[n + ":out"]))
             cur = A[n + ":out"]
 
+    def _stem_conv(self, wt, scale, shift, relu, dst):
+        """conv1 as a 4 x 1 convolution over the space-to-depth tensor; in pixel-pair form when enabled."""
+        N, A, ctx, L = self.N, self.a, self.ctx, self.layers[0]
+        if not self.stem_pairs:
+            self.conv(A["s2d"], N, self.s2d_hp, self.s2d_ow, 16, wt, L["kp"], 4, 1, (1, 1), (0, 0, 0, 0), scale, shift, None, relu, dst)
+            return
+        kp = L["kp"]
+        ctx.op_stem_pair_filter(_p(wt), kp, _p(A["stem:w2"]))
+        ctx.op_tile_f32(_p(shift), kp, 2, 0.0, _p(A["stem:shift2"]))
+        if scale is not None:
+            ctx.op_tile_f32(_p(scale), kp, 2, 1.0, _p(A["stem:scale2"]))
+        self.conv(A["s2d"], N, self.s2d_hp, self.s2d_ow // 2, 32, A["stem:w2"], 2 * kp, 4, 1, (1, 1), (0, 0, 0, 0),
+                  A["stem:scale2"] if scale is not None else None, A["stem:shift2"], None, relu, dst)
+
     def _record_forward_test(self):
         """dag.mode = 'test' (external/compute_audio_feats.m:106): BN uses the stored moments, so it folds -- together
         with the conv bias -- into the convolution's scale/shift epilogue and the activation is rounded to fp16 once."""
@@ -496,7 +518,7 @@ class StudentProgram(_Base):
             P = L["pool"]
             dst = A[n + ":raw"] if (P or not L["bn"]) else A[n + ":out"]
             if n == "conv1":
-                self.conv(cur, N, self.s2d_hp, self.s2d_ow, 16, wt, L["kp"], 4, 1, (1, 1), (0, 0, 0, 0), scale, shift, None, relu, dst)
+                self._stem_conv(wt, scale, shift, relu, dst)
             else:
                 self.conv(cur, N, L["h"], L["w"], _pad16(L["cin"]), wt, L["kp"], L["fh"], L["fw"], L["stride"], L["pad"], scale, shift,
                           None, relu, dst, out32, L["kp"])

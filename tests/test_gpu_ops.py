@@ -143,3 +143,97 @@ def test_student_from_waveforms(env):
     ref, _ = nets.student_forward({k: v.astype(np.float64) for k, v in p.items()}, spec, "test", nets.TorchOps)
     got = prog.forward(wav, "test")
     assert np.abs(got - ref.reshape(8, n).T).max() <= 1e-3 * np.abs(ref).max()
+
+
+# ---- student stem by linearity (csrc/stem_kernels.cuh): the kernels against the numpy restatement of test_stem_algebra.py
+@pytest.mark.parametrize("shape", [(40, 38, 3), (70, 400, 2), (512, 100, 2)])
+def test_stem_autocorrelation_and_bn_statistics(env, shape):
+    torch, ctx, stream = env
+    import test_stem_algebra as T
+    from oracle import mcn_ops as M
+    from mcncrossmodalemotions_b200.programs import student_conv1_to_s2d
+
+    H, W, N = shape
+    K = 32
+    rng = np.random.default_rng(H + W)
+    spec = rng.standard_normal((H, W, 1, N)).astype(np.float16).astype(np.float64)       # fp16-exact inputs
+    f = (rng.standard_normal((7, 7, 1, K)) * 0.2).astype(np.float16).astype(np.float64)
+    bias = (rng.standard_normal(K) * 0.3).astype(np.float32)
+    g = rng.uniform(0.5, 1.5, K).astype(np.float32)
+    beta = (rng.standard_normal(K) * 0.2).astype(np.float32)
+    X, OH, OW = T.s2d(spec)
+    HP = OH + 3
+    with torch.cuda.stream(stream):
+        sd = torch.from_numpy(np.ascontiguousarray(spec.astype(np.float32).transpose(3, 2, 1, 0)).reshape(-1)).cuda()
+        s2d = torch.zeros((N, HP, OW, 16), dtype=torch.float16, device="cuda")
+        ws = torch.zeros(int(ctx.lib.xemo_stem_ws_doubles()), dtype=torch.float64, device="cuda")
+        w16 = torch.from_numpy(student_conv1_to_s2d(f).reshape(K, 64)).cuda().half()
+        bd, gd, betad = (torch.from_numpy(v).cuda() for v in (bias, g, beta))
+        mom, a, b = (torch.zeros(n, dtype=torch.float32, device="cuda") for n in (2 * K, K, K))
+        ctx.op_spec_s2d(_p(sd), H, W, N, 1, 1, HP, OW, _p(s2d))
+        ctx.op_stem_autocorr(_p(s2d), N, HP, OW, OH, _p(ws))
+        ctx.op_stem_bn_train(_p(ws), _p(w16), _p(bd), N * OH * OW, K, _p(gd), _p(betad), 1e-5, _p(mom), _p(a), _p(b))
+    ctx.sync()
+    assert np.array_equal(s2d.cpu().numpy().astype(np.float64), X)
+    xs = T.patches(X, OH)
+    rs = ws.cpu().numpy()[-(64 * 64 + 64):]
+    R, S = rs[: 64 * 64].reshape(64, 64), rs[64 * 64 :]
+    Rref, Sref = xs.T @ xs, xs.sum(0)
+    assert np.abs(R - Rref).max() <= 5e-6 * np.abs(Rref).max()      # fp32 partial sums, fp64 across warps / CTAs
+    assert np.abs(S - Sref).max() <= 5e-6 * np.abs(xs).sum(0).max()
+    x = M.vl_nnconv(spec, f, bias.astype(np.float64), pad=1, stride=2)
+    _, moments = M.vl_nnbnorm(x, g.astype(np.float64), beta.astype(np.float64), epsilon=1e-5)
+    got = mom.cpu().numpy().reshape(2, K).T
+    assert np.abs(got - moments).max() <= 1e-5 * np.abs(moments).max()
+    assert np.allclose(a.cpu().numpy(), g / moments[:, 1], rtol=1e-5)
+
+
+def test_stem_pooled_bn_reduce_masks_and_sums(env):
+    torch, ctx, stream = env
+    P, Cc = 1000, 96
+    rng = np.random.default_rng(5)
+    xw = rng.standard_normal((P, Cc)).astype(np.float16)
+    g = rng.standard_normal((P, Cc)).astype(np.float16)
+    mu, sg = rng.standard_normal(Cc).astype(np.float32) * 0.1, rng.uniform(0.5, 1.5, Cc).astype(np.float32)
+    a = (rng.choice([-1.0, 1.0], Cc) * rng.uniform(0.5, 1.5, Cc)).astype(np.float32)
+    b = (rng.standard_normal(Cc) * 0.3).astype(np.float32)
+    alive = (a[None] * xw.astype(np.float32) + b[None]) > 0
+    gm = np.where(alive, g, np.float16(0))
+    ref1 = gm.astype(np.float64).sum(0)
+    ref2 = (gm.astype(np.float64) * (xw.astype(np.float64) - mu) / sg).sum(0)
+    with torch.cuda.stream(stream):
+        xd, gd = torch.from_numpy(xw).cuda(), torch.from_numpy(g).cuda()
+        mom = torch.from_numpy(np.concatenate([mu, sg])).cuda()
+        ad, bd = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        acc = torch.zeros(2 * Cc, dtype=torch.float64, device="cuda")
+        ctx.op_stem_pool_bn_reduce(_p(xd), _p(gd), P, Cc, _p(mom), _p(ad), _p(bd), _p(acc))
+    ctx.sync()
+    assert np.array_equal(gd.cpu().numpy(), gm)
+    got = acc.cpu().numpy()
+    assert np.abs(got[:Cc] - ref1).max() <= 1e-5 * np.abs(ref1).max()
+    assert np.abs(got[Cc:] - ref2).max() <= 1e-5 * np.abs(ref2).max()
+
+
+def test_maxpool_forward_records_raw_winner(env):
+    torch, ctx, stream = env
+    N, H, W, Cc = 2, 21, 15, 24
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((N, H, W, Cc)).astype(np.float16)
+    a = (rng.choice([-1.0, 1.0], Cc) * rng.uniform(0.5, 1.5, Cc)).astype(np.float32)
+    b = (rng.standard_normal(Cc) * 0.3).astype(np.float32)
+    OH, OW = (H - 3) // 2 + 1, (W - 3) // 2 + 1
+    z = a * x.astype(np.float32) + b
+    win = np.stack([z[:, dh : dh + 2 * OH - 1 : 2, dw : dw + 2 * OW - 1 : 2] for dw in range(3) for dh in range(3)], 0)
+    xr = np.stack([x[:, dh : dh + 2 * OH - 1 : 2, dw : dw + 2 * OW - 1 : 2] for dw in range(3) for dh in range(3)], 0)
+    ref = np.take_along_axis(xr, win.argmax(0)[None], 0)[0]
+    with torch.cuda.stream(stream):
+        xd, ad, bd = torch.from_numpy(x).cuda(), torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        y = torch.zeros((N, OH, OW, Cc), dtype=torch.float16, device="cuda")
+        xw = torch.zeros_like(y)
+        arg = torch.zeros((N, OH, OW, Cc), dtype=torch.uint8, device="cuda")
+        ctx.op_maxpool_fwd_win(_p(xd), N, H, W, Cc, 3, 3, 2, 2, 0, 0, 0, 0, _p(ad), _p(bd), _p(y), _p(arg), _p(xw))
+    ctx.sync()
+    got, yy = xw.cpu().numpy(), y.cpu().numpy().astype(np.float32)
+    live = yy > 0        # an all-non-positive window has no unique winner (and its gradient is masked)
+    assert np.array_equal(got[live], ref[live])
+    assert np.all(a * got.astype(np.float32)[~live] + b <= 0)

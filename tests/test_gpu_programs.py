@@ -84,8 +84,10 @@ def _l2(a, b):
     return float(np.linalg.norm(a - b) / np.linalg.norm(b))
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_student_training_step(nets, use_graph):
+@pytest.mark.parametrize("use_graph,stem", [(False, True), (True, True), (True, False)])
+def test_student_training_step(nets, use_graph, stem):
+    """stem = True: conv1 / bn1 / pool1 through the linearity path of csrc/stem_kernels.cuh and the pixel-pair conv1
+    (the defaults); False: the generic per-layer kernels."""
     from mcncrossmodalemotions_b200.programs import StudentProgram
 
     n, width, lr = 16, 300, 1e-4
@@ -95,7 +97,8 @@ def test_student_training_step(nets, use_graph):
     exact_p, model_p = _f64(p), _f64(p)
     exact = nets.distillation_student_step(exact_p, {}, spec.astype(np.float64), tgt.astype(np.float64), lr=lr, ops=nets.TorchOps)
     model = nets.distillation_student_step(model_p, {}, spec.astype(np.float64), tgt.astype(np.float64), lr=lr, ops=nets.Fp16ModelOps)
-    prog = StudentProgram(p, n, width, use_graph=use_graph)
+    prog = StudentProgram(p, n, width, use_graph=use_graph, stem_algebra=stem, stem_pairs=stem)
+    assert prog.stem_algebra == stem and prog.stem_pairs == stem
     prog.set_hyper(lr=lr)
     prog.reset_metrics()
     prog.train_step(spec, tgt)
@@ -126,6 +129,29 @@ def test_student_training_step(nets, use_graph):
     for k in ("fc8f", "conv3f", "bn2m"):
         expect = p[k].astype(np.float64) - lr * (5e-4 * p[k].astype(np.float64) + grads[k].reshape(p[k].shape).astype(np.float64) / n)
         assert rel_err(params[k], expect) < 1e-6, k
+
+
+def test_stem_linearity_path_agrees_with_generic_path(nets):
+    """Same step through both formulations of the first layer: identical up to fp16 storage rounding of the conv1
+    activation (statistics) and the ReLU-mask flips that rounding causes."""
+    from mcncrossmodalemotions_b200.programs import StudentProgram
+
+    n, width = 8, 100
+    p = nets.student_randomize_bn(nets.student_init())
+    spec, tgt = nets.synth_spectrograms(n, width), nets.synth_teacher_logits(n)
+    out = []
+    for stem in (False, True):
+        prog = StudentProgram(p, n, width, use_graph=False, stem_algebra=stem, stem_pairs=stem)
+        prog.reset_metrics()
+        prog.set_input(spec, tgt)
+        prog.grad_step()
+        out.append((prog.export_grads(), prog.metrics()))
+    (g0, m0), (g1, m1) = out
+    assert abs(m0["objective"] - m1["objective"]) <= 1e-4 * abs(m0["objective"])
+    assert rel_err(g1["bn1x"], g0["bn1x"]) < 1e-4
+    for k in ("conv1f", "bn1m", "bn1b", "conv2f", "fc8f"):
+        assert _l2(g1[k], g0[k]) < 2e-2, (k, _l2(g1[k], g0[k]))
+    assert np.abs(g1["conv1b"]).max() == 0
 
 
 def test_student_bias_before_train_bn_has_zero_gradient(nets):
