@@ -221,6 +221,8 @@ int xemo_op_add_act(xemo_ctx* ctx, const void* a16, const void* b16, size_t n, i
  * stem_bn_train      : as bn_train for x = conv(s2d, w16 [C][64]) + bias, from ws
  * stem_pool_bn_reduce: xwin16 / dpool16 [P][C] at the POOLED resolution (xemo_op_maxpool_fwd_win); masks dpool16
  *                      in place with [a*xwin+b > 0] and accumulates acc[2C] = {sum dz, sum dz*xhat} (doubles)
+ * stem_pool_bwd_reduce: the two steps above in one kernel for the 3x3 / stride-2 / pad-0 pool over [N][H][W][C]: dx16 =
+ *                      max-pool backward of the masked dpool16 (which is left untouched), acc as above
  * stem_wgrad_finalize: dW [C][64] holds G1 = inv_grad_scale * sum_p dz[p,.] patch[p] (xemo_op_conv_wgrad on the dz
  *                      that xemo_op_maxpool_bwd scatters from the masked dpool16) and is overwritten with the
  *                      filter gradient A*G1 - D*(R w + bias*S) + E*S; dgamma/dbeta = inv_grad_scale*acc; dbias = 0
@@ -235,6 +237,8 @@ int xemo_op_stem_bn_train(xemo_ctx* ctx, const double* ws, const void* w16, cons
                           const float* g, const float* beta, float eps, float* moments, float* a, float* b);
 int xemo_op_stem_pool_bn_reduce(xemo_ctx* ctx, const void* xwin16, void* dpool16, size_t P, int C, const float* moments,
                                 const float* a, const float* b, double* acc);
+int xemo_op_stem_pool_bwd_reduce(xemo_ctx* ctx, const void* dpool16, const uint8_t* argmax, const void* xwin16, int N, int H,
+                                 int W, int C, const float* moments, const float* a, const float* b, void* dx16, double* acc);
 int xemo_op_stem_wgrad_finalize(xemo_ctx* ctx, const double* ws, const void* w16, const float* bias, const double* acc,
                                 size_t P, int C, const float* moments, const float* a, float inv_grad_scale, float* dW,
                                 float* dbias, float* dgamma, float* dbeta);

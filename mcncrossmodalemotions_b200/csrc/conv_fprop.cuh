@@ -115,8 +115,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* epi_store_buf = b_res_buf + (b_res ? size_t(k_iters) * b_slot : 0);       // epi_bufs x 16 KB per group (if used)
   uint8_t* epi_res_buf = epi_store_buf + (p.use_tma_store ? kEpiGroups * epi_bufs * kEpiStageBytes : 0);
   uint8_t* after = epi_res_buf + (p.use_tma_residual ? kEpiGroups * epi_bufs * kEpiStageBytes : 0);
-  float* epi_ss = reinterpret_cast<float*>(after);                                   // [group][scale | shift][64]
-  after += kEpiGroups * 2 * 64 * sizeof(float);
+  float* epi_ss = reinterpret_cast<float*>(after);                                   // [group][scale | shift][256]
+  after += kEpiGroups * 2 * 256 * sizeof(float);
   uint64_t* bars = reinterpret_cast<uint64_t*>(after);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + num_stages;
@@ -246,8 +246,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ohw = p.OH * p.OW;
     uint8_t* sbuf0 = epi_store_buf + group * epi_bufs * kEpiStageBytes;
     uint8_t* rbuf0 = epi_res_buf + group * epi_bufs * kEpiStageBytes;
-    float* ss_scale = epi_ss + group * 128;
-    float* ss_shift = ss_scale + 64;
+    float* ss_scale = epi_ss + group * 512;   // this group's copy of the N tile's per-channel scale / shift
+    float* ss_shift = ss_scale + 256;
+    int ss_n_tile = -1;
     uint64_t* rbar0 = &res_bar[group * 2];
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -277,6 +278,17 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m0 = m_tile * kConvBlockM;
       const int row = m0 + row_in_tile;
       const int n0 = n_tile * p.block_n;
+      if (n_tile != ss_n_tile) {
+        // per-channel epilogue vectors of this N tile: fetched once per N-tile change (once per kernel when the
+        // filter is a single N tile) and before the accumulator wait, so the global-load latency is off the
+        // per-chunk critical path.  The previous chunk ended with a group barrier: nobody still reads the old values.
+        for (int i = tg; i < p.block_n; i += 128) {
+          ss_scale[i] = p.scale ? __ldg(p.scale + n0 + i) : 1.f;
+          ss_shift[i] = p.shift ? __ldg(p.shift + n0 + i) : 0.f;
+        }
+        ss_n_tile = n_tile;
+        epi_bar_sync(group);
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc) * 256u;
@@ -302,11 +314,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         uint32_t va[16], vb[16];
         tmem_ld16(taddr + uint32_t(q * cw), va);  // in flight across the waits below
-        if (tg < cw) {
-          ss_scale[tg] = p.scale ? __ldg(p.scale + n0 + q * cw + tg) : 1.f;
-          ss_shift[tg] = p.shift ? __ldg(p.shift + n0 + q * cw + tg) : 0.f;
-        }
-        epi_bar_sync(group);  // staging buffer free, scale/shift visible
+        epi_bar_sync(group);  // staging buffer free
         if (p.use_tma_residual) mbar_wait(rbar0 + buf, (epi_bufs == 2 ? (mine >> 1) : mine) & 1u);
 
         // 16 accumulator columns -> scale/shift (+residual, ReLU) -> fp16 staging / direct stores
@@ -315,8 +323,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float x[16];
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
-            const float4 sc = *reinterpret_cast<const float4*>(ss_scale + jj + i);
-            const float4 sh = *reinterpret_cast<const float4*>(ss_shift + jj + i);
+            const float4 sc = *reinterpret_cast<const float4*>(ss_scale + j + i);
+            const float4 sh = *reinterpret_cast<const float4*>(ss_shift + j + i);
             x[i] = fmaf(__uint_as_float(v[i]), sc.x, sh.x);
             x[i + 1] = fmaf(__uint_as_float(v[i + 1]), sc.y, sh.y);
             x[i + 2] = fmaf(__uint_as_float(v[i + 2]), sc.z, sh.z);
@@ -388,7 +396,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (p.use_tma_residual) prefetch_residual(G0 + q + 2 * epi_bufs, buf);
           }
         } else {
-          epi_bar_sync(group);       // scale / shift may be overwritten by the next chunk
+          epi_bar_sync(group);       // keeps the group in step (the next chunk's barrier count assumes it)
         }
       }
       tc_fence_before();

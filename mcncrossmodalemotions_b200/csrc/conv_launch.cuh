@@ -110,7 +110,7 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   int stages = 0, epi_bytes = 0;
   for (int bufs = 2; bufs >= 1; --bufs) {
     epi_bytes = (p.use_tma_store ? kEpiGroups * bufs * kEpiStageBytes : 0) + (p.use_tma_residual ? kEpiGroups * bufs * kEpiStageBytes : 0);
-    stages = (kSmemBudget - 1024 - 256 - 1024 - epi_bytes - fixed_bytes) / stage_bytes;
+    stages = (kSmemBudget - 1024 - 256 - 4096 - epi_bytes - fixed_bytes) / stage_bytes;
     p.epi_bufs = bufs;
     if (stages >= want_stages) break;
   }
@@ -118,7 +118,7 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   if (stages < 2) return false;
   p.num_stages = stages;
   plan->bk = bk;
-  plan->smem = stages * stage_bytes + fixed_bytes + epi_bytes + 1024 + kEpiGroups * 2 * 64 * 4 + (2 * stages + 9) * 8 + 16;
+  plan->smem = stages * stage_bytes + fixed_bytes + epi_bytes + 1024 + kEpiGroups * 2 * 256 * 4 + (2 * stages + 9) * 8 + 16;
   plan->grid = tiles < num_sms ? tiles : num_sms;
   plan->flops = 2.0 * double(p.M) * g.Kout * g.R * g.S * g.Cin;
 

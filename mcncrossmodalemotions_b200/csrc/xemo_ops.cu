@@ -677,6 +677,23 @@ extern "C" int xemo_op_stem_pool_bn_reduce(xemo_ctx* ctx, const void* xwin16, vo
   return XEMO_OK;
 }
 
+extern "C" int xemo_op_stem_pool_bwd_reduce(xemo_ctx* ctx, const void* dpool16, const uint8_t* argmax, const void* xwin16, int N,
+                                            int H, int W, int C, const float* moments, const float* a, const float* b,
+                                            void* dx16, double* acc) {
+  PoolGeom g;
+  XEMO_REQUIRE(ctx, dpool16 && argmax && xwin16 && moments && a && b && dx16 && acc && C <= 2048 &&
+                        pool_geom(&g, N, H, W, C, 3, 3, 2, 2, 0, 0, 0, 0),
+               "stem_pool_bwd_reduce: bad arguments (3x3 / stride 2 / pad 0 pooling over N x H x W x C)");
+  XEMO_REQUIRE(ctx, size_t(N) * H * W < (size_t(1) << 31), "stem_pool_bwd_reduce: tensor too large for 32-bit pixel indices");
+  XEMO_CUDA(ctx, cudaMemsetAsync(acc, 0, size_t(2) * C * sizeof(double), ctx->stream));
+  const size_t cells = size_t(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  stem_pool_bwd_reduce_kernel<<<fixed_channel_grid(cells, C / 8, 256, ctx->num_sms, 8), 256, size_t(2) * C * 4, ctx->stream>>>(
+      static_cast<const __half*>(dpool16), argmax, static_cast<const __half*>(xwin16), g, moments, a, b,
+      static_cast<__half*>(dx16), acc);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
 extern "C" int xemo_op_stem_wgrad_finalize(xemo_ctx* ctx, const double* ws, const void* w16, const float* bias,
                                            const double* acc, size_t P, int C, const float* moments, const float* a,
                                            float inv_grad_scale, float* dW, float* dbias, float* dgamma, float* dbeta) {

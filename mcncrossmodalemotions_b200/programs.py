@@ -318,6 +318,7 @@ class StudentProgram(_Base):
         # conv1 forward in pixel-pair form (32-channel view of the s2d tensor, block-diagonal filter): half the TMA row
         # requests per output pixel.  Needs an even conv1 output width (true for every width bucket 100..1000).
         self.stem_pairs = os.environ.get("XEMO_STEM_PAIRS", "1") != "0" if stem_pairs is None else bool(stem_pairs)
+        self.stem_fused_pool_bwd = os.environ.get("XEMO_STEM_FUSED_POOL_BWD", "1") != "0"
         self.side_stream = None   # torch.cuda.Stream: filter gradients run there, off the dgrad critical path
         self._geometry()
         self._load(params)
@@ -567,10 +568,15 @@ class StudentProgram(_Base):
                 prow = N * P["oh"] * P["ow"]
                 # ReLU mask + the two BN reductions at the pooled resolution, then the (masked) gradient w.r.t. the
                 # never-materialised ReLU output at the conv resolution: dz, which the filter gradient consumes directly
-                ctx.op_stem_pool_bn_reduce(_p(A[n + ":xwin"]), _p(A[n + ":dout"]), prow, L["cout"], _p(self.batch_moments[bn]),
-                                           _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":ws"]))
-                ctx.op_maxpool_bwd(_p(A[n + ":dout"]), _p(A[n + ":arg"]), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1],
-                                   P["stride"][0], P["stride"][1], 0, 0, 0, 0, _p(A[n + ":draw"]))
+                if P["win"] == (3, 3) and P["stride"] == (2, 2) and self.stem_fused_pool_bwd:
+                    ctx.op_stem_pool_bwd_reduce(_p(A[n + ":dout"]), _p(A[n + ":arg"]), _p(A[n + ":xwin"]), N, L["oh"], L["ow"], L["cout"],
+                                                _p(self.batch_moments[bn]), _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":draw"]),
+                                                _p(A[n + ":ws"]))
+                else:
+                    ctx.op_stem_pool_bn_reduce(_p(A[n + ":xwin"]), _p(A[n + ":dout"]), prow, L["cout"], _p(self.batch_moments[bn]),
+                                               _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":ws"]))
+                    ctx.op_maxpool_bwd(_p(A[n + ":dout"]), _p(A[n + ":arg"]), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1],
+                                       P["stride"][0], P["stride"][1], 0, 0, 0, 0, _p(A[n + ":draw"]))
                 fused_bias = True
             elif L["bn"]:
                 bn = "bn" + n[-1]
