@@ -26,6 +26,8 @@
 //              what the HBM-bound 1x1 layers (K = 64: one MMA k-block per 128 x 256 tile) need.
 //              Warp 2 also owns TMEM alloc/free.
 #pragma once
+#include <type_traits>
+
 #include "xemo_ptx.cuh"
 
 namespace xemo {
@@ -249,6 +251,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float* ss_scale = epi_ss + group * 512;   // this group's copy of the N tile's per-channel scale / shift
     float* ss_shift = ss_scale + 256;
     int ss_n_tile = -1;
+    // fast path (fp16 output through the TMA store, the case of every layer inside the fused graphs): explicit
+    // LDS / STS, no per-element control flow.  A thread's row inside a swizzled staging tile: byte offset
+    // row*pitch + chunk16*16 with address bits [4,7) ^= bits [7,10) & mask -- the XOR term depends on the row only.
+    const bool fast = p.use_tma_store && !p.out_f32;
+    const uint32_t ss_scale_u32 = smem_u32(ss_scale), ss_shift_u32 = smem_u32(ss_shift);
+    const uint32_t row_base = uint32_t(row_in_tile) * uint32_t(pitch);
+    const uint32_t row_xor = ((row_base >> 7) & swz_mask) << 4;
+    const float relu_floor = p.relu ? 0.f : -INFINITY;
     uint64_t* rbar0 = &res_bar[group * 2];
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -316,6 +326,64 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_ld16(taddr + uint32_t(q * cw), va);  // in flight across the waits below
         epi_bar_sync(group);  // staging buffer free
         if (p.use_tma_residual) mbar_wait(rbar0 + buf, (epi_bufs == 2 ? (mine >> 1) : mine) & 1u);
+
+        if (fast) {
+          const uint32_t sbuf_u32 = smem_u32(sbuf), rbuf_u32 = smem_u32(rbuf);
+          auto process_fast = [&](const uint32_t (&v)[16], int jj, auto res_tag) {
+            constexpr bool kRes = decltype(res_tag)::value;
+            const uint32_t jb = uint32_t(q * cw + jj) * 4u;
+            float x[16];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 sc = lds_f4(ss_scale_u32 + jb + i * 4);
+              const float4 sh = lds_f4(ss_shift_u32 + jb + i * 4);
+              x[i] = fmaf(__uint_as_float(v[i]), sc.x, sh.x);
+              x[i + 1] = fmaf(__uint_as_float(v[i + 1]), sc.y, sh.y);
+              x[i + 2] = fmaf(__uint_as_float(v[i + 2]), sc.z, sh.z);
+              x[i + 3] = fmaf(__uint_as_float(v[i + 3]), sc.w, sh.w);
+            }
+            const uint32_t c0 = (row_base + uint32_t(jj) * 2u) ^ row_xor, c1 = (row_base + uint32_t(jj) * 2u + 16u) ^ row_xor;
+            if constexpr (kRes) {
+              const uint4 r0 = lds_u4(rbuf_u32 + c0), r1 = lds_u4(rbuf_u32 + c1);
+              const __half2* ra = reinterpret_cast<const __half2*>(&r0);
+              const __half2* rb = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 fa = __half22float2(ra[i]), fb = __half22float2(rb[i]);
+                x[2 * i] += fa.x; x[2 * i + 1] += fa.y;
+                x[8 + 2 * i] += fb.x; x[8 + 2 * i + 1] += fb.y;
+              }
+            }
+            uint4 o[2];
+            __half2* o2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o2[i] = __floats2half2_rn(fmaxf(x[2 * i], relu_floor), fmaxf(x[2 * i + 1], relu_floor));
+            sts_u4(sbuf_u32 + c0, o[0]);
+            sts_u4(sbuf_u32 + c1, o[1]);
+          };
+          auto run_fast = [&](auto res_tag) {
+            for (int jj = 0; jj < cw; jj += 32) {
+              tmem_ld_wait();
+              const bool second = jj + 16 < cw;
+              if (second) tmem_ld16(taddr + uint32_t(q * cw + jj + 16), vb);
+              process_fast(va, jj, res_tag);
+              if (second) {
+                tmem_ld_wait();
+                if (jj + 32 < cw) tmem_ld16(taddr + uint32_t(q * cw + jj + 32), va);
+                process_fast(vb, jj + 16, res_tag);
+              }
+            }
+          };
+          if (p.use_tma_residual) run_fast(std::true_type{}); else run_fast(std::false_type{});
+          fence_proxy_async_smem();
+          epi_bar_sync(group);
+          if (leader) {
+            tma_store_2d(&tmOut, sbuf, n0 + q * cw, m0);
+            tma_store_commit();
+            if (p.use_tma_residual) prefetch_residual(G0 + q + 2 * epi_bufs, buf);
+          }
+          continue;
+        }
 
         // 16 accumulator columns -> scale/shift (+residual, ReLU) -> fp16 staging / direct stores
         auto process = [&](const uint32_t (&v)[16], int jj) {

@@ -318,7 +318,9 @@ class StudentProgram(_Base):
         # conv1 forward in pixel-pair form (32-channel view of the s2d tensor, block-diagonal filter): half the TMA row
         # requests per output pixel.  Needs an even conv1 output width (true for every width bucket 100..1000).
         self.stem_pairs = os.environ.get("XEMO_STEM_PAIRS", "1") != "0" if stem_pairs is None else bool(stem_pairs)
-        self.stem_fused_pool_bwd = os.environ.get("XEMO_STEM_FUSED_POOL_BWD", "1") != "0"
+        # mask + BN reductions inside the pool-backward kernel: measured SLOWER on B200 than the two-kernel form (1.01 ms vs
+        # 0.35 + 0.60 ms at batch 256 -- the cell-owned gather becomes instruction-bound), so off by default
+        self.stem_fused_pool_bwd = os.environ.get("XEMO_STEM_FUSED_POOL_BWD", "0") != "0"
         self.side_stream = None   # torch.cuda.Stream: filter gradients run there, off the dgrad critical path
         self._geometry()
         self._load(params)
