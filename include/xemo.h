@@ -225,7 +225,9 @@ int xemo_op_add_act(xemo_ctx* ctx, const void* a16, const void* b16, size_t n, i
  *                      max-pool backward of the masked dpool16 (which is left untouched), acc as above
  * stem_wgrad_finalize: dW [C][64] holds G1 = inv_grad_scale * sum_p dz[p,.] patch[p] (xemo_op_conv_wgrad on the dz
  *                      that xemo_op_maxpool_bwd scatters from the masked dpool16) and is overwritten with the
- *                      filter gradient A*G1 - D*(R w + bias*S) + E*S; dgamma/dbeta = inv_grad_scale*acc; dbias = 0
+ *                      filter gradient A*G1 - D*(R w + bias*S) + E*S; dgamma/dbeta = inv_grad_scale*acc; dbias = 0.
+ *                      g1_pair (optional): G1 in pixel-pair form [2C][4][32] instead (wgrad on the 32-channel view of
+ *                      s2d16 and the [P/2][2C] view of dz -- fewer TMA rows per pixel); its diagonal blocks are summed
  * stem_pair_filter   : w16 [C][4][1][16] -> w2 [2C][4][1][32], w2[(e,k)][j][e'*16+c] = [e==e'] w[k][j][c]: the filter
  *                      of the pixel-pair form (s2d viewed as [N][HP][OW/2][32], output as [N][OH][OW/2][2C]; OW even)
  * tile_f32           : dst[r*C + c] = src[c] (or `fill` when src is NULL), r < reps */
@@ -241,7 +243,7 @@ int xemo_op_stem_pool_bwd_reduce(xemo_ctx* ctx, const void* dpool16, const uint8
                                  int W, int C, const float* moments, const float* a, const float* b, void* dx16, double* acc);
 int xemo_op_stem_wgrad_finalize(xemo_ctx* ctx, const double* ws, const void* w16, const float* bias, const double* acc,
                                 size_t P, int C, const float* moments, const float* a, float inv_grad_scale, float* dW,
-                                float* dbias, float* dgamma, float* dbeta);
+                                float* dbias, float* dgamma, float* dbeta, const float* g1_pair);
 
 /* squeeze-and-excitation: s = mean_hw(u) ; gate = sigmoid(W2 relu(W1 s + b1) + b2) ; y = relu(gate*u + shortcut).
  * w1 is [Cr][C]; w2 is passed TRANSPOSED, [Cr][C] (w2t[j][c] = W2[c][j]), so that the gate kernel reads it coalesced. */

@@ -88,7 +88,7 @@ SIGNATURES = {
     "xemo_op_stem_pool_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p]),
     "xemo_op_stem_wgrad_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p,
-                                            c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                            c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "xemo_op_maxpool_bwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]),
     "xemo_op_avgpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]),
     "xemo_op_avgpool_bwd": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]),

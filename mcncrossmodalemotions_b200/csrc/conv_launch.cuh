@@ -213,30 +213,43 @@ inline bool conv_wgrad_plan(WgradPlan* plan, const ConvGeom& g, const __half* x,
   p.block_c = block_c;
   p.c_tiles = g.Cin / block_c;
   const int total_sub = g.R * g.S * p.c_tiles;
-  const int t_max = (512 / block_c) < total_sub ? (512 / block_c) : total_sub;
-  // Pixels per stage and sub-tiles per item: prefer the largest TMA boxes (128 / 64 / 32 pixels) that
-  // still leave >= 4 pipeline stages with at least two sub-tiles sharing each dY tile; short reductions
-  // (fc layers) stay at 32 pixels.
+  p.m_tiles = (g.Kout + kWgBlockM - 1) / kWgBlockM;
+  // Stage shape.  The kernel is bound by the shared-memory fill rate (TMA rows), so among the shapes that fit --
+  // mt 128-kout dY tiles and T sub-tiles of block_c channels per stage, mt * T * block_c <= 512 TMEM columns, at
+  // least 3 stages (4 for stages under 48 KB) -- take the one with the most FLOP per staged byte,
+  //   mt * T * 128 * block_c / (mt * 128 + T * block_c)  per pixel,
+  // preferring the larger TMA boxes (128 > 64 pixels); short reductions (fc layers) stay at 32 pixels, mt = 1.
   const int P_total = g.N * OH * OW;
   const int budget = kSmemBudget - 2048;
-  int pix = 32, T = t_max;
-  while (T > 1 && wgrad_stage_bytes(T, block_c, 32) * 3 > budget) --T;
-  for (int cand = 128; cand >= 64; cand >>= 1) {
-    if (P_total < cand * 8) continue;
-    int tc = t_max;
-    while (tc > 1 && wgrad_stage_bytes(tc, block_c, cand) * 4 > budget) --tc;
-    if (wgrad_stage_bytes(tc, block_c, cand) * 4 > budget) continue;
-    if (tc < 2 && t_max >= 2 && block_c < 192) continue;  // a 192+-column sub-tile amortises the dY tile by itself
-    pix = cand;
-    T = tc;
-    break;
+  static const bool mt2_enabled = [] { const char* e = getenv("XEMO_WGRAD_MT2"); return !(e && e[0] == '0'); }();
+  int pix = 0, T = 1, mt = 1;
+  double best = -1.0;
+  for (int cm = (mt2_enabled && p.m_tiles >= 2) ? 2 : 1; cm >= 1; --cm) {
+    const int t_cap = 512 / (cm * block_c);
+    for (int ct = t_cap < total_sub ? t_cap : total_sub; ct >= 1; --ct) {
+      for (int cand = 128; cand >= 64; cand >>= 1) {
+        if (P_total < cand * 8) continue;
+        const int sb = wgrad_stage_bytes(ct, block_c, cand, cm);
+        const int need = sb >= 48 * 1024 ? 3 : 4;
+        if (sb * need > budget) continue;
+        double score = double(cm) * ct * 128.0 * block_c / (cm * 128.0 + double(ct) * block_c);
+        if (cand == 128) score *= 1.05;
+        if (score > best) { best = score; pix = cand; T = ct; mt = cm; }
+      }
+    }
+  }
+  if (pix == 0) {  // short reduction: 32-pixel stages
+    const int t_max = (512 / block_c) < total_sub ? (512 / block_c) : total_sub;
+    pix = 32; T = t_max; mt = 1;
+    while (T > 1 && wgrad_stage_bytes(T, block_c, 32) * 3 > budget) --T;
   }
   p.T = T;
   p.pix = pix;
+  p.mt = mt;
+  p.m_items = (p.m_tiles + mt - 1) / mt;
   p.groups = (total_sub + T - 1) / T;
-  p.m_tiles = (g.Kout + kWgBlockM - 1) / kWgBlockM;
   const int pix_blocks = (p.P + p.pix - 1) / p.pix;
-  const int base_items = p.m_tiles * p.groups;
+  const int base_items = p.m_items * p.groups;
   // split the pixel reduction so that there are ~2 items per SM, each at least 8 pixel blocks long
   // (rounded DOWN so that the item count stays within two full waves of the persistent grid)
   int splits = (2 * num_sms) / base_items;
@@ -245,7 +258,7 @@ inline bool conv_wgrad_plan(WgradPlan* plan, const ConvGeom& g, const __half* x,
   if (splits < 1) splits = 1;
   p.pix_blocks_per_split = (pix_blocks + splits - 1) / splits;
   p.splits = (pix_blocks + p.pix_blocks_per_split - 1) / p.pix_blocks_per_split;
-  const int stage_bytes = wgrad_stage_bytes(T, block_c, p.pix);
+  const int stage_bytes = wgrad_stage_bytes(T, block_c, p.pix, mt);
   int stages = (kSmemBudget - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return false;
@@ -253,7 +266,7 @@ inline bool conv_wgrad_plan(WgradPlan* plan, const ConvGeom& g, const __half* x,
   p.dF = dF;
   p.scale = scale;
   plan->smem = stages * stage_bytes + 1024 + (2 * stages + 2) * 8 + 16;
-  const int items = p.m_tiles * p.groups * p.splits;
+  const int items = p.m_items * p.groups * p.splits;
   plan->grid = items < num_sms ? items : num_sms;
   plan->flops = 2.0 * double(p.P) * g.Kout * g.R * g.S * g.Cin;
   const int upper_w = (OW - 1) * g.sw - g.pl - (g.W - 1);

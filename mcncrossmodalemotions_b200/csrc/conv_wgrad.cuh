@@ -30,9 +30,11 @@ struct ConvWgradParams {
   int chunk_b;  // contiguous channel elements per smem chunk
   int block_c;  // channels per sub-tile (multiple of 16, <= 256)
   int c_tiles;  // ceil(Cin / block_c)
-  int T;        // sub-tiles per item, T * block_c <= 512
+  int T;        // sub-tiles per item, mt * T * block_c <= 512
   int groups;   // ceil(R*S*c_tiles / T)
   int m_tiles;  // ceil(Kout / 128)
+  int mt;       // 128-kout slices per item: 1 or 2
+  int m_items;  // ceil(m_tiles / mt)
   int splits;
   int pix_blocks_per_split;
   int num_stages;
@@ -41,8 +43,8 @@ struct ConvWgradParams {
   float scale;  // applied to the accumulators before the atomic add (1/grad_scale)
 };
 
-__host__ __device__ inline int wgrad_stage_bytes(int T, int block_c, int pix) {
-  return pix * kWgBlockM * 2 + T * pix * block_c * 2;
+__host__ __device__ inline int wgrad_stage_bytes(int T, int block_c, int pix, int mt = 1) {
+  return mt * pix * kWgBlockM * 2 + T * pix * block_c * 2;
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -53,7 +55,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   const int kWgPix = p.pix;
   const int a_bytes = kWgPix * kWgBlockM * 2;
   const int b_sub_bytes = kWgPix * p.block_c * 2;
-  const int stage_bytes = wgrad_stage_bytes(p.T, p.block_c, p.pix);
+  const int stage_bytes = wgrad_stage_bytes(p.T, p.block_c, p.pix, p.mt);
   const int num_stages = p.num_stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(num_stages) * stage_bytes);
   uint64_t* full_bar = bars;
@@ -85,7 +87,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int num_items = p.m_tiles * p.groups * p.splits;
+  const int num_items = p.m_items * p.groups * p.splits;
   const int total_sub = p.R * p.S * p.c_tiles;
   const int pix_blocks = (p.P + kWgPix - 1) / kWgPix;
   const int ohw = p.OH * p.OW;
@@ -102,7 +104,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int split = item % p.splits;
         const int grp = (item / p.splits) % p.groups;
-        const int m_tile = item / (p.splits * p.groups);
+        const int m0 = (item / (p.splits * p.groups)) * p.mt;
+        const int nm = min(p.mt, p.m_tiles - m0);
         const int sub0 = grp * p.T;
         const int nsub = min(p.T, total_sub - sub0);
         const int pb0 = split * p.pix_blocks_per_split;
@@ -117,10 +120,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
           const int h_base = oh * p.stride_h - p.pad_t;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + size_t(stage) * stage_bytes;
-          uint8_t* sb = sa + a_bytes;
-          mbar_arrive_expect_tx(&full_bar[stage], uint32_t(a_bytes + nsub * b_sub_bytes));
-          for (int ca = 0; ca < a_chunks; ++ca)
-            tma_load_2d(&tmY, &full_bar[stage], sa + ca * a_chunk_bytes, m_tile * kWgBlockM + ca * p.chunk_a, p0);
+          uint8_t* sb = sa + p.mt * a_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], uint32_t(nm * a_bytes + nsub * b_sub_bytes));
+          for (int mi = 0; mi < nm; ++mi)
+            for (int ca = 0; ca < a_chunks; ++ca)
+              tma_load_2d(&tmY, &full_bar[stage], sa + mi * a_bytes + ca * a_chunk_bytes,
+                          (m0 + mi) * kWgBlockM + ca * p.chunk_a, p0);
           for (int t = 0; t < nsub; ++t) {
             const int sub = sub0 + t;
             const int tap = sub / p.c_tiles;
@@ -148,6 +153,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int split = item % p.splits;
         const int grp = (item / p.splits) % p.groups;
+        const int m0 = (item / (p.splits * p.groups)) * p.mt;
+        const int nm = min(p.mt, p.m_tiles - m0);
         const int sub0 = grp * p.T;
         const int nsub = min(p.T, total_sub - sub0);
         const int pb0 = split * p.pix_blocks_per_split;
@@ -158,13 +165,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + size_t(stage) * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
+          const uint32_t sb = sa + p.mt * a_bytes;
           for (int k = 0; k < kWgPix / 16; ++k) {
             // 16 pixels (GEMM-K) = two 8-row groups: advance by 2*SBO
-            const uint64_t a_desc = make_smem_desc(sa + k * 2 * sbo_a, lbo_a, sbo_a, swz_a);
-            for (int t = 0; t < nsub; ++t) {
-              const uint64_t b_desc = make_smem_desc(sb + t * b_sub_bytes + k * 2 * sbo_b, lbo_b, sbo_b, swz_b);
-              umma_f16_ss(tmem_base + uint32_t(t * p.block_c), a_desc, b_desc, idesc, (pb > pb0 || k > 0) ? 1u : 0u);
+            for (int mi = 0; mi < nm; ++mi) {
+              const uint64_t a_desc = make_smem_desc(sa + mi * a_bytes + k * 2 * sbo_a, lbo_a, sbo_a, swz_a);
+              for (int t = 0; t < nsub; ++t) {
+                const uint64_t b_desc = make_smem_desc(sb + t * b_sub_bytes + k * 2 * sbo_b, lbo_b, sbo_b, swz_b);
+                umma_f16_ss(tmem_base + uint32_t((mi * p.T + t) * p.block_c), a_desc, b_desc, idesc,
+                            (pb > pb0 || k > 0) ? 1u : 0u);
+              }
             }
           }
           umma_commit(&empty_bar[stage]);
@@ -181,7 +191,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
     uint32_t item_phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int grp = (item / p.splits) % p.groups;
-      const int m_tile = item / (p.splits * p.groups);
+      const int m0 = (item / (p.splits * p.groups)) * p.mt;
+      const int nm = min(p.mt, p.m_tiles - m0);
       const int split = item % p.splits;
       const int sub0 = grp * p.T;
       const int nsub = min(p.T, total_sub - sub0);
@@ -189,21 +200,23 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
       const bool has_work = pb0 < pix_blocks;
       mbar_wait(tmem_full_bar, item_phase);
       tc_fence_after();
-      const int kout = m_tile * kWgBlockM + row_in_tile;
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16);
-      for (int t = 0; t < nsub; ++t) {
-        const int sub = sub0 + t;
-        const int tap = sub / p.c_tiles;
-        const int c0 = (sub - tap * p.c_tiles) * p.block_c;
-        float* dst = p.dF + (size_t(kout) * p.R * p.S + tap) * p.Cin + c0;
-        for (int j = 0; j < p.block_c; j += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + uint32_t(t * p.block_c + j), v);
-          tmem_ld_wait();
-          if (has_work && kout < p.Kout) {
+      for (int mi = 0; mi < nm; ++mi) {
+        const int kout = (m0 + mi) * kWgBlockM + row_in_tile;
+        for (int t = 0; t < nsub; ++t) {
+          const int sub = sub0 + t;
+          const int tap = sub / p.c_tiles;
+          const int c0 = (sub - tap * p.c_tiles) * p.block_c;
+          float* dst = p.dF + (size_t(kout) * p.R * p.S + tap) * p.Cin + c0;
+          for (int j = 0; j < p.block_c; j += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + uint32_t((mi * p.T + t) * p.block_c + j), v);
+            tmem_ld_wait();
+            if (has_work && kout < p.Kout) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c0 + j + i < p.Cin) atomicAdd(dst + j + i, __uint_as_float(v[i]) * p.scale);
+              for (int i = 0; i < 16; ++i)
+                if (c0 + j + i < p.Cin) atomicAdd(dst + j + i, __uint_as_float(v[i]) * p.scale);
+            }
           }
         }
       }

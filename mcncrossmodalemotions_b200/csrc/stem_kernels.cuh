@@ -319,14 +319,15 @@ static __global__ void stem_pool_bn_reduce_kernel(const __half* __restrict__ xw,
 
 // Filter / BN-parameter gradients of the stem from G1 (in dW, written by the wgrad kernel on dz with scale
 // 1/grad_scale), (R, S), the BN reductions `acc` (scaled by grad_scale) and the batch moments.  One block of 64
-// threads per output channel; dW is overwritten in place, structurally-zero s2d slots are cleared
+// threads per output channel; dW is overwritten (G1 is read from it unless g1_pair is given), structurally-zero s2d slots are cleared
 // (column 7 / 15 of every tap, and rows 8..15 of tap 3 -- programs.py: student_conv1_to_s2d).
 //   A = a, D = a*dg/(P*sigma), E = mu*D - a*db/P  (bn_bwd_apply_kernel);  dW = A*G1 - D*(R w + bias*S) + E*S
 static __global__ void stem_wgrad_finalize_kernel(const double* __restrict__ rs, const __half* __restrict__ w16,
                                                   const float* __restrict__ bias, const double* __restrict__ acc, double P,
                                                   int C, const float* __restrict__ moments, const float* __restrict__ a,
                                                   float inv_grad_scale, float* __restrict__ dW, float* __restrict__ dbias,
-                                                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                  const float* __restrict__ g1_pair) {
   __shared__ double wv[kStemT];
   const int k = blockIdx.x, t = threadIdx.x;
   wv[t] = double(__half2float(w16[size_t(k) * kStemT + t]));
@@ -342,7 +343,11 @@ static __global__ void stem_wgrad_finalize_kernel(const double* __restrict__ rs,
   const int j = t >> 4, c = t & 15;
   const bool structural_zero = (c & 7) == 7 || (j == 3 && c >= 8);
   const size_t o = size_t(k) * kStemT + t;
-  dW[o] = structural_zero ? 0.f : float(av * double(dW[o]) - D * g2 + E * St);
+  // G1: in place, or the two diagonal blocks of the pixel-pair form [2C][4][32] (the wgrad kernel run on the 32-channel
+  // view of the s2d tensor and the [P/2][2C] view of dz): G1[k][j][c] = pair[(0,k)][j][c] + pair[(1,k)][j][16 + c]
+  const double g1 = g1_pair ? double(g1_pair[(size_t(k) * 4 + j) * 32 + c]) + double(g1_pair[(size_t(C + k) * 4 + j) * 32 + 16 + c])
+                            : double(dW[o]);
+  dW[o] = structural_zero ? 0.f : float(av * g1 - D * g2 + E * St);
   if (t == 0) {
     dgamma[k] = float(dg);
     dbeta[k] = float(db);

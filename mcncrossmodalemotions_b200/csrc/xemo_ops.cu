@@ -696,10 +696,11 @@ extern "C" int xemo_op_stem_pool_bwd_reduce(xemo_ctx* ctx, const void* dpool16, 
 
 extern "C" int xemo_op_stem_wgrad_finalize(xemo_ctx* ctx, const double* ws, const void* w16, const float* bias,
                                            const double* acc, size_t P, int C, const float* moments, const float* a,
-                                           float inv_grad_scale, float* dW, float* dbias, float* dgamma, float* dbeta) {
+                                           float inv_grad_scale, float* dW, float* dbias, float* dgamma, float* dbeta,
+                                           const float* g1_pair) {
   XEMO_REQUIRE(ctx, ws && w16 && bias && acc && moments && a && dW && dgamma && dbeta && C > 0 && P > 0, "stem_wgrad_finalize: bad arguments");
   stem_wgrad_finalize_kernel<<<C, kStemT, 0, ctx->stream>>>(ws + kAcAccDoubles, static_cast<const __half*>(w16), bias, acc,
-                                                           double(P), C, moments, a, inv_grad_scale, dW, dbias, dgamma, dbeta);
+                                                           double(P), C, moments, a, inv_grad_scale, dW, dbias, dgamma, dbeta, g1_pair);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }

@@ -406,6 +406,7 @@ class StudentProgram(_Base):
             c1 = self.layers[0]["kp"]
             A["stem:w2"] = self.f16(2 * c1 * 4 * 32)
             A["stem:shift2"], A["stem:scale2"] = self.f32(2 * c1), self.f32(2 * c1)
+            A["stem:g1pair"] = self.f32(2 * c1 * 4 * 32)
         if self.stem_algebra:
             A["stem:ws"] = torch.zeros(int(self.ctx.lib.xemo_stem_ws_doubles()), dtype=torch.float64, device=self.device)
         A["target"] = self.f32(N, self.K)                        # aggregated teacher logits
@@ -615,11 +616,18 @@ class StudentProgram(_Base):
                 ctx.set_stream(VP(self.side_stream.cuda_stream))
             if stem:
                 gf = self.view(self.grad, n + "f")
-                ctx.op_conv_wgrad(_p(x), N, self.s2d_hp, self.s2d_ow, 16, _p(dy), L["kp"], L["kp"], 4, 1, 1, 1, 0, 0, 0, 0, _p(gf), inv)
+                if self.stem_pairs:   # G1 in pixel-pair form: 64-byte TMA rows, both 128-kout tiles share the patch tiles
+                    g1p = A["stem:g1pair"]
+                    ctx.memset(_p(g1p), 0, g1p.numel() * 4)
+                    ctx.op_conv_wgrad(_p(x), N, self.s2d_hp, self.s2d_ow // 2, 32, _p(dy), 2 * L["kp"], 2 * L["kp"], 4, 1, 1, 1,
+                                      0, 0, 0, 0, _p(g1p), inv)
+                else:
+                    g1p = None
+                    ctx.op_conv_wgrad(_p(x), N, self.s2d_hp, self.s2d_ow, 16, _p(dy), L["kp"], L["kp"], 4, 1, 1, 1, 0, 0, 0, 0, _p(gf), inv)
                 ctx.op_stem_wgrad_finalize(_p(A["stem:ws"]), _p(self.view(self.w16, n + "f")), _p(self.view(self.master, n + "b")),
                                            _p(A[n + ":ws"]), rows, L["cout"], _p(self.batch_moments["bn1"]), _p(A[n + ":a"]), inv,
                                            _p(gf), _p(self.view(self.grad, n + "b")), _p(self.view(self.grad, "bn1m")),
-                                           _p(self.view(self.grad, "bn1b")))
+                                           _p(self.view(self.grad, "bn1b")), _p(g1p))
             elif n == "conv1":
                 ctx.op_conv_wgrad(_p(x), N, self.s2d_hp, self.s2d_ow, 16, _p(dy), L["kp"], L["kp"], 4, 1, 1, 1, 0, 0, 0, 0,
                                   _p(self.view(self.grad, n + "f")), inv)

@@ -41,6 +41,8 @@ CONV_CASES = [
     (40, 30, 1, 2, 7, 7, 96, 1, 2, True),                 # student conv1 (C = 1)
     (32, 32, 3, 2, 7, 7, 64, 3, 2, False),                # teacher conv1
     (17, 13, 24, 1, 4, 2, 40, (2, 1, 0, 1), (3, 2), True),
+    (34, 30, 64, 2, 3, 3, 384, 1, 1, True),               # 3 x 128 kout: filter-gradient items own two kout tiles (mt = 2), odd count
+    (40, 36, 96, 2, 5, 5, 256, 1, 2, False),              # student conv2 with enough pixels for the 64-pixel wgrad stages
 ]
 
 
