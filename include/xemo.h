@@ -174,10 +174,15 @@ int xemo_op_colsum(xemo_ctx* ctx, const void* dy16, size_t P, int ld, int C, flo
  * the pooling read) and emits the uint8 window-local arg-max dw*PH + dh that maxpool_bwd consumes. */
 int xemo_op_maxpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
                         int pt, int pb, int pl, int pr, const float* a, const float* b, void* y16, uint8_t* argmax);
-/* the same, also recording the raw (pre-affine) value of each window's winner in xwin16 [N][OH][OW][C] (3x3 / 5x3 windows) */
+/* the same, also recording the raw (pre-affine) value of each window's winner in xwin16 (optional; 3x3 / 5x3 windows).
+ * pooled_ld (0 = C): channel pitch of y16 / argmax / xwin16, so that the pooled tensor can carry zero-padded channels
+ * for its consumer (the student's conv2 reads 128-byte TMA rows from a 96 -> 128 channel pitch); maxpool_bwd_ld is the
+ * matching backward (3x3 / stride 2 / pad 0), reading dy16 / argmax with that pitch */
 int xemo_op_maxpool_fwd_win(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
                             int pt, int pb, int pl, int pr, const float* a, const float* b, void* y16, uint8_t* argmax,
-                            void* xwin16);
+                            void* xwin16, int pooled_ld);
+int xemo_op_maxpool_bwd_ld(xemo_ctx* ctx, const void* dy16, const uint8_t* argmax, int N, int H, int W, int C, int PH,
+                           int PW, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16, int pooled_ld);
 int xemo_op_maxpool_bwd(xemo_ctx* ctx, const void* dy16, const uint8_t* argmax, int N, int H, int W, int C, int PH,
                         int PW, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16);
 int xemo_op_avgpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
@@ -219,10 +224,8 @@ int xemo_op_add_act(xemo_ctx* ctx, const void* a16, const void* b16, size_t n, i
  * stem_autocorr      : s2d16 [N][HP][OW][16] (xemo_op_spec_s2d), HP == OH + 3 -> ws (xemo_stem_ws_doubles() doubles):
  *                      row-pair products then the assembled [R | S]
  * stem_bn_train      : as bn_train for x = conv(s2d, w16 [C][64]) + bias, from ws
- * stem_pool_bn_reduce: xwin16 / dpool16 [P][C] at the POOLED resolution (xemo_op_maxpool_fwd_win); masks dpool16
+ * stem_pool_bn_reduce: xwin16 / dpool16 [P][ld] (ld = 0: C) at the POOLED resolution (xemo_op_maxpool_fwd_win); masks dpool16
  *                      in place with [a*xwin+b > 0] and accumulates acc[2C] = {sum dz, sum dz*xhat} (doubles)
- * stem_pool_bwd_reduce: the two steps above in one kernel for the 3x3 / stride-2 / pad-0 pool over [N][H][W][C]: dx16 =
- *                      max-pool backward of the masked dpool16 (which is left untouched), acc as above
  * stem_wgrad_finalize: dW [C][64] holds G1 = inv_grad_scale * sum_p dz[p,.] patch[p] (xemo_op_conv_wgrad on the dz
  *                      that xemo_op_maxpool_bwd scatters from the masked dpool16) and is overwritten with the
  *                      filter gradient A*G1 - D*(R w + bias*S) + E*S; dgamma/dbeta = inv_grad_scale*acc; dbias = 0.
@@ -237,10 +240,8 @@ int xemo_op_tile_f32(xemo_ctx* ctx, const float* src, int C, int reps, float fil
 int xemo_op_stem_autocorr(xemo_ctx* ctx, const void* s2d16, int N, int HP, int OW, int OH, double* ws);
 int xemo_op_stem_bn_train(xemo_ctx* ctx, const double* ws, const void* w16, const float* bias, size_t P, int C,
                           const float* g, const float* beta, float eps, float* moments, float* a, float* b);
-int xemo_op_stem_pool_bn_reduce(xemo_ctx* ctx, const void* xwin16, void* dpool16, size_t P, int C, const float* moments,
-                                const float* a, const float* b, double* acc);
-int xemo_op_stem_pool_bwd_reduce(xemo_ctx* ctx, const void* dpool16, const uint8_t* argmax, const void* xwin16, int N, int H,
-                                 int W, int C, const float* moments, const float* a, const float* b, void* dx16, double* acc);
+int xemo_op_stem_pool_bn_reduce(xemo_ctx* ctx, const void* xwin16, void* dpool16, size_t P, int C, int ld,
+                                const float* moments, const float* a, const float* b, double* acc);
 int xemo_op_stem_wgrad_finalize(xemo_ctx* ctx, const double* ws, const void* w16, const float* bias, const double* acc,
                                 size_t P, int C, const float* moments, const float* a, float inv_grad_scale, float* dW,
                                 float* dbias, float* dgamma, float* dbeta, const float* g1_pair);

@@ -77,16 +77,15 @@ SIGNATURES = {
                                    c_int, c_int, c_int, c_int, c_int, c_void_p, c_float]),
     "xemo_op_colsum": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_float, c_void_p]),
     "xemo_op_maxpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p, c_void_p, c_void_p, c_void_p]),
-    "xemo_op_maxpool_fwd_win": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "xemo_op_maxpool_fwd_win": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "xemo_op_maxpool_bwd_ld": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 12 + [c_void_p, c_int]),
     "xemo_stem_ws_doubles": (c_size_t, []),
     "xemo_op_stem_pair_filter": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "xemo_op_tile_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "xemo_op_stem_autocorr": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "xemo_op_stem_bn_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_float,
                                       c_void_p, c_void_p, c_void_p]),
-    "xemo_op_stem_pool_bn_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "xemo_op_stem_pool_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                                             c_void_p, c_void_p, c_void_p]),
+    "xemo_op_stem_pool_bn_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "xemo_op_stem_wgrad_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p,
                                             c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "xemo_op_maxpool_bwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]),

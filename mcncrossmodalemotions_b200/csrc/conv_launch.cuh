@@ -221,10 +221,12 @@ inline bool conv_wgrad_plan(WgradPlan* plan, const ConvGeom& g, const __half* x,
   // preferring the larger TMA boxes (128 > 64 pixels); short reductions (fc layers) stay at 32 pixels, mt = 1.
   const int P_total = g.N * OH * OW;
   const int budget = kSmemBudget - 2048;
+  // (measured on B200: two-tile items win when one sub-tile spans all input channels -- conv2 / conv3 / conv5 of the
+  // student, 5-15 % -- and lose when the channels are split over sub-tiles -- conv4, -25 %; XEMO_WGRAD_MT2=0 disables)
   static const bool mt2_enabled = [] { const char* e = getenv("XEMO_WGRAD_MT2"); return !(e && e[0] == '0'); }();
   int pix = 0, T = 1, mt = 1;
   double best = -1.0;
-  for (int cm = (mt2_enabled && p.m_tiles >= 2) ? 2 : 1; cm >= 1; --cm) {
+  for (int cm = (mt2_enabled && p.m_tiles >= 2 && p.c_tiles == 1) ? 2 : 1; cm >= 1; --cm) {
     const int t_cap = 512 / (cm * block_c);
     for (int ct = t_cap < total_sub ? t_cap : total_sub; ct >= 1; --ct) {
       for (int cand = 128; cand >= 64; cand >>= 1) {

@@ -212,10 +212,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
             uint32_t v[16];
             tmem_ld16(taddr + uint32_t((mi * p.T + t) * p.block_c + j), v);
             tmem_ld_wait();
-            if (has_work && kout < p.Kout) {
+            // Cin and block_c are multiples of 16: a 16-column group is inside the filter or not at all
+            if (has_work && kout < p.Kout && c0 + j < p.Cin) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (c0 + j + i < p.Cin) atomicAdd(dst + j + i, __uint_as_float(v[i]) * p.scale);
+              for (int i = 0; i < 16; i += 4)
+                red_add_v4(dst + j + i, __uint_as_float(v[i]) * p.scale, __uint_as_float(v[i + 1]) * p.scale,
+                           __uint_as_float(v[i + 2]) * p.scale, __uint_as_float(v[i + 3]) * p.scale);
             }
           }
         }

@@ -208,6 +208,8 @@ static __global__ void spec_s2d_from_hwcn_kernel(const float* __restrict__ src, 
 // ============================================================================================
 struct PoolGeom {
   int N, H, W, C;       // input
+  int OC;               // channel pitch of the pooled-side tensors (y / arg-max / winner / dy): C, or larger when the
+                        // consumer wants zero-padded channels (fp16 fast paths only)
   int PH, PW, sh, sw, pt, pl;
   int OH, OW;
 };
@@ -416,7 +418,7 @@ __global__ void maxpool_fwd_h2_kernel(const __half* __restrict__ x, PoolGeom g, 
       }
       o2[k] = __floats2half2_rn(f.x, f.y);
     }
-    const size_t off = ((size_t(n) * g.OH + oh) * g.OW + ow) * g.C + c8 * 8;
+    const size_t off = ((size_t(n) * g.OH + oh) * g.OW + ow) * g.OC + c8 * 8;
     *reinterpret_cast<uint4*>(y + off) = o;
     if (xwin) *reinterpret_cast<uint4*>(xwin + off) = xo;   // consumed by stem_pool_bn_reduce_kernel
     if (idx) {
@@ -502,7 +504,7 @@ static __global__ void maxpool_bwd_3x3s2_h2_kernel(const __half* __restrict__ dy
       for (int b = 0; b < 2; ++b) {
         const int oh = i - a, ow = j - b;
         const bool valid = oh >= 0 && oh < g.OH && ow >= 0 && ow < g.OW;
-        const size_t off = ((size_t(n) * g.OH + (valid ? oh : 0)) * g.OW + (valid ? ow : 0)) * g.C + c8 * 8;
+        const size_t off = ((size_t(n) * g.OH + (valid ? oh : 0)) * g.OW + (valid ? ow : 0)) * g.OC + c8 * 8;
         pk[a][b] = __ldg(reinterpret_cast<const uint2*>(idx + off));
         v[a][b] = __ldg(reinterpret_cast<const uint4*>(dy + off));
         if (!valid) pk[a][b] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);  // matches no window-local index

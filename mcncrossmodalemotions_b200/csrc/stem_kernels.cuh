@@ -239,13 +239,13 @@ static __global__ void stem_bn_stats_kernel(const double* __restrict__ rs, const
 }
 
 // BN-backward reductions at the pooled resolution + ReLU masking of the pooled gradient (in place).
-//   xw  : [P][C] raw (pre-BN) value of each pooling window's winner (maxpool_fwd_h2_kernel's `xwin`)
-//   g   : [P][C] gradient w.r.t. the pooled output; on exit g *= [a*xw + b > 0]
+//   xw  : [P][ld] raw (pre-BN) value of each pooling window's winner (maxpool_fwd_h2_kernel's `xwin`), C <= ld valid
+//   g   : [P][ld] gradient w.r.t. the pooled output; on exit g *= [a*xw + b > 0]
 //   acc : [2C] doubles, acc[c] += sum g_masked, acc[C+c] += sum g_masked * (xw - mu)/sigma
 // Every conv-resolution position that receives gradient is the winner of the windows that route to it, so these sums
 // equal the full-resolution sums of bn_bwd_reduce_kernel.  Same block layout as bn_stats_kernel.
 static __global__ void stem_pool_bn_reduce_kernel(const __half* __restrict__ xw, __half* __restrict__ g, size_t P, int C,
-                                                  int lanes, int rows_par, const float* __restrict__ moments,
+                                                  int ld, int lanes, int rows_par, const float* __restrict__ moments,
                                                   const float* __restrict__ a, const float* __restrict__ b,
                                                   double* __restrict__ acc) {
   __shared__ float red[2][256][8];
@@ -269,7 +269,7 @@ static __global__ void stem_pool_bn_reduce_kernel(const __half* __restrict__ xw,
     const size_t stride = size_t(gridDim.x) * rows_par;
     for (size_t r = size_t(blockIdx.x) * rows_par + rl; r < P; r += 2 * stride) {
       const bool two = r + stride < P;
-      const size_t o0 = r * C + c8 * 8, o1 = (two ? r + stride : r) * C + c8 * 8;
+      const size_t o0 = r * ld + c8 * 8, o1 = (two ? r + stride : r) * ld + c8 * 8;
       uint4 vx0 = __ldg(reinterpret_cast<const uint4*>(xw + o0));
       uint4 vg0 = *reinterpret_cast<const uint4*>(g + o0);
       uint4 vx1 = __ldg(reinterpret_cast<const uint4*>(xw + o1));
@@ -353,112 +353,6 @@ static __global__ void stem_wgrad_finalize_kernel(const double* __restrict__ rs,
     dbeta[k] = float(db);
     if (dbias) dbias[k] = 0.f;   // a bias ahead of train-mode BN has an identically zero gradient
   }
-}
-
-// 3x3 / stride 2 / pad 0 max-pool backward of the stem fused with the ReLU mask and the two BN reductions: the
-// cell-owned gather of maxpool_bwd_3x3s2_h2_kernel (one thread owns the 2x2 input cell (2i..2i+1, 2j..2j+1) of one
-// channel group and loads the four windows (i-a, j-b) that cover it), where every window's gradient is first masked
-// with [a*xwin + b > 0] and the window (i, j) itself -- each window is "its own" cell's a = b = 0 load exactly once --
-// contributes to  acc[c] += g_masked,  acc[C+c] += g_masked * (xwin - mu)/sigma.  Replaces a separate pass over the
-// pooled tensors (stem_pool_bn_reduce_kernel) and leaves the pooled gradient untouched.
-static __global__ void __launch_bounds__(256)
-stem_pool_bwd_reduce_kernel(const __half* __restrict__ dy, const uint8_t* __restrict__ idx, const __half* __restrict__ xwin,
-                            PoolGeom g, const float* __restrict__ moments, const float* __restrict__ a,
-                            const float* __restrict__ b, __half* __restrict__ dx, double* __restrict__ acc) {
-  extern __shared__ float pbr_smem[];   // [2][C]
-  const uint32_t C8 = uint32_t(g.C >> 3);
-  const uint32_t HC = uint32_t(g.H + 1) >> 1, WC = uint32_t(g.W + 1) >> 1;
-  const uint32_t ncell = uint32_t(g.N) * HC * WC;
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t c8 = tid % C8;
-  const uint32_t pstride = (gridDim.x * blockDim.x) / C8;
-  float av[8], bv[8], s1[8], s2[8];   // s2 accumulates g*x; centred and scaled at the flush
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    av[k] = a[c8 * 8 + k];
-    bv[k] = b[c8 * 8 + k];
-    s1[k] = 0.f;
-    s2[k] = 0.f;
-  }
-  for (int c = threadIdx.x; c < 2 * g.C; c += blockDim.x) pbr_smem[c] = 0.f;
-  __syncthreads();
-  for (uint32_t pp = tid / C8; pp < ncell; pp += pstride) {
-    const uint32_t t1 = pp / WC;
-    const int j = int(pp - t1 * WC);
-    const int n = int(t1 / HC);
-    const int i = int(t1 - uint32_t(n) * HC);
-    uint2 pk[2][2];
-    uint4 v[2][2];
-#pragma unroll
-    for (int wa = 0; wa < 2; ++wa)
-#pragma unroll
-      for (int wb = 0; wb < 2; ++wb) {
-        const int oh = i - wa, ow = j - wb;
-        const bool valid = oh >= 0 && oh < g.OH && ow >= 0 && ow < g.OW;
-        const size_t off = ((size_t(n) * g.OH + (valid ? oh : 0)) * g.OW + (valid ? ow : 0)) * g.C + c8 * 8;
-        pk[wa][wb] = __ldg(reinterpret_cast<const uint2*>(idx + off));
-        uint4 gv = __ldg(reinterpret_cast<const uint4*>(dy + off));
-        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xwin + off));
-        if (!valid) pk[wa][wb] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);  // matches no window-local index
-        // ReLU mask on the window's gradient; the window's own cell also accumulates the BN reductions
-        const __half2* x2 = reinterpret_cast<const __half2*>(&xv);
-        __half2* g2 = reinterpret_cast<__half2*>(&gv);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 fx = __half22float2(x2[k]);
-          float2 fg = __half22float2(g2[k]);
-          if (!(fmaf(av[2 * k], fx.x, bv[2 * k]) > 0.f)) fg.x = 0.f;
-          if (!(fmaf(av[2 * k + 1], fx.y, bv[2 * k + 1]) > 0.f)) fg.y = 0.f;
-          g2[k] = __floats2half2_rn(fg.x, fg.y);   // exact: the stored fp16 value or zero
-          if (wa == 0 && wb == 0 && valid) {
-            s1[2 * k] += fg.x;
-            s1[2 * k + 1] += fg.y;
-            s2[2 * k] = fmaf(fg.x, fx.x, s2[2 * k]);
-            s2[2 * k + 1] = fmaf(fg.y, fx.y, s2[2 * k + 1]);
-          }
-        }
-        v[wa][wb] = gv;
-      }
-#pragma unroll
-    for (int py = 0; py < 2; ++py)
-#pragma unroll
-      for (int px = 0; px < 2; ++px) {
-        const int h = 2 * i + py, w = 2 * j + px;
-        if (h >= g.H || w >= g.W) continue;
-        __half2 accv[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) accv[k] = __floats2half2_rn(0.f, 0.f);
-#pragma unroll
-        for (int wa = 0; wa < 2; ++wa) {
-          if (wa == 1 && py == 1) continue;  // window i-1 reaches row 2i only (dh = 2)
-#pragma unroll
-          for (int wb = 0; wb < 2; ++wb) {
-            if (wb == 1 && px == 1) continue;
-            const uint32_t me4 = uint32_t((px + 2 * wb) * 3 + (py + 2 * wa)) * 0x01010101u;  // dw * PH + dh
-            const uint32_t m0 = __vcmpeq4(pk[wa][wb].x, me4), m1 = __vcmpeq4(pk[wa][wb].y, me4);
-            const uint32_t w0 = v[wa][wb].x & __byte_perm(m0, 0, 0x1100), w1 = v[wa][wb].y & __byte_perm(m0, 0, 0x3322);
-            const uint32_t w2 = v[wa][wb].z & __byte_perm(m1, 0, 0x1100), w3 = v[wa][wb].w & __byte_perm(m1, 0, 0x3322);
-            accv[0] = __hadd2(accv[0], *reinterpret_cast<const __half2*>(&w0));
-            accv[1] = __hadd2(accv[1], *reinterpret_cast<const __half2*>(&w1));
-            accv[2] = __hadd2(accv[2], *reinterpret_cast<const __half2*>(&w2));
-            accv[3] = __hadd2(accv[3], *reinterpret_cast<const __half2*>(&w3));
-          }
-        }
-        uint4 o;
-        __half2* o2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) o2[k] = accv[k];
-        *reinterpret_cast<uint4*>(dx + ((size_t(n) * g.H + h) * g.W + w) * g.C + c8 * 8) = o;
-      }
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float m = moments[c8 * 8 + k], isg = 1.f / moments[g.C + c8 * 8 + k];
-    atomicAdd(&pbr_smem[c8 * 8 + k], s1[k]);
-    atomicAdd(&pbr_smem[g.C + c8 * 8 + k], (s2[k] - m * s1[k]) * isg);   // sum g*(x - mu)/sigma
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < 2 * g.C; c += blockDim.x) atomicAdd(acc + c, double(pbr_smem[c]));
 }
 
 // Pixel-pair form of the stem convolution: the s2d tensor [N][HP][OW][16] viewed as [N][HP][OW/2][32] and the

@@ -389,14 +389,20 @@ static bool pool_geom(PoolGeom* g, int N, int H, int W, int C, int PH, int PW, i
   g->N = N; g->H = H; g->W = W; g->C = C; g->PH = PH; g->PW = PW; g->sh = sh; g->sw = sw; g->pt = pt; g->pl = pl;
   g->OH = (H + pt + pb - PH) / sh + 1;
   g->OW = (W + pl + pr - PW) / sw + 1;
+  g->OC = C;
   return g->OH > 0 && g->OW > 0 && C % 8 == 0 && PH * PW <= 255;
 }
 
 static int maxpool_fwd_impl(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
                             int pt, int pb, int pl, int pr, const float* a, const float* b, void* y16, uint8_t* argmax,
-                            __half* xwin) {
+                            __half* xwin, int pooled_ld) {
   PoolGeom g;
   XEMO_REQUIRE(ctx, x16 && y16 && pool_geom(&g, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr), "maxpool_fwd: bad geometry");
+  if (pooled_ld) {
+    XEMO_REQUIRE(ctx, pooled_ld >= C && pooled_ld % 8 == 0 && ((PH == 3 && PW == 3) || (PH == 5 && PW == 3)),
+                 "maxpool_fwd: a pooled-side pitch needs the 3x3 / 5x3 fast paths and ld >= C, ld %% 8 == 0");
+    g.OC = pooled_ld;
+  }
   const size_t total = size_t(N) * g.OH * g.OW * (C / 8);
   XEMO_REQUIRE(ctx, size_t(N) * g.OH * g.OW < (size_t(1) << 31), "maxpool_fwd: tensor too large for 32-bit pixel indices");
   const int grid = fixed_channel_grid(total, C / 8, 256, ctx->num_sms, 8);
@@ -422,21 +428,26 @@ static int maxpool_fwd_impl(xemo_ctx* ctx, const void* x16, int N, int H, int W,
 extern "C" int xemo_op_maxpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
                                    int pt, int pb, int pl, int pr, const float* a, const float* b, void* y16,
                                    uint8_t* argmax) {
-  return maxpool_fwd_impl(ctx, x16, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr, a, b, y16, argmax, nullptr);
+  return maxpool_fwd_impl(ctx, x16, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr, a, b, y16, argmax, nullptr, 0);
 }
 
 extern "C" int xemo_op_maxpool_fwd_win(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh,
                                        int sw, int pt, int pb, int pl, int pr, const float* a, const float* b, void* y16,
-                                       uint8_t* argmax, void* xwin16) {
-  XEMO_REQUIRE(ctx, xwin16, "maxpool_fwd_win: null winner buffer");
-  return maxpool_fwd_impl(ctx, x16, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr, a, b, y16, argmax, static_cast<__half*>(xwin16));
+                                       uint8_t* argmax, void* xwin16, int pooled_ld) {
+  return maxpool_fwd_impl(ctx, x16, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr, a, b, y16, argmax, static_cast<__half*>(xwin16),
+                          pooled_ld);
 }
 
-extern "C" int xemo_op_maxpool_bwd(xemo_ctx* ctx, const void* dy16, const uint8_t* argmax, int N, int H, int W, int C, int PH,
-                                   int PW, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16) {
+static int maxpool_bwd_impl(xemo_ctx* ctx, const void* dy16, const uint8_t* argmax, int N, int H, int W, int C, int PH, int PW,
+                            int sh, int sw, int pt, int pb, int pl, int pr, void* dx16, int pooled_ld) {
   PoolGeom g;
   XEMO_REQUIRE(ctx, dy16 && argmax && dx16 && pool_geom(&g, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr),
                "maxpool_bwd: bad geometry");
+  if (pooled_ld) {
+    XEMO_REQUIRE(ctx, pooled_ld >= C && pooled_ld % 8 == 0 && PH == 3 && PW == 3 && sh == 2 && sw == 2 && pt == 0 && pl == 0,
+                 "maxpool_bwd: a pooled-side pitch needs the 3x3 / stride 2 / pad 0 path and ld >= C, ld %% 8 == 0");
+    g.OC = pooled_ld;
+  }
   const size_t total = size_t(N) * H * W * (C / 8);
   XEMO_REQUIRE(ctx, size_t(N) * H * W < (size_t(1) << 31), "maxpool_bwd: tensor too large for 32-bit pixel indices");
   const int grid = fixed_channel_grid(total, C / 8, 256, ctx->num_sms, 8);
@@ -450,6 +461,16 @@ extern "C" int xemo_op_maxpool_bwd(xemo_ctx* ctx, const void* dy16, const uint8_
     maxpool_bwd_kernel<__half, 0, 0><<<grid, 256, 0, ctx->stream>>>(static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
+}
+
+extern "C" int xemo_op_maxpool_bwd(xemo_ctx* ctx, const void* dy16, const uint8_t* argmax, int N, int H, int W, int C, int PH,
+                                   int PW, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16) {
+  return maxpool_bwd_impl(ctx, dy16, argmax, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr, dx16, 0);
+}
+
+extern "C" int xemo_op_maxpool_bwd_ld(xemo_ctx* ctx, const void* dy16, const uint8_t* argmax, int N, int H, int W, int C, int PH,
+                                      int PW, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16, int pooled_ld) {
+  return maxpool_bwd_impl(ctx, dy16, argmax, N, H, W, C, PH, PW, sh, sw, pt, pb, pl, pr, dx16, pooled_ld);
 }
 
 extern "C" int xemo_op_avgpool_fwd(xemo_ctx* ctx, const void* x16, int N, int H, int W, int C, int PH, int PW, int sh, int sw,
@@ -665,31 +686,16 @@ extern "C" int xemo_op_stem_bn_train(xemo_ctx* ctx, const double* ws, const void
   return XEMO_OK;
 }
 
-extern "C" int xemo_op_stem_pool_bn_reduce(xemo_ctx* ctx, const void* xwin16, void* dpool16, size_t P, int C,
+extern "C" int xemo_op_stem_pool_bn_reduce(xemo_ctx* ctx, const void* xwin16, void* dpool16, size_t P, int C, int ld,
                                            const float* moments, const float* a, const float* b, double* acc) {
-  XEMO_REQUIRE(ctx, xwin16 && dpool16 && moments && a && b && acc && C % 8 == 0 && P > 0, "stem_pool_bn_reduce: bad arguments");
+  if (ld == 0) ld = C;
+  XEMO_REQUIRE(ctx, xwin16 && dpool16 && moments && a && b && acc && C % 8 == 0 && ld % 8 == 0 && ld >= C && P > 0,
+               "stem_pool_bn_reduce: bad arguments");
   XEMO_CUDA(ctx, cudaMemsetAsync(acc, 0, size_t(2) * C * sizeof(double), ctx->stream));
   const BnGrid bg = bn_grid(P, C, ctx->num_sms);
   dim3 grid(bg.slabs_x, bg.slabs_y);
   stem_pool_bn_reduce_kernel<<<grid, kBnThreads, 0, ctx->stream>>>(static_cast<const __half*>(xwin16), static_cast<__half*>(dpool16),
-                                                                  P, C, bg.lanes, bg.rows_par, moments, a, b, acc);
-  XEMO_LAUNCHED(ctx, 1);
-  return XEMO_OK;
-}
-
-extern "C" int xemo_op_stem_pool_bwd_reduce(xemo_ctx* ctx, const void* dpool16, const uint8_t* argmax, const void* xwin16, int N,
-                                            int H, int W, int C, const float* moments, const float* a, const float* b,
-                                            void* dx16, double* acc) {
-  PoolGeom g;
-  XEMO_REQUIRE(ctx, dpool16 && argmax && xwin16 && moments && a && b && dx16 && acc && C <= 2048 &&
-                        pool_geom(&g, N, H, W, C, 3, 3, 2, 2, 0, 0, 0, 0),
-               "stem_pool_bwd_reduce: bad arguments (3x3 / stride 2 / pad 0 pooling over N x H x W x C)");
-  XEMO_REQUIRE(ctx, size_t(N) * H * W < (size_t(1) << 31), "stem_pool_bwd_reduce: tensor too large for 32-bit pixel indices");
-  XEMO_CUDA(ctx, cudaMemsetAsync(acc, 0, size_t(2) * C * sizeof(double), ctx->stream));
-  const size_t cells = size_t(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  stem_pool_bwd_reduce_kernel<<<fixed_channel_grid(cells, C / 8, 256, ctx->num_sms, 8), 256, size_t(2) * C * 4, ctx->stream>>>(
-      static_cast<const __half*>(dpool16), argmax, static_cast<const __half*>(xwin16), g, moments, a, b,
-      static_cast<__half*>(dx16), acc);
+                                                                  P, C, ld, bg.lanes, bg.rows_par, moments, a, b, acc);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }

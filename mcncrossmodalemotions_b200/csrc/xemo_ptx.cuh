@@ -167,6 +167,11 @@ __device__ __forceinline__ void sts_u4(uint32_t saddr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// fp32 x 4 reduction into global memory (one 16-byte sector operation instead of four)
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 // Instruction descriptor for kind::f16: fp16 A/B, fp32 D.  Bit layout (PTX ISA "Instruction descriptor"):
 // [4,6) D fmt (1=f32) | [7,10) A fmt (0=f16) | [10,13) B fmt | 15 A major (0=K) | 16 B major (0=K)

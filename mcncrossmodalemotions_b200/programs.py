@@ -318,9 +318,11 @@ class StudentProgram(_Base):
         # conv1 forward in pixel-pair form (32-channel view of the s2d tensor, block-diagonal filter): half the TMA row
         # requests per output pixel.  Needs an even conv1 output width (true for every width bucket 100..1000).
         self.stem_pairs = os.environ.get("XEMO_STEM_PAIRS", "1") != "0" if stem_pairs is None else bool(stem_pairs)
-        # mask + BN reductions inside the pool-backward kernel: measured SLOWER on B200 than the two-kernel form (1.01 ms vs
-        # 0.35 + 0.60 ms at batch 256 -- the cell-owned gather becomes instruction-bound), so off by default
-        self.stem_fused_pool_bwd = os.environ.get("XEMO_STEM_FUSED_POOL_BWD", "0") != "0"
+        # conv2 reads its input (pool1's output) with a 128-channel pitch (96 real + 32 zero channels): 128-byte TMA rows for
+        # the forward / filter-gradient operand tiles instead of 64-byte ones (the kernels are bound by TMA rows, not bytes).
+        # Rides on the stem path (its pooling kernels take a pooled-side pitch).  XEMO_CONV2_PAD=0 disables.
+        self.conv2_pad = self.stem_algebra and os.environ.get("XEMO_CONV2_PAD", "1") != "0"
+        self.stem_wgrad_pairs = os.environ.get("XEMO_STEM_WGRAD_PAIRS", "0") != "0"
         self.side_stream = None   # torch.cuda.Stream: filter gradients run there, off the dgrad critical path
         self._geometry()
         self._load(params)
@@ -349,6 +351,11 @@ class StudentProgram(_Base):
         L1 = self.layers[0]
         self.s2d_hp, self.s2d_ow = L1["oh"] + 3, L1["ow"]
         self.stem_pairs = self.stem_pairs and L1["ow"] % 2 == 0
+        for L in self.layers:
+            L["cp"] = _pad16(L["cin"])
+        if self.conv2_pad:
+            self.layers[1]["cp"] = (self.layers[1]["cin"] + 63) // 64 * 64
+        self.pool1_ld = self.layers[1]["cp"]   # channel pitch of pool1's output / gradient / arg-max / winner tensors
 
     # ---- parameters: one flat fp32 master / momentum / gradient buffer (single all-reduce payload)
     def _load(self, p):
@@ -364,7 +371,7 @@ class StudentProgram(_Base):
         for L in self.layers:
             n = L["name"]
             f = p[n + "f"].astype(np.float32)
-            dev = student_conv1_to_s2d(f) if n == "conv1" else krsc(f)
+            dev = student_conv1_to_s2d(f) if n == "conv1" else krsc(f, cp=L["cp"])
             host[n + "f"] = seg(n + "f", dev)
             b = np.zeros(L["kp"], np.float32)
             b[: L["cout"]] = p[n + "b"]
@@ -419,12 +426,13 @@ class StudentProgram(_Base):
                 A[n + ":ws"] = torch.zeros(2 * L["cout"], dtype=torch.float64, device=self.device)
             P = L["pool"]
             if P:
-                A[n + ":out"] = self.f16(N, P["oh"], P["ow"], L["cout"])
-                A[n + ":dout"] = self.f16(N, P["oh"], P["ow"], L["cout"])
+                pc = self.pool1_ld if n == "conv1" else L["cout"]   # (padding channels stay zero: never written)
+                A[n + ":out"] = self.f16(N, P["oh"], P["ow"], pc)
+                A[n + ":dout"] = self.f16(N, P["oh"], P["ow"], pc)
                 if P["method"] == "max":
-                    A[n + ":arg"] = torch.zeros((N, P["oh"], P["ow"], L["cout"]), dtype=torch.uint8, device=self.device)
+                    A[n + ":arg"] = torch.zeros((N, P["oh"], P["ow"], pc), dtype=torch.uint8, device=self.device)
                     if n == "conv1" and self.stem_algebra:
-                        A[n + ":xwin"] = self.f16(N, P["oh"], P["ow"], L["cout"])
+                        A[n + ":xwin"] = self.f16(N, P["oh"], P["ow"], pc)
                 else:
                     A[n + ":act"] = self.f16(N, L["oh"], L["ow"], L["cout"])
                     A[n + ":dact"] = self.f16(N, L["oh"], L["ow"], L["cout"])
@@ -432,7 +440,7 @@ class StudentProgram(_Base):
                 A[n + ":out"] = self.f16(N, L["oh"], L["ow"], L["cout"])
                 A[n + ":dout"] = self.f16(N, L["oh"], L["ow"], L["cout"])
             if n not in ("conv1",):
-                A[n + ":packed"] = self.f16(int(self.ctx.lib.xemo_dgrad_pack_elems(_pad16(L["cin"]), L["kp"], L["fh"], L["fw"],
+                A[n + ":packed"] = self.f16(int(self.ctx.lib.xemo_dgrad_pack_elems(L["cp"], L["kp"], L["fh"], L["fw"],
                                                                                   L["stride"][0], L["stride"][1])))
         A["pred32"] = self.f32(N, self.layers[-1]["kp"])
         A["scalars"] = self.f32(2)          # objective, classerror (accumulated)
@@ -456,7 +464,7 @@ class StudentProgram(_Base):
             if n == "conv1":
                 self._stem_conv(wt, None, bias, 0, A[n + ":raw"])
             else:
-                self.conv(cur, N, L["h"], L["w"], _pad16(L["cin"]), wt, L["kp"], L["fh"], L["fw"], L["stride"], L["pad"], None, bias,
+                self.conv(cur, N, L["h"], L["w"], L["cp"], wt, L["kp"], L["fh"], L["fw"], L["stride"], L["pad"], None, bias,
                           None, 0, A[n + ":raw"], A["pred32"] if last else None, L["kp"])
             cur = A[n + ":raw"]
             if not L["bn"]:
@@ -475,7 +483,7 @@ class StudentProgram(_Base):
             if P and P["method"] == "max" and stem:
                 ctx.op_maxpool_fwd_win(_p(cur), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1], P["stride"][0],
                                        P["stride"][1], 0, 0, 0, 0, _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":out"]),
-                                       _p(A[n + ":arg"]), _p(A[n + ":xwin"]))
+                                       _p(A[n + ":arg"]), _p(A[n + ":xwin"]), self.pool1_ld)
             elif P and P["method"] == "max":
                 ctx.op_maxpool_fwd(_p(cur), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1], P["stride"][0], P["stride"][1],
                                    0, 0, 0, 0, _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":out"]), _p(A[n + ":arg"]))
@@ -524,9 +532,13 @@ class StudentProgram(_Base):
             if n == "conv1":
                 self._stem_conv(wt, scale, shift, relu, dst)
             else:
-                self.conv(cur, N, L["h"], L["w"], _pad16(L["cin"]), wt, L["kp"], L["fh"], L["fw"], L["stride"], L["pad"], scale, shift,
+                self.conv(cur, N, L["h"], L["w"], L["cp"], wt, L["kp"], L["fh"], L["fw"], L["stride"], L["pad"], scale, shift,
                           None, relu, dst, out32, L["kp"])
-            if P and P["method"] == "max":
+            if P and P["method"] == "max" and n == "conv1" and self.pool1_ld != L["cout"]:
+                ctx.op_maxpool_fwd_win(_p(dst), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1], P["stride"][0], P["stride"][1],
+                                       0, 0, 0, 0, None, None, _p(A[n + ":out"]), None, None, self.pool1_ld)
+                dst = A[n + ":out"]
+            elif P and P["method"] == "max":
                 ctx.op_maxpool_fwd(_p(dst), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1], P["stride"][0], P["stride"][1],
                                    0, 0, 0, 0, None, None, _p(A[n + ":out"]), None)
                 dst = A[n + ":out"]
@@ -571,15 +583,11 @@ class StudentProgram(_Base):
                 prow = N * P["oh"] * P["ow"]
                 # ReLU mask + the two BN reductions at the pooled resolution, then the (masked) gradient w.r.t. the
                 # never-materialised ReLU output at the conv resolution: dz, which the filter gradient consumes directly
-                if P["win"] == (3, 3) and P["stride"] == (2, 2) and self.stem_fused_pool_bwd:
-                    ctx.op_stem_pool_bwd_reduce(_p(A[n + ":dout"]), _p(A[n + ":arg"]), _p(A[n + ":xwin"]), N, L["oh"], L["ow"], L["cout"],
-                                                _p(self.batch_moments[bn]), _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":draw"]),
-                                                _p(A[n + ":ws"]))
-                else:
-                    ctx.op_stem_pool_bn_reduce(_p(A[n + ":xwin"]), _p(A[n + ":dout"]), prow, L["cout"], _p(self.batch_moments[bn]),
-                                               _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":ws"]))
-                    ctx.op_maxpool_bwd(_p(A[n + ":dout"]), _p(A[n + ":arg"]), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1],
-                                       P["stride"][0], P["stride"][1], 0, 0, 0, 0, _p(A[n + ":draw"]))
+                ld = self.pool1_ld
+                ctx.op_stem_pool_bn_reduce(_p(A[n + ":xwin"]), _p(A[n + ":dout"]), prow, L["cout"], ld, _p(self.batch_moments[bn]),
+                                           _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":ws"]))
+                ctx.op_maxpool_bwd_ld(_p(A[n + ":dout"]), _p(A[n + ":arg"]), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1],
+                                      P["stride"][0], P["stride"][1], 0, 0, 0, 0, _p(A[n + ":draw"]), ld)
                 fused_bias = True
             elif L["bn"]:
                 bn = "bn" + n[-1]
@@ -616,7 +624,7 @@ class StudentProgram(_Base):
                 ctx.set_stream(VP(self.side_stream.cuda_stream))
             if stem:
                 gf = self.view(self.grad, n + "f")
-                if self.stem_pairs:   # G1 in pixel-pair form: 64-byte TMA rows, both 128-kout tiles share the patch tiles
+                if self.stem_pairs and self.stem_wgrad_pairs:   # G1 in pixel-pair form (measured slower: 0.80 vs 0.74 ms)
                     g1p = A["stem:g1pair"]
                     ctx.memset(_p(g1p), 0, g1p.numel() * 4)
                     ctx.op_conv_wgrad(_p(x), N, self.s2d_hp, self.s2d_ow // 2, 32, _p(dy), 2 * L["kp"], 2 * L["kp"], 4, 1, 1, 1,
@@ -637,7 +645,7 @@ class StudentProgram(_Base):
                 ctx.op_fill_strided_f32(_p(gf), L["kp"] * 4, 16, 15, 1, 0.0)
                 ctx.op_fill_strided_f32(_p(gf), L["kp"], 64, 3 * 16 + 8, 8, 0.0)
             else:
-                cp = _pad16(L["cin"])
+                cp = L["cp"]
                 ctx.op_conv_wgrad(_p(x), N, L["h"], L["w"], cp, _p(dy), L["kp"], L["kp"], L["fh"], L["fw"], L["stride"][0],
                                   L["stride"][1], *L["pad"], _p(self.view(self.grad, n + "f")), inv)
             if not fused_bias:
@@ -645,7 +653,7 @@ class StudentProgram(_Base):
             if side:
                 ctx.set_stream(None)
             if i > 0:
-                cp = _pad16(L["cin"])
+                cp = L["cp"]
                 ctx.op_pack_dgrad_filters(_p(self.view(self.w16, n + "f")), L["kp"], L["fh"], L["fw"], cp, L["stride"][0],
                                           L["stride"][1], L["pad"][0], L["pad"][2], _p(A[n + ":packed"]))
                 ctx.op_conv_dgrad(_p(dy), N, L["h"], L["w"], cp, _p(A[n + ":packed"]), L["kp"], L["fh"], L["fw"], L["stride"][0],
@@ -791,7 +799,7 @@ class StudentProgram(_Base):
         for L in self.layers:
             n = L["name"]
             o, shape = self.segs[n + "f"]
-            w = student_conv1_to_s2d(momentum[n + "f"]) if n == "conv1" else krsc(momentum[n + "f"])
+            w = student_conv1_to_s2d(momentum[n + "f"]) if n == "conv1" else krsc(momentum[n + "f"], cp=L["cp"])
             flat[o : o + w.size] = w.reshape(-1)
             o, _ = self.segs[n + "b"]
             flat[o : o + L["cout"]] = momentum[n + "b"]
