@@ -128,6 +128,8 @@ class ConvProfiler:
             fl *= 49.0 / 128.0     # student conv1 in pixel-pair form: block-diagonal 4x1x32 filter, 2 x kout columns
         elif cin == 32 and r == 7 and s == 1:
             fl *= 147.0 / 224.0    # teacher conv1: 7x7x3 taps inside the 7x1x32 row-im2col filter
+        if cin == 128 and r == 5 and s == 5:
+            fl *= 96.0 / 128.0     # student conv2: 96 real input channels inside the 128-channel pitch
         if kout == 16 and cin in (1024, 2048):
             fl *= 0.5              # 8 logits padded to 16 output channels
         return fl

@@ -207,7 +207,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int acc = 0;
       uint32_t acc_phase = 0;
       if (b_res && int(blockIdx.x) < num_tiles) mbar_wait(b_res_bar, 0);
-      const uint32_t sb_res = smem_u32(b_res_buf);
+      const uint64_t desc0 = make_smem_desc(smem_u32(smem), 16, kSbo, ConvSwizzle<BK>::mode);
+      const uint32_t desc_hi = uint32_t(desc0 >> 32), desc_lo0 = uint32_t(desc0);
+      const uint32_t stage_inc = uint32_t(stage_bytes) >> 4, bslot_inc = uint32_t(b_slot) >> 4;
+      const uint32_t bres_off = (smem_u32(b_res_buf) - smem_u32(smem)) >> 4;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -215,14 +218,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + size_t(stage) * stage_bytes);
-          const uint32_t sb = b_res ? sb_res + uint32_t(it) * uint32_t(b_slot) : sa + kABytes;
-          const uint64_t a_desc = make_smem_desc(sa, 16, kSbo, ConvSwizzle<BK>::mode);
-          const uint64_t b_desc = make_smem_desc(sb, 16, kSbo, ConvSwizzle<BK>::mode);
+          // descriptors: the (smem base) descriptor is built once; only the 14-bit address field moves (no carry:
+          // smem < 256 KB) -- the single issuing thread has 32..128 cycles per MMA
+          const uint32_t a_lo = desc_lo0 + uint32_t(stage) * stage_inc;
+          const uint32_t b_lo = b_res ? desc_lo0 + bres_off + uint32_t(it) * bslot_inc : a_lo + (uint32_t(kABytes) >> 4);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
-            umma_f16_ss(d_tmem, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc,
+            umma_f16_ss(d_tmem, (uint64_t(desc_hi) << 32) | (a_lo + 2u * k), (uint64_t(desc_hi) << 32) | (b_lo + 2u * k), idesc,
                         (it > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire

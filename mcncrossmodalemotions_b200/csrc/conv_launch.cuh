@@ -267,6 +267,7 @@ inline bool conv_wgrad_plan(WgradPlan* plan, const ConvGeom& g, const __half* x,
   p.num_stages = stages;
   p.dF = dF;
   p.scale = scale;
+  p.red_vec = p.splits <= 64 ? 1 : 0;
   plan->smem = stages * stage_bytes + 1024 + (2 * stages + 2) * 8 + 16;
   const int items = p.m_items * p.groups * p.splits;
   plan->grid = items < num_sms ? items : num_sms;

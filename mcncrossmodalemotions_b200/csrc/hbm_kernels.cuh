@@ -208,10 +208,11 @@ static __global__ void spec_s2d_from_hwcn_kernel(const float* __restrict__ src, 
 // ============================================================================================
 struct PoolGeom {
   int N, H, W, C;       // input
-  int OC;               // channel pitch of the pooled-side tensors (y / arg-max / winner / dy): C, or larger when the
-                        // consumer wants zero-padded channels (fp16 fast paths only)
   int PH, PW, sh, sw, pt, pl;
   int OH, OW;
+  int OC;               // channel pitch of the pooled-side tensors (y / arg-max / winner / dy): C, or larger when the
+                        // consumer wants zero-padded channels (fp16 fast paths only).  Last member: aggregate
+                        // initialisers that stop at OW leave it 0 and only reach kernels that ignore it.
 };
 
 // Grid for kernels whose threads keep per-channel coefficients in registers: the total thread count is
