@@ -154,7 +154,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_f16(kWgBlockM, p.block_c, 1, 1);  // A and B MN-major
+      const uint32_t idesc0 = make_idesc_f16(kWgBlockM, 0, 1, 1);  // A and B MN-major; the N field is added per MMA
+      const int max_merge = p.block_c >= 256 ? 1 : 256 / p.block_c;
       const uint32_t swz_a = (p.chunk_a == 64) ? 2u : (p.chunk_a == 32) ? 4u : 6u;
       const uint32_t swz_b = (p.chunk_b == 64) ? 2u : (p.chunk_b == 32) ? 4u : 6u;
       const uint32_t sbo_a = 8 * p.chunk_a * 2, lbo_a = kWgPix * p.chunk_a * 2;
@@ -194,10 +195,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
             for (int mi = 0; mi < nm; ++mi) {
               const uint64_t a_desc = (uint64_t(a_hi) << 32) | a_d;
               uint32_t b_d = b_k, d = d_mi;
-              for (int t = 0; t < nsub; ++t) {
-                umma_f16_ss(d, a_desc, (uint64_t(b_hi) << 32) | b_d, idesc, accumulate);
-                b_d += b_t_inc;
-                d += d_t_inc;
+              // consecutive sub-tiles are consecutive chunk sequences in smem (b_sub_bytes = b_chunks * LBO) and
+              // consecutive TMEM column ranges: up to 256 / block_c of them go out as ONE MMA with N = tm * block_c
+              for (int t = 0; t < nsub;) {
+                const int tm = min(nsub - t, max_merge);
+                umma_f16_ss(d, a_desc, (uint64_t(b_hi) << 32) | b_d, idesc0 + (uint32_t(tm * p.block_c) >> 3 << 17), accumulate);
+                b_d += uint32_t(tm) * b_t_inc;
+                d += uint32_t(tm) * d_t_inc;
+                t += tm;
               }
               a_d += a_mi_inc;
               d_mi += d_mi_inc;
