@@ -126,6 +126,8 @@ class ConvProfiler:
             fl *= 49.0 / 64.0      # student conv1: 7x7x1 taps inside the 4x1x16 space-to-depth filter
         elif cin == 32 and r == 4 and s == 1:
             fl *= 49.0 / 128.0     # student conv1 in pixel-pair form: block-diagonal 4x1x32 filter, 2 x kout columns
+        elif cin == 64 and r == 7 and s == 1:
+            fl *= 147.0 / 448.0    # teacher conv1 in pixel-pair form: block-diagonal 7x1x64 filter, 2 x kout columns
         elif cin == 32 and r == 7 and s == 1:
             fl *= 147.0 / 224.0    # teacher conv1: 7x7x3 taps inside the 7x1x32 row-im2col filter
         if cin == 128 and r == 5 and s == 5:

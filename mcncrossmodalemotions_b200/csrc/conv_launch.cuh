@@ -100,11 +100,11 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   const int k_iters = g.R * g.S * p.kc_blocks;
   const int want_stages = k_iters + 1 < 3 ? k_iters + 1 : 3;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
-  // resident filter (one load per CTA instead of one per tile): a single N tile, at most 80 KB, and enough tiles per
-  // CTA to amortise it.  XEMO_CONV_BRES=0 disables (A/B measurements).
+  // resident filter (one load per CTA instead of one per tile): a single N tile, at most 112 KB (the teacher stem in
+  // pixel-pair form: 7 x 16 KB), and at least one tile per CTA.  XEMO_CONV_BRES=0 disables (A/B measurements).
   static const bool bres_enabled = [] { const char* e = getenv("XEMO_CONV_BRES"); return !(e && e[0] == '0'); }();
   const int bres_bytes = k_iters * conv_b_slot_bytes(bk, p.block_n);
-  p.b_resident = (bres_enabled && p.num_n_tiles == 1 && bres_bytes <= 80 * 1024 && tiles >= num_sms) ? 1 : 0;
+  p.b_resident = (bres_enabled && p.num_n_tiles == 1 && bres_bytes <= 112 * 1024 && tiles >= num_sms) ? 1 : 0;
   const int stage_bytes = conv_stage_bytes(bk, p.block_n, p.b_resident);
   const int fixed_bytes = p.b_resident ? bres_bytes : 0;
   int stages = 0, epi_bytes = 0;

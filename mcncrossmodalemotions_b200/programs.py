@@ -87,6 +87,16 @@ def student_conv1_from_s2d(g):
     return f
 
 
+def pair_filter(g):
+    """[K][R][1][C] filter -> block-diagonal [2K][R][1][2C] filter of the pixel-pair form (two horizontally adjacent
+    output pixels as one GEMM row): G2[e*K + k][r][0][e'*C + c] = [e == e'] G[k][r][0][c]."""
+    k, r, _, c = g.shape
+    g2 = np.zeros((2 * k, r, 1, 2 * c), g.dtype)
+    g2[:k, :, :, :c] = g
+    g2[k:, :, :, c:] = g
+    return g2
+
+
 def teacher_conv1_to_rows(f):
     """7 x 7 x 3 x K stride-2 filter -> [K][7][1][32] filter over the row-im2col input:
     G[k][r][0][s*4 + c] = F[r, s, c, k]."""
@@ -163,8 +173,16 @@ class TeacherProgram(_Base):
 
     def _load(self, p):
         W = self.w = {}
-        W["conv1"] = self.upload(teacher_conv1_to_rows(p["conv1f"]), torch.float16)
-        W["bn1"] = self._fold(p, "bn1")
+        # the stem in pixel-pair form: 128-byte TMA rows over the [N][224][56][64] view of the row-im2col tensor,
+        # block-diagonal [128][7][1][64] filter (resident in smem), output = the [N][112][56][128] view of c1
+        self.stem_pairs = os.environ.get("XEMO_TEACHER_STEM_PAIRS", "1") != "0"
+        g = teacher_conv1_to_rows(p["conv1f"])
+        W["conv1"] = self.upload(pair_filter(g) if self.stem_pairs else g, torch.float16)
+        a1, b1 = self._fold(p, "bn1")
+        if self.stem_pairs:
+            with torch.cuda.stream(self.stream):
+                a1, b1 = torch.cat([a1, a1]), torch.cat([b1, b1])
+        W["bn1"] = (a1, b1)
         cin = 64
         self.blocks = []
         for si, (blocks, mid, cout, stride) in enumerate(TEACHER_STAGES):
@@ -221,7 +239,10 @@ class TeacherProgram(_Base):
         else:
             ctx.op_face_rows_im2col(_p(A["faces"]), 224, 224, 3, N, 7, 2, 3, 112, _p(A["rows"]))
         a, b = W["bn1"]
-        self.conv(A["rows"], N, 224, 112, 32, W["conv1"], 64, 7, 1, (2, 1), (3, 3, 0, 0), a, b, None, 1, A["c1"])
+        if self.stem_pairs:
+            self.conv(A["rows"], N, 224, 56, 64, W["conv1"], 128, 7, 1, (2, 1), (3, 3, 0, 0), a, b, None, 1, A["c1"])
+        else:
+            self.conv(A["rows"], N, 224, 112, 32, W["conv1"], 64, 7, 1, (2, 1), (3, 3, 0, 0), a, b, None, 1, A["c1"])
         ctx.op_maxpool_fwd(_p(A["c1"]), N, 112, 112, 64, 3, 3, 2, 2, 0, 1, 0, 1, None, None, _p(A["p1"]), None)
         cur, hw = A["p1"], 56
         se = self.arch == "senet50"
