@@ -190,6 +190,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           uint32_t a_k = a_lo0 + uint32_t(stage) * stage_inc, b_k = b_lo0 + uint32_t(stage) * stage_inc;
+          if (nm == 1 && nsub <= max_merge) {
+            // one MMA per k step (the stem: N = 64, 32 tensor cycles each): the tightest possible issue loop
+            const uint32_t idesc1 = idesc0 + (uint32_t(nsub * p.block_c) >> 3 << 17);
+#pragma unroll 4
+            for (int k = 0; k < k_steps; ++k) {
+              umma_f16_ss(tmem_base, (uint64_t(a_hi) << 32) | a_k, (uint64_t(b_hi) << 32) | b_k, idesc1, accumulate);
+              accumulate = 1;
+              a_k += a_k_inc;
+              b_k += b_k_inc;
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           for (int k = 0; k < k_steps; ++k) {   // 16 pixels (GEMM-K) = two 8-row groups: advance by 2*SBO
             uint32_t a_d = a_k, d_mi = tmem_base;
             for (int mi = 0; mi < nm; ++mi) {

@@ -157,11 +157,13 @@ static __global__ void rows_im2col_from_hwcn_kernel(const float* __restrict__ sr
     __align__(16) __half v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __float2half_rn(0.f);
-    for (int s = 0; s < S; ++s) {
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {   // S <= 8, C <= 4 (host check): compile-time trip counts keep v[] in registers
       const int w = ow * stride_w + s - pad_l;
-      if (w < 0 || w >= W) continue;
-      for (int c = 0; c < C; ++c)
-        v[s * 4 + c] = __float2half_rn(src[h + size_t(H) * (w + size_t(W) * (c + size_t(C) * n))]);
+      if (s >= S || w < 0 || w >= W) continue;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) v[s * 4 + c] = __float2half_rn(src[h + size_t(H) * (w + size_t(W) * (c + size_t(C) * n))]);
     }
     uint4* o = reinterpret_cast<uint4*>(dst + ((size_t(n) * H + h) * OW + ow) * 32);
     const uint4* vi = reinterpret_cast<const uint4*>(v);

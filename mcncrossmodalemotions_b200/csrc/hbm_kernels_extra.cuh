@@ -226,9 +226,10 @@ static __global__ void face_u8_rows_im2col_kernel(const uint8_t* __restrict__ sr
     __align__(16) __half v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __float2half_rn(0.f);
-    for (int s = 0; s < S; ++s) {
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {   // S <= 8 (host check); compile-time trip count keeps v[] in registers
       const int w = ow * stride_w + s - pad_l;
-      if (w < 0 || w >= OWt) continue;
+      if (s >= S || w < 0 || w >= OWt) continue;
       const float xs = w * sx;
       int x0 = int(floorf(xs));
       x0 = min(max(x0, 0), IW - 1);
