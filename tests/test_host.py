@@ -261,3 +261,30 @@ def test_zoo_model_mirrors_the_dagnn_calls_of_the_reference_scripts():
     assert teacher.mode == "test" and teacher.getInputs() == ["data"] and teacher.vars[-1].name == "prediction"
     assert teacher.meta["normalization"]["imageSize"] == (224, 224, 3) and len(teacher.meta["classes"]["name"]) == 8
     assert sum(l.block.type == "bottleneck" for l in teacher.layers) == 16
+
+
+def test_bench_clock_sampler_windows_rows_by_time(tmp_path, monkeypatch):
+    """bench.py's nvidia-smi sampler: rows are time-stamped, only those inside the marked window count, and the caller
+    can keep the load running until two samples have landed (a fake nvidia-smi stands in for the driver tool)."""
+    import time
+
+    import bench
+
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nsleep 0.2\nwhile true; do echo '1900, 1965, 700.0, Not Active, Not Active, Not Active, Active'; sleep 0.1; done\n")
+    fake.chmod(0o755)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ["PATH"])
+    c = bench.ClockSampler(0)
+    c.start()
+    time.sleep(0.05)
+    t0 = c.mark()
+    t1 = c.mark()
+    assert c.count_between(t0, t1) == 0            # nothing can have landed in an empty window
+    for _ in range(100):
+        if c.count_between(t0, t1) >= 2:
+            break
+        time.sleep(0.05)
+        t1 = c.mark()
+    out = c.stop(t0, t1)
+    assert out["samples"] >= 2 and out["sm_mhz"] == 1900.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"]
