@@ -167,6 +167,14 @@ int xemo_op_conv_dgrad(xemo_ctx* ctx, const void* dy16, int N, int H, int W, int
 /* filter gradient, accumulated (+=) into dF[Kout][R][S][Cin] fp32, scaled by `scale` */
 int xemo_op_conv_wgrad(xemo_ctx* ctx, const void* x16, int N, int H, int W, int Cin, const void* dy16, int ldy,
                        int Kout, int R, int S, int sh, int sw, int pt, int pb, int pl, int pr, float* dF, float scale);
+/* host-side shape planning of the two tcgen05 kernels without a device (no tensor maps are encoded): the tile shape,
+ * pipeline depth and work split chosen for a geometry, for CPU-side invariant checks.  out receives 12 ints --
+ * conv : bk, block_n, num_m_tiles, num_n_tiles, num_stages, epi_bufs, b_resident, use_tma_store, smem, grid, epi_cw, k_iters
+ * wgrad: chunk_a, chunk_b, block_c, c_tiles, T, mt, pix, groups, splits, num_stages, smem, grid */
+int xemo_debug_conv_plan(int N, int H, int W, int Cin, int Kout, int R, int S, int sh, int sw, int pt, int pb, int pl, int pr,
+                         int num_sms, int* out);
+int xemo_debug_wgrad_plan(int N, int H, int W, int Cin, int ldy, int Kout, int R, int S, int sh, int sw, int pt, int pb, int pl,
+                          int pr, int num_sms, int* out);
 /* bias gradient: out[c] = scale * sum_p dy[p][c] */
 int xemo_op_colsum(xemo_ctx* ctx, const void* dy16, size_t P, int ld, int C, float scale, float* out);
 

@@ -51,7 +51,14 @@ constexpr int kSmemBudget = 227 * 1024;
 inline int conv_pick_bk(int cin) { return (cin % 64 == 0) ? 64 : (cin % 32 == 0) ? 32 : (cin % 16 == 0) ? 16 : 0; }
 
 // Pick the N tile: a multiple of 16 dividing Kout, <= 256, minimising (waves x per-tile cost).
-inline int conv_pick_block_n(int M, int Kout, int k_steps16, int num_sms) {
+// Per-tile cost = max(MMA issue, operand fetch, epilogue): the fetch term is what the profiler showed to bind the
+// K-heavy layers (profiles/ncu/r01_epilogue_and_issue_studies.txt): TMA fills shared memory at ~60 B/clk/SM with
+// 128-byte rows (BK = 64) and proportionally less with 64- / 32-byte rows, and every tile re-fetches its
+// block_n x K filter slice unless the filter is resident (one N tile, <= 112 KB).  The term only enters when there are
+// at least four full waves of M tiles (wave quantisation does not blur the comparison there; smaller problems keep the
+// measured fetch-blind choice).  XEMO_CONV_COSTMODEL=0 restores the fetch-blind model everywhere.
+inline int conv_pick_block_n(int M, int Kout, int k_steps16, int num_sms, int bk = 64, int k_iters = 0) {
+  static const bool fetch_aware = [] { const char* e = getenv("XEMO_CONV_COSTMODEL"); return !(e && e[0] == '0'); }();
   int best = 0;
   double best_cost = 1e300;
   const int m_tiles = (M + kConvBlockM - 1) / kConvBlockM;
@@ -63,7 +70,15 @@ inline int conv_pick_block_n(int M, int Kout, int k_steps16, int num_sms) {
     // epilogue is ~bn*6 cycles per tile but overlaps the next tile's main loop.
     const double mainloop = double(k_steps16) * (bn > 96 ? bn * 0.5 : 48.0);
     const double epi = bn * 6.0 + 300.0;
-    const double tile_cost = (mainloop > epi ? mainloop : epi) + 200.0;
+    double fetch = 0.0;
+    if (fetch_aware && k_iters > 0 && m_tiles >= 4 * num_sms) {
+      const bool resident = (bn == Kout) && (long(k_iters) * conv_b_slot_bytes(bk, bn) <= 112 * 1024) && tiles >= num_sms;
+      const double bytes = double(k_iters) * (kConvBlockM * bk * 2 + (resident ? 0 : bn * bk * 2));
+      fetch = bytes / (60.0 * bk / 64.0);
+    }
+    double tile_cost = mainloop > epi ? mainloop : epi;
+    if (fetch > tile_cost) tile_cost = fetch;
+    tile_cost += 200.0;
     const double cost = waves * tile_cost;
     if (cost < best_cost * 0.999) { best_cost = cost; best = bn; }
   }
@@ -71,7 +86,7 @@ inline int conv_pick_block_n(int M, int Kout, int k_steps16, int num_sms) {
 }
 
 inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, const __half* w,
-                            const ConvEpilogue& e, int num_sms, int force_block_n = 0) {
+                            const ConvEpilogue& e, int num_sms, int force_block_n = 0, bool encode_maps = true) {
   const int bk = conv_pick_bk(g.Cin);
   if (!bk) { fprintf(stderr, "[xemo] conv: Cin=%d must be a multiple of 16\n", g.Cin); return false; }
   if (g.Kout % 16) { fprintf(stderr, "[xemo] conv: Kout=%d must be a multiple of 16\n", g.Kout); return false; }
@@ -85,7 +100,7 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   p.stride_h = g.sh; p.stride_w = g.sw; p.pad_t = g.pt; p.pad_l = g.pl;
   p.kc_blocks = g.Cin / bk;
   const int k_steps16 = g.R * g.S * g.Cin / 16;
-  p.block_n = force_block_n ? force_block_n : conv_pick_block_n(p.M, g.Kout, k_steps16, num_sms);
+  p.block_n = force_block_n ? force_block_n : conv_pick_block_n(p.M, g.Kout, k_steps16, num_sms, bk, g.R * g.S * p.kc_blocks);
   if (p.block_n <= 0 || g.Kout % p.block_n) return false;
   p.num_m_tiles = (p.M + kConvBlockM - 1) / kConvBlockM;
   p.num_n_tiles = g.Kout / p.block_n;
@@ -121,6 +136,7 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   plan->smem = stages * stage_bytes + fixed_bytes + epi_bytes + 1024 + kEpiGroups * 2 * 256 * 4 + (2 * stages + 9) * 8 + 16;
   plan->grid = tiles < num_sms ? tiles : num_sms;
   plan->flops = 2.0 * double(p.M) * g.Kout * g.R * g.S * g.Cin;
+  if (!encode_maps) return true;
 
   const CUtensorMapSwizzle swz = swizzle_for_bytes(bk * 2);
   // upper corner: pad_upper - (filter - 1); the effective pad_upper only matters through the number of
@@ -190,7 +206,7 @@ inline int pick_chunk(int n) { return (n % 64 == 0) ? 64 : (n % 32 == 0) ? 32 : 
 // x: NHWC fp16 [N][H][W][Cin] (Cin % 16 == 0); dy: [P][ldy] fp16 (ldy % 16 == 0, Kout <= ldy);
 // dF: [Kout][R][S][Cin] fp32, accumulated into.
 inline bool conv_wgrad_plan(WgradPlan* plan, const ConvGeom& g, const __half* x, const __half* dy, int ldy, float* dF,
-                            float scale, int num_sms) {
+                            float scale, int num_sms, bool encode_maps = true) {
   if (g.Cin % 16 || ldy % 16 || g.Kout > ldy) {
     fprintf(stderr, "[xemo] wgrad: Cin=%d / ldy=%d must be multiples of 16 and Kout=%d <= ldy\n", g.Cin, ldy, g.Kout);
     return false;
@@ -272,6 +288,7 @@ inline bool conv_wgrad_plan(WgradPlan* plan, const ConvGeom& g, const __half* x,
   const int items = p.m_items * p.groups * p.splits;
   plan->grid = items < num_sms ? items : num_sms;
   plan->flops = 2.0 * double(p.P) * g.Kout * g.R * g.S * g.Cin;
+  if (!encode_maps) return true;
   const int upper_w = (OW - 1) * g.sw - g.pl - (g.W - 1);
   const int upper_h = (OH - 1) * g.sh - g.pt - (g.H - 1);
   if (!make_tmap_im2col_nhwc_f16(&plan->tmX, x, g.N, g.H, g.W, g.Cin, -g.pl, -g.pt, upper_w, upper_h, g.sw, g.sh,

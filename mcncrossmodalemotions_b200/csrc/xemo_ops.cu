@@ -262,6 +262,38 @@ extern "C" int xemo_op_conv_fwd(xemo_ctx* ctx, const void* x16, int N, int H, in
   return run_fprop(ctx, g, static_cast<const __half*>(x16), static_cast<const __half*>(w16), e);
 }
 
+// Shape planning without a device (no tensor-map encoding): what tile shape / pipeline depth / work split the host code
+// picks for a convolution.  out[] (12 ints):
+//   fprop: bk, block_n, num_m_tiles, num_n_tiles, num_stages, epi_bufs, b_resident, use_tma_store, smem bytes, grid, epi_cw, k_iters
+//   wgrad: chunk_a, chunk_b, block_c, c_tiles, T, mt, pix, groups, splits, num_stages, smem bytes, grid
+extern "C" int xemo_debug_conv_plan(int N, int H, int W, int Cin, int Kout, int R, int S, int sh, int sw, int pt, int pb, int pl,
+                                    int pr, int num_sms, int* out) {
+  if (!out) return XEMO_ERR_INVALID;
+  ConvGeom g{N, H, W, Cin, Kout, R, S, sh, sw, pt, pb, pl, pr};
+  ConvEpilogue e;
+  e.out = reinterpret_cast<__half*>(uintptr_t(16));   // never dereferenced: only "an fp16 output exists"
+  e.ldc = Kout;
+  ConvPlan plan;
+  if (!conv_fprop_plan(&plan, g, nullptr, nullptr, e, num_sms, 0, false)) return XEMO_ERR_INVALID;
+  const ConvFpropParams& p = plan.p;
+  const int v[12] = {plan.bk, p.block_n, p.num_m_tiles, p.num_n_tiles, p.num_stages, p.epi_bufs, p.b_resident, p.use_tma_store,
+                     plan.smem, plan.grid, p.epi_cw, p.R * p.S * p.kc_blocks};
+  for (int i = 0; i < 12; ++i) out[i] = v[i];
+  return XEMO_OK;
+}
+
+extern "C" int xemo_debug_wgrad_plan(int N, int H, int W, int Cin, int ldy, int Kout, int R, int S, int sh, int sw, int pt, int pb,
+                                     int pl, int pr, int num_sms, int* out) {
+  if (!out) return XEMO_ERR_INVALID;
+  ConvGeom g{N, H, W, Cin, Kout, R, S, sh, sw, pt, pb, pl, pr};
+  WgradPlan plan;
+  if (!conv_wgrad_plan(&plan, g, nullptr, nullptr, ldy, nullptr, 1.f, num_sms, false)) return XEMO_ERR_INVALID;
+  const ConvWgradParams& p = plan.p;
+  const int v[12] = {p.chunk_a, p.chunk_b, p.block_c, p.c_tiles, p.T, p.mt, p.pix, p.groups, p.splits, p.num_stages, plan.smem, plan.grid};
+  for (int i = 0; i < 12; ++i) out[i] = v[i];
+  return XEMO_OK;
+}
+
 // parity classes of the data gradient (see hbm_kernels_extra.cuh)
 static int dgrad_classes(int Cin, int Kout, int R, int S, int sh, int sw, int pt, int pl, DgradPackParams* p) {
   p->num_classes = 0;

@@ -288,3 +288,55 @@ def test_bench_clock_sampler_windows_rows_by_time(tmp_path, monkeypatch):
     out = c.stop(t0, t1)
     assert out["samples"] >= 2 and out["sm_mhz"] == 1900.0 and out["sm_max_mhz"] == 1965.0
     assert out["reasons"] == ["sw_power_cap"]
+
+
+def _student_teacher_conv_shapes(n):
+    """(name, N, H, W, Cin, Kout, R, S, sh, sw, pt, pb, pl, pr) of every convolution the fused programs launch."""
+    shapes = [("t.conv1", n, 224, 56, 64, 128, 7, 1, 2, 1, 3, 3, 0, 0)]
+    cin, hw = 64, 56
+    for si, (blocks, mid, cout, stride) in enumerate([(3, 64, 256, 1), (4, 128, 512, 2), (6, 256, 1024, 2), (3, 512, 2048, 2)]):
+        for bi in range(blocks):
+            st = stride if bi == 0 else 1
+            ohw = hw // st
+            pre = "t.s%db%d." % (si + 2, bi + 1)
+            shapes.append((pre + "c1", n, hw, hw, cin, mid, 1, 1, st, st, 0, 0, 0, 0))
+            shapes.append((pre + "c2", n, ohw, ohw, mid, mid, 3, 3, 1, 1, 1, 1, 1, 1))
+            if bi == 0:
+                shapes.append((pre + "proj", n, hw, hw, cin, cout, 1, 1, st, st, 0, 0, 0, 0))
+            shapes.append((pre + "c3", n, ohw, ohw, mid, cout, 1, 1, 1, 1, 0, 0, 0, 0))
+            cin, hw = cout, ohw
+    shapes += [("s.conv1", n, 257, 74, 32, 192, 4, 1, 1, 1, 0, 0, 0, 0), ("s.conv1u", n, 257, 148, 16, 96, 4, 1, 1, 1, 0, 0, 0, 0),
+               ("s.conv2", n, 126, 73, 128, 256, 5, 5, 2, 2, 1, 1, 1, 1), ("s.conv2u", n, 126, 73, 96, 256, 5, 5, 2, 2, 1, 1, 1, 1),
+               ("s.conv3", n, 30, 17, 256, 384, 3, 3, 1, 1, 1, 1, 1, 1), ("s.conv4", n, 30, 17, 384, 256, 3, 3, 1, 1, 1, 1, 1, 1),
+               ("s.conv5", n, 30, 17, 256, 256, 3, 3, 1, 1, 1, 1, 1, 1), ("s.fc6", n, 9, 8, 256, 4096, 9, 1, 1, 1, 0, 0, 0, 0),
+               ("s.fc7", n, 1, 1, 4096, 1024, 1, 1, 1, 1, 0, 0, 0, 0), ("s.fc8", n, 1, 1, 1024, 16, 1, 1, 1, 1, 0, 0, 0, 0)]
+    return shapes
+
+
+@pytest.mark.parametrize("n", [1, 8, 64, 256, 1024])
+def test_conv_plans_respect_the_hardware_budgets(n):
+    """Host-side planning of the tcgen05 kernels (no device needed): every layer of the three networks gets a tile
+    shape that fits 227 KB of shared memory and 512 TMEM columns, at every batch size the sweeps use."""
+    import ctypes as C
+
+    from mcncrossmodalemotions_b200 import _lib
+
+    lib = _lib.load_library()
+    out = (C.c_int * 12)()
+    for name, *g in _student_teacher_conv_shapes(n):
+        N, H, W, Cin, Kout, R, S, sh, sw, pt, pb, pl, pr = g
+        assert lib.xemo_debug_conv_plan(*g, 148, out) == 0, name
+        bk, bn, m_tiles, n_tiles, stages, epib, bres, tma_store, smem, grid, cw, k_iters = list(out)
+        assert bk in (16, 32, 64) and Cin % bk == 0, name
+        assert 16 <= bn <= 256 and Kout % bn == 0 and n_tiles == Kout // bn, name
+        assert stages >= 2 and epib in (1, 2) and smem <= 227 * 1024, (name, smem)
+        assert 1 <= grid <= 148 and cw in (16, 32, 64) and bn % cw == 0, name
+        assert not bres or (n_tiles == 1 and k_iters * bn * bk * 2 <= 112 * 1024), name
+        assert k_iters == R * S * (Cin // bk), name
+        if name.startswith("s."):   # the student's layers also run the filter-gradient kernel
+            assert lib.xemo_debug_wgrad_plan(N, H, W, Cin, Kout, Kout, R, S, sh, sw, pt, pb, pl, pr, 148, out) == 0, name
+            chunk_a, chunk_b, block_c, c_tiles, T, mt, pix, groups, splits, wstages, wsmem, wgrid = list(out)
+            assert block_c * c_tiles == Cin and block_c % chunk_b == 0 and chunk_b in (16, 32, 64), name
+            assert mt in (1, 2) and mt * T * block_c <= 512, (name, mt, T, block_c)       # TMEM columns
+            assert pix in (32, 64, 128) and wstages >= 2 and wsmem <= 227 * 1024, (name, wsmem)
+            assert groups * T >= R * S * c_tiles and splits >= 1 and 1 <= wgrid <= 148, name

@@ -177,3 +177,21 @@ def test_stem_backward_by_linearity_matches_oracle_chain(case):
     dW7 = np.stack([dW.reshape(K, 4, 2, 8)[:, r // 2, r % 2, :7] for r in range(7)], 0).transpose(0, 2, 1)[:, :, None, :]
     assert np.abs(dW7 - df_ref).max() < 1e-9 * max(1.0, np.abs(df_ref).max())   # the same comparison in fp64
     assert np.abs(db_ref).max() < 1e-8        # the bias ahead of train-mode BN has a zero gradient
+
+
+def test_pixel_pair_form_is_the_same_convolution(case):
+    """programs.pair_filter: the [N][HP][OW/2][32] view of the s2d tensor convolved with the block-diagonal
+    [2K][4][1][32] filter, read back as [N][OH][OW][K], equals the 16-channel form (same bytes in memory)."""
+    from mcncrossmodalemotions_b200.programs import pair_filter
+
+    K, N = case["K"], case["N"]
+    X, OH, OW = s2d(np.random.default_rng(3).standard_normal((40, 40, 1, N)))    # an even conv1 output width
+    assert OW % 2 == 0
+    w = student_conv1_to_s2d(case["f"]).astype(np.float64)                      # [K][4][1][16]
+    y = patches(X, OH) @ w.reshape(K, 64).T                                       # [N*OH*OW][K]
+    Xp = X.reshape(N, X.shape[1], OW // 2, 32)
+    xs2 = np.concatenate([Xp[:, j : j + OH] for j in range(4)], axis=-1).reshape(N * OH * (OW // 2), 128)
+    w2 = pair_filter(w)                                                           # [2K][4][1][32]
+    assert w2.shape == (2 * K, 4, 1, 32)
+    y2 = xs2 @ w2.reshape(2 * K, 128).T                                           # [N*OH*OW/2][2K]
+    assert np.abs(y2.reshape(N * OH * OW, K) - y).max() < 1e-12
