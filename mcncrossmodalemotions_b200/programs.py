@@ -316,12 +316,19 @@ class StudentProgram(_Base):
     AUDIO = dict(fs=16000, Tw=25, Ts=10, alpha=0.97)   # emoVoxCeleb/run_distillation.m:109-117
 
     def __init__(self, params, batch, width=300, device=0, stream=None, use_graph=True, grad_scale=1024.0, num_classes=8,
-                 temperature=2.0, ctx=None, audio_input="spectrogram", stem_algebra=None, stem_pairs=None):
+                 temperature=2.0, ctx=None, audio_input="spectrogram", stem_algebra=None, stem_pairs=None,
+                 loss_type="hot-cross-ent"):
         """audio_input 'spectrogram': 512 x W x 1 x N row-normalised spectrograms (what getBatchEmoVoxCeleb hands to
         dag.eval); 'wav': N x L waveform crops of L = (0.01 W + 0.024) * fs samples -- runSpec + the row normalisation
         (getBatchEmoVoxCeleb.m:162-169) then run on the device ahead of the graph."""
+        # emoVoxZoo.m:137-157: 'hot-cross-ent' = SoftmaxCELoss(temperature, logitTargets) on {prediction, logitTarget};
+        # 'softmaxlog' = dagnn.Loss('softmaxlog') on {prediction, maxLabel}, i.e. the same cross-entropy against a one-hot
+        # distribution at T = 1 (the fused kernel's logit_targets = 0 mode).  'euclidean' / 'huber' are not on the hot path.
+        if loss_type not in ("hot-cross-ent", "softmaxlog"):
+            raise NotImplementedError("loss type %r is not on the hot path (hot-cross-ent, softmaxlog)" % (loss_type,))
         super().__init__(device, stream, ctx)
         self.audio_input = audio_input
+        self.loss_type = loss_type
         a = self.AUDIO
         self.Nw, self.Ns = int(round(1e-3 * a["Tw"] * a["fs"])), int(round(1e-3 * a["Ts"] * a["fs"]))
         self.wav_len = (width - 1) * self.Ns + self.Nw + (a["fs"] * 24 // 1000 - self.Nw + self.Ns)  # = (0.01 W + 0.024) fs
@@ -591,8 +598,9 @@ class StudentProgram(_Base):
             ctx.memset(_p(self.grad), 0, self.nparam * 4)
             ctx.memset(_p(A["fc8:draw"]), 0, A["fc8:draw"].numel() * 2)
             ctx.memset(_p(A["scalars"]), 0, 8)  # objective / classerror of THIS batch (class_stats keep accumulating)
-            ctx.op_softmaxce(_p(A["fc8:raw"]), last["kp"], _p(A["target"]), self.K, None, N, self.K, self.T, 1, 1.0, gs,
-                             _p(A["fc8:draw"]), _p(A["scalars"]), _p(A["class_stats"]), _p(A["max_label"]))
+            soft = self.loss_type == "hot-cross-ent"
+            ctx.op_softmaxce(_p(A["fc8:raw"]), last["kp"], _p(A["target"]), self.K, None, N, self.K, self.T if soft else 1.0,
+                             1 if soft else 0, 1.0, gs, _p(A["fc8:draw"]), _p(A["scalars"]), _p(A["class_stats"]), _p(A["max_label"]))
         for i in range(hi - 1, lo - 1, -1):
             L = self.layers[i]
             n = L["name"]
@@ -729,7 +737,14 @@ class StudentProgram(_Base):
         with torch.cuda.stream(self.stream):
             self.a[key].view(-1).copy_(spec.reshape(-1), non_blocking=True)
             if target is not None:
-                if isinstance(target, np.ndarray):
+                if isinstance(target, np.ndarray) and self.loss_type == "softmaxlog":
+                    # maxLabel (1 x 1 x 1 x N, 1-based; getBatchEmoVoxCeleb.m:32) -> one-hot rows
+                    lab = np.asarray(target).reshape(-1).astype(np.int64)
+                    assert lab.size == self.N and lab.min() >= 1 and lab.max() <= self.K, "maxLabel must hold N labels in 1..K"
+                    onehot = np.zeros((self.N, self.K), np.float32)
+                    onehot[np.arange(self.N), lab - 1] = 1.0
+                    target = torch.from_numpy(onehot)
+                elif isinstance(target, np.ndarray):
                     target = torch.from_numpy(np.ascontiguousarray(target.astype(np.float32).reshape(self.K, self.N).T))
                 self.a["target"].copy_(target.reshape(self.N, self.K), non_blocking=True)
 

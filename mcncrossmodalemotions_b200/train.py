@@ -67,7 +67,7 @@ def load_checkpoint(exp_dir, epoch):
 
 def cnn_train_dag(params, imdb, get_batch, *, learning_rate, batch_size=64, num_epochs=300, train=None, val=None, cont=True,
                   exp_dir=None, width=400, epoch_size=None, momentum=0.9, weight_decay=5e-4, device=0, world=1, rank=0, seed=0,
-                  max_steps_per_epoch=None, log=print):
+                  max_steps_per_epoch=None, log=print, loss_type="hot-cross-ent"):
     """Train the student.  `params`: zoo parameter dict; `imdb`: anything `get_batch(imdb, indices)` understands;
     get_batch returns the dict of batch.get_batch ('data', 'logitTarget').  Returns (params, info)."""
     train = np.asarray(train if train is not None else [], np.int64)
@@ -83,7 +83,8 @@ def cnn_train_dag(params, imdb, get_batch, *, learning_rate, batch_size=64, num_
                 params, mom, info = load_checkpoint(exp_dir, start)
                 log("resuming from epoch %d" % start)
     per_rank = batch_size // world
-    prog = StudentProgram(params, per_rank, width, device=device)
+    prog = StudentProgram(params, per_rank, width, device=device, loss_type=loss_type)
+    tkey = "maxLabel" if loss_type == "softmaxlog" else "logitTarget"   # the loss layer's second input (emoVoxZoo.m:137-157)
     if mom is not None:
         prog.load_momentum(mom)
     allreduce = GradientAllReducer() if world > 1 else None
@@ -102,7 +103,7 @@ def cnn_train_dag(params, imdb, get_batch, *, learning_rate, batch_size=64, num_
         for it in range(steps):
             idx = order[it * batch_size : (it + 1) * batch_size][rank::world]   # labindex:numlabs:end
             inputs = get_batch(imdb, idx)
-            prog.train_step(inputs["data"], inputs["logitTarget"], allreduce)
+            prog.train_step(inputs["data"], inputs[tkey], allreduce)
             m = prog.metrics()   # objective / classerror of this batch; class counters accumulate
             obj += m["objective"]; err += m["classerror"]; seen += len(idx)
         m = prog.metrics()
@@ -111,7 +112,7 @@ def cnn_train_dag(params, imdb, get_batch, *, learning_rate, batch_size=64, num_
         info["train"].append(tr)
         vs = None
         if len(val):
-            vs = evaluate(prog, imdb, get_batch, val, per_rank)
+            vs = evaluate(prog, imdb, get_batch, val, per_rank, tkey)
             info["val"].append(vs)
         log("epoch %d lr %.3g train obj %.4f err %.3f%s" % (epoch + 1, lr, tr["objective"], tr["classerror"],
                                                           "" if vs is None else " | val err %.3f" % vs["classerror"]))
@@ -120,14 +121,17 @@ def cnn_train_dag(params, imdb, get_batch, *, learning_rate, batch_size=64, num_
     return prog.export_params(), info
 
 
-def evaluate(prog, imdb, get_batch, indices, batch):
+def evaluate(prog, imdb, get_batch, indices, batch, tkey="logitTarget"):
     """Validation pass: forward in test mode, class error against the arg-max teacher label."""
     wrong = total = 0
     for it in range(len(indices) // batch):
         idx = indices[it * batch : (it + 1) * batch]
         inputs = get_batch(imdb, idx)
         pred = prog.forward(inputs["data"], "test")
-        label = inputs["logitTarget"].reshape(pred.shape[1], -1).argmax(axis=0)
+        if tkey == "maxLabel":
+            label = np.asarray(inputs["maxLabel"]).reshape(-1).astype(np.int64) - 1
+        else:
+            label = inputs["logitTarget"].reshape(pred.shape[1], -1).argmax(axis=0)
         wrong += int((pred.argmax(axis=1) != label).sum())
         total += len(idx)
     return {"classerror": wrong / max(total, 1), "num": total}
@@ -156,8 +160,8 @@ def run_distillation(imdb, get_batch, root="data/xEmo18", **overrides):
     opts.update(overrides)
     opts["miniEpochRatio"] = extra.get("miniEpochRatio", 0.05 * len(opts["gpus"]))
     opts["learningRate"] = extra.get("learningRate", learning_rate_schedule(opts["numEpochs"]))
-    if opts["lossType"] != "hot-cross-ent":
-        raise NotImplementedError("only the 'hot-cross-ent' distillation loss is on the hot path")
+    if opts["lossType"] not in ("hot-cross-ent", "softmaxlog"):
+        raise NotImplementedError("loss type %r is not on the hot path (hot-cross-ent, softmaxlog)" % (opts["lossType"],))
     exp_dir = os.path.join(root, exp_dir_name(opts["teacher"], opts["student"], opts["lossType"], opts["numSeconds"],
                                               opts["numPredEmotions"], opts["logitAggregator"], opts["temperature"], opts["fromScratch"]))
     os.makedirs(exp_dir, exist_ok=True)
@@ -170,4 +174,4 @@ def run_distillation(imdb, get_batch, root="data/xEmo18", **overrides):
     return cnn_train_dag(net.params, imdb, get_batch, learning_rate=opts["learningRate"], batch_size=opts["batchSize"],
                          num_epochs=opts["numEpochs"], train=train, val=val, cont=opts["cont"], exp_dir=exp_dir,
                          width=100 * opts["numSeconds"], epoch_size=int(len(train) * opts["miniEpochRatio"]), device=opts["gpus"][0],
-                         max_steps_per_epoch=extra.get("max_steps_per_epoch"))
+                         max_steps_per_epoch=extra.get("max_steps_per_epoch"), loss_type=opts["lossType"])

@@ -157,6 +157,34 @@ def test_stem_linearity_path_agrees_with_generic_path(nets):
     assert np.abs(g1["conv1b"]).max() == 0
 
 
+def test_student_softmaxlog_loss_type(nets):
+    """lossType 'softmaxlog' (emoVoxZoo.m:147-149: dagnn.Loss('softmaxlog') on {prediction, maxLabel}) through the fused
+    loss kernel's one-hot / T = 1 mode: objective, class error and the fc8 bias gradient against the oracle's vl_nnloss
+    applied to the step's own predictions."""
+    import torch
+
+    from mcncrossmodalemotions_b200.programs import StudentProgram
+    from oracle import mcn_ops as M
+
+    n, width = 8, 100
+    labels = np.array([1, 1, 1, 2, 2, 3, 5, 8]).reshape(1, 1, 1, n)
+    prog = StudentProgram(nets.student_init(), n, width, use_graph=False, loss_type="softmaxlog")
+    prog.reset_metrics()
+    prog.set_input(nets.synth_spectrograms(n, width), labels)
+    prog.grad_step()
+    m, g = prog.metrics(), prog.export_grads()
+    with torch.cuda.stream(prog.stream):
+        pred = prog.a["pred32"][:, :8].cpu().numpy()
+    prog.sync()
+    x4 = pred.T.reshape(1, 1, 8, n).astype(np.float64)
+    obj = M.vl_nnloss(x4, labels, loss="softmaxlog")
+    assert abs(m["objective"] - obj) <= 1e-3 * abs(obj)            # pred32 is fp32, the loss kernel reads the fp16 copy
+    assert abs(m["classerror"] - M.vl_nnloss(x4, labels, loss="classerror")) <= 1
+    assert np.array_equal(m["count"], np.bincount(labels.ravel() - 1, minlength=8))
+    dx = M.vl_nnloss(x4, labels, 1.0, loss="softmaxlog")             # softmax(x) - onehot
+    assert rel_err(g["fc8b"], dx.sum(axis=(0, 1, 3))) < 5e-3
+
+
 def test_student_bias_before_train_bn_has_zero_gradient(nets):
     from mcncrossmodalemotions_b200.programs import StudentProgram
 

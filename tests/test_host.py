@@ -340,3 +340,13 @@ def test_conv_plans_respect_the_hardware_budgets(n):
             assert mt in (1, 2) and mt * T * block_c <= 512, (name, mt, T, block_c)       # TMEM columns
             assert pix in (32, 64, 128) and wstages >= 2 and wsmem <= 227 * 1024, (name, wsmem)
             assert groups * T >= R * S * c_tiles and splits >= 1 and 1 <= wgrid <= 148, name
+
+
+def test_unsupported_loss_types_fail_loudly_before_touching_the_device():
+    """emoVoxZoo.m:137-150 also offers 'euclidean' and 'huber'; they are not on the hot path and must not silently
+    train with another loss."""
+    from mcncrossmodalemotions_b200.programs import StudentProgram
+
+    for lt in ("euclidean", "huber", "nonsense"):
+        with pytest.raises(NotImplementedError):
+            StudentProgram({}, 4, 100, loss_type=lt)
