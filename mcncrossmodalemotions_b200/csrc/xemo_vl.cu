@@ -202,7 +202,7 @@ extern "C" int xemo_vl_nnpool(xemo_ctx* ctx, const xemo_array* x, const int pool
   XEMO_REQUIRE(ctx, xemo_out_size(H, W, pool[0], pool[1], pad, stride, &OH64, &OW64) == 0, "vl_nnpool: window larger than input");
   XEMO_REQUIRE(ctx, pool[0] * pool[1] <= 255, "vl_nnpool: window too large for uint8 indices");
   const int OH = int(OH64), OW = int(OW64), Cp = pad_to(C, 8);
-  PoolGeom g{N, H, W, Cp, pool[0], pool[1], stride[0], stride[1], pad[0], pad[2], OH, OW};
+  PoolGeom g{N, H, W, Cp, pool[0], pool[1], stride[0], stride[1], pad[0], pad[2], OH, OW, Cp};
   Arena ar(ctx);
   const float* xd = static_cast<const float*>(ar.in(x->data, numel(x) * 4));
   float* xn = ar.alloc_n<float>(size_t(N) * H * W * Cp);
