@@ -4,7 +4,7 @@ CPU oracle, through libxemo.so.
 Tolerances.  north_star: logits within 1e-3 relative (max|a-b| <= 1e-3 * max|ref|) of the fp32/fp64
 CPU path; pooling indices / class-error counts exact.  Convolution operands are fp16 (fp32
 accumulation), so a single contraction is good to ~3e-4 and a 50-layer teacher to ~7e-4 (measured;
-tools/precision_emulation.py reproduces it on the CPU).  Train-mode quantities that are *discontinuous*
+tests/tools/precision_emulation.py reproduces it on the CPU).  Train-mode quantities that are *discontinuous*
 in the activations (ReLU masks under batch-statistics BN) cannot be held to 1e-3 by any 16-bit-operand
 pipeline: they are checked (a) tightly against the oracle's fp16 number-format model
 (oracle.nets.Fp16ModelOps) and (b) against the exact oracle through continuous quantities (objective,
@@ -135,7 +135,7 @@ def test_stem_linearity_path_agrees_with_generic_path(nets):
     """Same step through both formulations of the first layer.  The batch statistics agree to fp16 storage rounding of
     the conv1 activation; the gradients differ by what ANY two fp16 pipelines differ by (ReLU-mask flips, DESIGN.md
     section 5: measured 0.08-0.09 relative L2 between the two paths, each 0.12-0.14 from the exact oracle and 0.08
-    from the fp16 model -- tools/stem_diag.py), so they are held to the same 0.15 as the oracle comparison."""
+    from the fp16 model -- tests/tools/stem_diag.py), so they are held to the same 0.15 as the oracle comparison."""
     from mcncrossmodalemotions_b200.programs import StudentProgram
 
     n, width = 8, 100

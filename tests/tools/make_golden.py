@@ -5,13 +5,13 @@ The reference repository has no golden vectors, tests or runnable arithmetic for
 parity unpinned), so these are *oracle-generated* fixtures, not reference outputs.  Inputs and weights are seeded
 (oracle/nets.py synth_* / *_init), so only the small outputs are stored.
 
-    python tools/make_golden.py"""
+    python tests/tools/make_golden.py"""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import mcn_ops as M  # noqa: E402
 from oracle import nets  # noqa: E402

@@ -1,6 +1,6 @@
 """GPU-box parity report: fused device programs (through the C ABI) vs the CPU oracle, per tensor.
 
-    python tools/parity_report.py [--teacher-batch 4] [--student-batch 4] > gpurun_out/parity.txt
+    python tests/tools/parity_report.py [--teacher-batch 4] [--student-batch 4] > gpurun_out/parity.txt
 
 The oracle is the checker here (test infrastructure); nothing in the product imports it."""
 import argparse
@@ -11,7 +11,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 from oracle import nets  # noqa: E402
 

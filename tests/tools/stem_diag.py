@@ -1,11 +1,11 @@
 """Distance of the first-layer gradients to the oracle for both formulations of the student stem
-(generic per-layer kernels vs. csrc/stem_kernels.cuh).   python tools/stem_diag.py [n] [width]"""
+(generic per-layer kernels vs. csrc/stem_kernels.cuh).   python tests/tools/stem_diag.py [n] [width]"""
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import nets  # noqa: E402  (diagnostic tool: the oracle is the checker)
 from mcncrossmodalemotions_b200.programs import StudentProgram  # noqa: E402
 

@@ -7,7 +7,7 @@ echo "pytest exit=$?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 timeout 300 python tools/op_breakdown.py 256 > gpurun_out/op_breakdown_new.txt 2>&1; echo "op_new exit=$?"
 tail -32 gpurun_out/op_breakdown_new.txt
-timeout 300 python tools/stem_diag.py 16 300 > gpurun_out/stem_diag.txt 2>&1; timeout 300 python tools/stem_diag.py 8 100 >> gpurun_out/stem_diag.txt 2>&1
+timeout 300 python tests/tools/stem_diag.py 16 300 > gpurun_out/stem_diag.txt 2>&1; timeout 300 python tests/tools/stem_diag.py 8 100 >> gpurun_out/stem_diag.txt 2>&1
 cat gpurun_out/stem_diag.txt
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit=$?"
 cat gpurun_out/bench_n1.json
