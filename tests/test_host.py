@@ -46,6 +46,11 @@ def test_product_never_imports_the_oracle():
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("the oracle", ""), fn
+    # the measurement / profiling helpers under tools/ are product-side too: scripts that need the checker live in tests/tools/
+    for fn in os.listdir(os.path.join(ROOT, "tools")):
+        if fn.endswith((".py", ".sh")):
+            txt = open(os.path.join(ROOT, "tools", fn)).read()
+            assert "import oracle" not in txt and "from oracle" not in txt, fn
 
 
 def test_out_size_rule():
