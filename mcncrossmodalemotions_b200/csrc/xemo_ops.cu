@@ -646,7 +646,10 @@ extern "C" int xemo_op_se_squeeze(xemo_ctx* ctx, const void* u16, int N, int HW,
   const int C8 = C / 8;
   int lx = 1;
   while (lx < 32 && lx * 2 <= C8) lx *= 2;   // min(32, largest power of two <= C/8)
-  dim3 grid((C8 + lx - 1) / lx, N), block(lx, 1024 / lx);
+  // pixel-stride lanes: 1024 / lx for the large maps; the 7 x 7 maps (49 pixels) would leave half of a 32-lane stride
+  // idle and pay a 1024-thread barrier for two loads per thread (1.4 TB/s in the launch list): 8 lanes there
+  const int ly = HW < 128 ? 8 : 1024 / lx;
+  dim3 grid((C8 + lx - 1) / lx, N), block(lx, ly);
   se_squeeze_kernel<__half><<<grid, block, 0, ctx->stream>>>(static_cast<const __half*>(u16), HW, C, s);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
