@@ -56,9 +56,12 @@ inline int conv_pick_bk(int cin) { return (cin % 64 == 0) ? 64 : (cin % 32 == 0)
 // 128-byte rows (BK = 64) and proportionally less with 64- / 32-byte rows, and every tile re-fetches its
 // block_n x K filter slice unless the filter is resident (one N tile, <= 112 KB).  The term only enters when there are
 // at least four full waves of M tiles (wave quantisation does not blur the comparison there; smaller problems keep the
-// measured fetch-blind choice).  XEMO_CONV_COSTMODEL=0 restores the fetch-blind model everywhere.
+// measured fetch-blind choice).  XEMO_CONV_COSTMODEL=0 restores the fetch-blind model everywhere, =2 applies the fetch
+// term to every problem size (fc6's data gradient and the 7 x 7 teacher layers then move to 256-wide tiles: to be measured).
 inline int conv_pick_block_n(int M, int Kout, int k_steps16, int num_sms, int bk = 64, int k_iters = 0) {
-  static const bool fetch_aware = [] { const char* e = getenv("XEMO_CONV_COSTMODEL"); return !(e && e[0] == '0'); }();
+  static const int fetch_mode = [] { const char* e = getenv("XEMO_CONV_COSTMODEL"); return e ? (e[0] - '0') : 1; }();
+  const bool fetch_aware = fetch_mode != 0;
+  const int min_m_tiles = fetch_mode == 2 ? 0 : 4 * num_sms;   // 2 (experimental, unmeasured): the fetch term for every size
   int best = 0;
   double best_cost = 1e300;
   const int m_tiles = (M + kConvBlockM - 1) / kConvBlockM;
@@ -71,7 +74,7 @@ inline int conv_pick_block_n(int M, int Kout, int k_steps16, int num_sms, int bk
     const double mainloop = double(k_steps16) * (bn > 96 ? bn * 0.5 : 48.0);
     const double epi = bn * 6.0 + 300.0;
     double fetch = 0.0;
-    if (fetch_aware && k_iters > 0 && m_tiles >= 4 * num_sms) {
+    if (fetch_aware && k_iters > 0 && m_tiles >= min_m_tiles) {
       const bool resident = (bn == Kout) && (long(k_iters) * conv_b_slot_bytes(bk, bn) <= 112 * 1024) && tiles >= num_sms;
       const double bytes = double(k_iters) * (kConvBlockM * bk * 2 + (resident ? 0 : bn * bk * 2));
       fetch = bytes / (60.0 * bk / 64.0);

@@ -351,6 +351,10 @@ class StudentProgram(_Base):
         # Rides on the stem path (its pooling kernels take a pooled-side pitch).  XEMO_CONV2_PAD=0 disables.
         self.conv2_pad = self.stem_algebra and os.environ.get("XEMO_CONV2_PAD", "1") != "0"
         self.stem_wgrad_pairs = os.environ.get("XEMO_STEM_WGRAD_PAIRS", "0") != "0"
+        # EXPERIMENTAL, off by default, not yet measured: run conv1 -> pool1 (and pool1-backward -> conv1 filter gradient) in
+        # sub-batches of this many clips through the first images of the conv1 buffers, so that the 1.85 GB activation /
+        # gradient is produced and consumed out of the 126 MB L2 instead of HBM (8 clips = 58 MB).  Same kernels, same results.
+        self.stem_chunk = int(os.environ.get("XEMO_STEM_CHUNK", "0")) if (self.stem_algebra and not self.stem_wgrad_pairs) else 0
         self.side_stream = None   # torch.cuda.Stream: filter gradients run there, off the dgrad critical path
         self._geometry()
         self._load(params)
@@ -489,6 +493,10 @@ class StudentProgram(_Base):
             n = L["name"]
             wt, bias = self.view(self.w16, n + "f"), self.view(self.master, n + "b")
             last = n == "fc8"
+            if n == "conv1" and self.stem_chunk > 0:
+                self._stem_forward_chunked(L, wt, bias)
+                cur = A[n + ":out"]
+                continue
             if n == "conv1":
                 self._stem_conv(wt, None, bias, 0, A[n + ":raw"])
             else:
@@ -523,19 +531,39 @@ class StudentProgram(_Base):
                 ctx.op_affine_act(_p(cur), rows, L["cout"], _p(A[n + ":a"]), _p(A[n + ":b"]), 1, _p(A[n + ":out"]))
             cur = A[n + ":out"]
 
-    def _stem_conv(self, wt, scale, shift, relu, dst):
-        """conv1 as a 4 x 1 convolution over the space-to-depth tensor; in pixel-pair form when enabled."""
-        N, A, ctx, L = self.N, self.a, self.ctx, self.layers[0]
+    def _stem_conv(self, wt, scale, shift, relu, dst, x=None, n=None, prepare=True):
+        """conv1 as a 4 x 1 convolution over the space-to-depth tensor (`x`, `n` clips: default the whole batch); in
+        pixel-pair form when enabled (`prepare`: expand the block-diagonal filter / duplicated epilogue vectors first)."""
+        A, ctx, L = self.a, self.ctx, self.layers[0]
+        x = A["s2d"] if x is None else x
+        N = self.N if n is None else n
         if not self.stem_pairs:
-            self.conv(A["s2d"], N, self.s2d_hp, self.s2d_ow, 16, wt, L["kp"], 4, 1, (1, 1), (0, 0, 0, 0), scale, shift, None, relu, dst)
+            self.conv(x, N, self.s2d_hp, self.s2d_ow, 16, wt, L["kp"], 4, 1, (1, 1), (0, 0, 0, 0), scale, shift, None, relu, dst)
             return
         kp = L["kp"]
-        ctx.op_stem_pair_filter(_p(wt), kp, _p(A["stem:w2"]))
-        ctx.op_tile_f32(_p(shift), kp, 2, 0.0, _p(A["stem:shift2"]))
-        if scale is not None:
-            ctx.op_tile_f32(_p(scale), kp, 2, 1.0, _p(A["stem:scale2"]))
-        self.conv(A["s2d"], N, self.s2d_hp, self.s2d_ow // 2, 32, A["stem:w2"], 2 * kp, 4, 1, (1, 1), (0, 0, 0, 0),
+        if prepare:
+            ctx.op_stem_pair_filter(_p(wt), kp, _p(A["stem:w2"]))
+            ctx.op_tile_f32(_p(shift), kp, 2, 0.0, _p(A["stem:shift2"]))
+            if scale is not None:
+                ctx.op_tile_f32(_p(scale), kp, 2, 1.0, _p(A["stem:scale2"]))
+        self.conv(x, N, self.s2d_hp, self.s2d_ow // 2, 32, A["stem:w2"], 2 * kp, 4, 1, (1, 1), (0, 0, 0, 0),
                   A["stem:scale2"] if scale is not None else None, A["stem:shift2"], None, relu, dst)
+
+    def _stem_forward_chunked(self, L, wt, bias):
+        """EXPERIMENTAL (XEMO_STEM_CHUNK): statistics first (they come from the patch autocorrelation, not from the
+        activation), then conv1 -> pool1 per sub-batch through the head of the conv1 buffer (L2-resident)."""
+        N, A, ctx, n = self.N, self.a, self.ctx, "conv1"
+        P = L["pool"]
+        g, beta = self.view(self.master, "bn1m"), self.view(self.master, "bn1b")
+        ctx.op_stem_bn_train(_p(A["stem:ws"]), _p(wt), _p(bias), N * L["oh"] * L["ow"], L["cout"], _p(g), _p(beta), BN_EPS,
+                             _p(self.batch_moments["bn1"]), _p(A[n + ":a"]), _p(A[n + ":b"]))
+        for i0 in range(0, N, self.stem_chunk):
+            nb = min(self.stem_chunk, N - i0)
+            raw = A[n + ":raw"][:nb]
+            self._stem_conv(wt, None, bias, 0, raw, x=A["s2d"][i0 : i0 + nb], n=nb, prepare=(i0 == 0))
+            ctx.op_maxpool_fwd_win(_p(raw), nb, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1], P["stride"][0], P["stride"][1],
+                                   0, 0, 0, 0, _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":out"][i0 : i0 + nb]),
+                                   _p(A[n + ":arg"][i0 : i0 + nb]), _p(A[n + ":xwin"][i0 : i0 + nb]), self.pool1_ld)
 
     def _record_forward_test(self):
         """dag.mode = 'test' (external/compute_audio_feats.m:106): BN uses the stored moments, so it folds -- together
@@ -615,8 +643,9 @@ class StudentProgram(_Base):
                 ld = self.pool1_ld
                 ctx.op_stem_pool_bn_reduce(_p(A[n + ":xwin"]), _p(A[n + ":dout"]), prow, L["cout"], ld, _p(self.batch_moments[bn]),
                                            _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":ws"]))
-                ctx.op_maxpool_bwd_ld(_p(A[n + ":dout"]), _p(A[n + ":arg"]), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1],
-                                      P["stride"][0], P["stride"][1], 0, 0, 0, 0, _p(A[n + ":draw"]), ld)
+                if self.stem_chunk == 0:
+                    ctx.op_maxpool_bwd_ld(_p(A[n + ":dout"]), _p(A[n + ":arg"]), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1],
+                                          P["stride"][0], P["stride"][1], 0, 0, 0, 0, _p(A[n + ":draw"]), ld)
                 fused_bias = True
             elif L["bn"]:
                 bn = "bn" + n[-1]
@@ -658,6 +687,16 @@ class StudentProgram(_Base):
                     ctx.memset(_p(g1p), 0, g1p.numel() * 4)
                     ctx.op_conv_wgrad(_p(x), N, self.s2d_hp, self.s2d_ow // 2, 32, _p(dy), 2 * L["kp"], 2 * L["kp"], 4, 1, 1, 1,
                                       0, 0, 0, 0, _p(g1p), inv)
+                elif self.stem_chunk > 0:
+                    # EXPERIMENTAL: pool1 backward -> filter gradient per sub-batch through the head of the dz buffer
+                    g1p, P = None, L["pool"]
+                    for i0 in range(0, N, self.stem_chunk):
+                        nb = min(self.stem_chunk, N - i0)
+                        ctx.op_maxpool_bwd_ld(_p(A[n + ":dout"][i0 : i0 + nb]), _p(A[n + ":arg"][i0 : i0 + nb]), nb, L["oh"], L["ow"],
+                                              L["cout"], P["win"][0], P["win"][1], P["stride"][0], P["stride"][1], 0, 0, 0, 0,
+                                              _p(A[n + ":draw"][:nb]), self.pool1_ld)
+                        ctx.op_conv_wgrad(_p(A["s2d"][i0 : i0 + nb]), nb, self.s2d_hp, self.s2d_ow, 16, _p(A[n + ":draw"][:nb]), L["kp"],
+                                          L["kp"], 4, 1, 1, 1, 0, 0, 0, 0, _p(gf), inv)
                 else:
                     g1p = None
                     ctx.op_conv_wgrad(_p(x), N, self.s2d_hp, self.s2d_ow, 16, _p(dy), L["kp"], L["kp"], 4, 1, 1, 1, 0, 0, 0, 0, _p(gf), inv)
