@@ -259,6 +259,17 @@ int xemo_op_stem_wgrad_finalize(xemo_ctx* ctx, const double* ws, const void* w16
 int xemo_op_se_squeeze(xemo_ctx* ctx, const void* u16, int N, int HW, int C, float* s);
 int xemo_op_se_gate(xemo_ctx* ctx, const float* s, int N, int C, int Cr, const float* w1, const float* b1,
                     const float* w2, const float* b2, float* gate);
+/* EXPERIMENTAL, default-off in the programs (not yet run on a GPU): the SE block by linearity.  The
+ * squeeze is linear in the bottleneck's 3x3 output t2, s = a3 * (W3 . mean_hw t2) + b3, so the gate is known before the
+ * expand convolution runs and the excite folds into that convolution's epilogue: m2 = se_squeeze(t2) ([N][Cm]) ->
+ * se_gate_lin -> nc_scale = gate*a3, nc_shift = gate*b3 ([N][C]) -> conv_fwd_nc: out = act(nc_scale[n,k]*conv + nc_shift[n,k]
+ * + residual).  The expand output u is never written or re-read. */
+int xemo_op_se_gate_lin(xemo_ctx* ctx, const float* m2, int N, int C, int Cm, int Cr, const void* w3_16, const float* a3,
+                        const float* b3, const float* w1, const float* b1, const float* w2t, const float* b2,
+                        float* nc_scale, float* nc_shift);
+int xemo_op_conv_fwd_nc(xemo_ctx* ctx, const void* x16, int N, int H, int W, int Cin, const void* w16, int Kout, int R, int S,
+                        int sh, int sw, int pt, int pb, int pl, int pr, const float* nc_scale, const float* nc_shift,
+                        const void* residual16, int relu, void* out16);
 int xemo_op_se_excite(xemo_ctx* ctx, const void* u16, const float* gate, const void* shortcut16, int N, int HW, int C,
                       int relu, void* y16);
 

@@ -103,6 +103,9 @@ SIGNATURES = {
     "xemo_op_add_act": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "xemo_op_se_squeeze": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "xemo_op_se_gate": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "xemo_op_se_gate_lin": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 9),
+    "xemo_op_conv_fwd_nc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p] + [c_int] * 9 + [c_void_p, c_void_p, c_void_p,
+                                                                                                          c_int, c_void_p]),
     "xemo_op_se_excite": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "xemo_op_logit_aggregate": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "xemo_op_softmaxce": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_int, c_float,

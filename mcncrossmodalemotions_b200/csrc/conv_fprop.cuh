@@ -69,7 +69,15 @@ struct ConvFpropParams {
   // ONCE per CTA (k_iters slots) instead of once per tile -- for the K = 64..576 layers at 56 x 56 and the stems the
   // per-tile filter re-fetch is 40-65 % of the L2->smem traffic and of the TMA row requests
   int b_resident;
+  // per-(image, channel) epilogue vectors (kNC instantiation only; EXPERIMENTAL, see conv_fprop_kernel): the SE block's
+  // excite fused into its expand convolution,  y = relu(gate[n,c] * (a[c]*acc + b[c]) + shortcut)
+  //   = relu(nc_scale[n,c]*acc + nc_shift[n,c] + residual),  nc_scale = gate*a, nc_shift = gate*b  ([N][Kout] fp32)
+  const float* nc_scale;
+  const float* nc_shift;
+  int nc_hw;                // pixels per image (OH*OW): image of a GEMM row = row / nc_hw
 };
+
+constexpr int kNcSlots = 4;   // images one 128-row tile can touch (7 x 7 maps: 128 / 49 -> up to 4)
 
 template <int BK>
 struct ConvSwizzle;
@@ -95,7 +103,9 @@ __device__ __forceinline__ uint32_t swz_off(int row, int chunk, int pitch, uint3
 
 __device__ __forceinline__ void epi_bar_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 
-template <int BK>
+// kNC = true (EXPERIMENTAL, default-off path): scale / shift are per (image, channel) instead of per channel.  A separate
+// instantiation so that the code of the default kernels is untouched.
+template <int BK, bool kNC = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -119,6 +129,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* after = epi_res_buf + (p.use_tma_residual ? kEpiGroups * epi_bufs * kEpiStageBytes : 0);
   float* epi_ss = reinterpret_cast<float*>(after);                                   // [group][scale | shift][256]
   after += kEpiGroups * 2 * 256 * sizeof(float);
+  float* epi_nc = reinterpret_cast<float*>(after);                                   // [group][scale | shift][slot][256] (kNC)
+  if (kNC) after += kEpiGroups * 2 * kNcSlots * 256 * sizeof(float);
   uint64_t* bars = reinterpret_cast<uint64_t*>(after);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + num_stages;
@@ -302,6 +314,22 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         ss_n_tile = n_tile;
         epi_bar_sync(group);
       }
+      int nc_slot = 0;
+      if constexpr (kNC) {
+        // the images this tile's rows belong to: their [block_n] scale / shift rows go to this group's slots (the previous
+        // chunk ended with a group barrier, so nobody still reads the old ones); a thread's slot = its row's image - first
+        const int img0 = m0 / p.nc_hw;
+        const int last_row = min(m0 + kConvBlockM, p.M) - 1;
+        const int nimg = last_row / p.nc_hw - img0 + 1;   // <= kNcSlots (host check: nc_hw >= 43)
+        float* ncs = epi_nc + group * (2 * kNcSlots * 256);
+        for (int i = tg; i < nimg * p.block_n; i += 128) {
+          const int sl = i / p.block_n, c = i - sl * p.block_n;
+          ncs[sl * 256 + c] = __ldg(p.nc_scale + size_t(img0 + sl) * p.Kout + n0 + c);
+          ncs[(kNcSlots + sl) * 256 + c] = __ldg(p.nc_shift + size_t(img0 + sl) * p.Kout + n0 + c);
+        }
+        nc_slot = min(row, p.M - 1) / p.nc_hw - img0;
+        epi_bar_sync(group);
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc) * 256u;
@@ -332,14 +360,17 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
         if (fast) {
           const uint32_t sbuf_u32 = smem_u32(sbuf), rbuf_u32 = smem_u32(rbuf);
+          // (kNC) this thread's image slot of the per-(image, channel) vectors
+          const uint32_t nc_scale_u32 = kNC ? smem_u32(epi_nc + group * (2 * kNcSlots * 256) + nc_slot * 256) : 0u;
+          const uint32_t nc_shift_u32 = kNC ? smem_u32(epi_nc + group * (2 * kNcSlots * 256) + (kNcSlots + nc_slot) * 256) : 0u;
           auto process_fast = [&](const uint32_t (&v)[16], int jj, auto res_tag) {
             constexpr bool kRes = decltype(res_tag)::value;
             const uint32_t jb = uint32_t(q * cw + jj) * 4u;
             float x[16];
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
-              const float4 sc = lds_f4(ss_scale_u32 + jb + i * 4);
-              const float4 sh = lds_f4(ss_shift_u32 + jb + i * 4);
+              const float4 sc = lds_f4((kNC ? nc_scale_u32 : ss_scale_u32) + jb + i * 4);
+              const float4 sh = lds_f4((kNC ? nc_shift_u32 : ss_shift_u32) + jb + i * 4);
               x[i] = fmaf(__uint_as_float(v[i]), sc.x, sh.x);
               x[i + 1] = fmaf(__uint_as_float(v[i + 1]), sc.y, sh.y);
               x[i + 2] = fmaf(__uint_as_float(v[i + 2]), sc.z, sh.z);

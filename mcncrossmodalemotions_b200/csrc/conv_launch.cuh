@@ -35,6 +35,9 @@ struct ConvEpilogue {
   int strided_out = 0;
   long long out_sn = 0, out_sh = 0, out_sw = 0;
   int allow_tma_epilogue = 1;  // 0 forces the direct-store epilogue
+  // EXPERIMENTAL per-(image, channel) scale / shift ([N][Kout] fp32; replaces scale / shift), fp16 TMA-store outputs only
+  const float* nc_scale = nullptr;
+  const float* nc_shift = nullptr;
 };
 
 struct ConvPlan {
@@ -114,6 +117,12 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   p.use_tma_store = (e.allow_tma_epilogue && e.out && !e.strided_out && (p.ldc % 8 == 0)) ? 1 : 0;
   p.use_tma_residual = (p.use_tma_store && e.residual) ? 1 : 0;
   p.epi_cw = (p.block_n % 64 == 0) ? 64 : (p.block_n % 32 == 0) ? 32 : 16;
+  p.nc_scale = e.nc_scale; p.nc_shift = e.nc_shift; p.nc_hw = OH * OW;
+  const int nc_bytes = e.nc_scale ? kEpiGroups * 2 * kNcSlots * 256 * 4 : 0;
+  if (e.nc_scale) {
+    // the fast epilogue only; a 128-row tile may touch at most kNcSlots images
+    if (!e.nc_shift || !p.use_tma_store || e.out_f32 || bk != 64 || (kConvBlockM + p.nc_hw - 2) / p.nc_hw + 1 > kNcSlots) return false;
+  }
   // staging buffers per epilogue group: two when the pipeline still keeps enough stages for the K loop
   const int k_iters = g.R * g.S * p.kc_blocks;
   const int want_stages = k_iters + 1 < 3 ? k_iters + 1 : 3;
@@ -128,7 +137,7 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   int stages = 0, epi_bytes = 0;
   for (int bufs = 2; bufs >= 1; --bufs) {
     epi_bytes = (p.use_tma_store ? kEpiGroups * bufs * kEpiStageBytes : 0) + (p.use_tma_residual ? kEpiGroups * bufs * kEpiStageBytes : 0);
-    stages = (kSmemBudget - 1024 - 256 - 4096 - epi_bytes - fixed_bytes) / stage_bytes;
+    stages = (kSmemBudget - 1024 - 256 - 4096 - nc_bytes - epi_bytes - fixed_bytes) / stage_bytes;
     p.epi_bufs = bufs;
     if (stages >= want_stages) break;
   }
@@ -136,7 +145,7 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   if (stages < 2) return false;
   p.num_stages = stages;
   plan->bk = bk;
-  plan->smem = stages * stage_bytes + fixed_bytes + epi_bytes + 1024 + kEpiGroups * 2 * 256 * 4 + (2 * stages + 9) * 8 + 16;
+  plan->smem = stages * stage_bytes + fixed_bytes + epi_bytes + 1024 + kEpiGroups * 2 * 256 * 4 + nc_bytes + (2 * stages + 9) * 8 + 16;
   plan->grid = tiles < num_sms ? tiles : num_sms;
   plan->flops = 2.0 * double(p.M) * g.Kout * g.R * g.S * g.Cin;
   if (!encode_maps) return true;
@@ -167,6 +176,13 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
 
 inline cudaError_t conv_fprop_run(const ConvPlan& plan, cudaStream_t stream) {
   cudaError_t err = cudaSuccess;
+  if (plan.p.nc_scale) {   // EXPERIMENTAL per-(image, channel) epilogue: BK = 64 only (checked by the plan)
+    static bool attr = false;
+    if (!attr) { err = cudaFuncSetAttribute(conv_fprop_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget); attr = true; }
+    if (err != cudaSuccess) return err;
+    conv_fprop_kernel<64, true><<<plan.grid, kConvThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
+    return cudaGetLastError();
+  }
   switch (plan.bk) {
     case 64: {
       static bool attr = false;

@@ -1114,6 +1114,86 @@ static __global__ void se_gate_kernel(const float* __restrict__ s, int N, int C,
   }
 }
 
+// EXPERIMENTAL (default-off SE-by-linearity path).  The SE squeeze is linear in the bottleneck's
+// 3x3 output t2:  s[n,c] = mean_hw(a3[c] * (W3 t2)[n,.,c] + b3[c]) = a3[c] * (W3[c,:] . mean_hw t2[n,:]) + b3[c],
+// so the expand convolution's output u never has to exist before the gate is known.  This kernel takes
+// m2 = mean_hw(t2) ([N][Cm], se_squeeze_kernel on the C/4-channel tensor), forms s, runs the two gate FCs and emits the
+// per-(image, channel) epilogue vectors of the fused expand+excite convolution (conv_fprop_kernel<64, true>):
+//   nc_scale = gate * a3,  nc_shift = gate * b3    ->   y = relu(nc_scale * acc + nc_shift + shortcut).
+// w3: [C][Cm] fp16 (the KRSC 1x1 filter); w1, w2t as in se_gate_kernel.  Dynamic smem: kSeSpb * (Cm + C + Cr) floats.
+static __global__ void se_gate_lin_kernel(const float* __restrict__ m2, int N, int C, int Cm, int Cr,
+                                          const __half* __restrict__ w3, const float* __restrict__ a3,
+                                          const float* __restrict__ b3, const float* __restrict__ w1,
+                                          const float* __restrict__ b1, const float* __restrict__ w2t,
+                                          const float* __restrict__ b2, float* __restrict__ nc_scale,
+                                          float* __restrict__ nc_shift) {
+  extern __shared__ float sm[];
+  float* mv = sm;                       // [kSeSpb][Cm]
+  float* sv = mv + kSeSpb * Cm;         // [kSeSpb][C]
+  float* hid = sv + kSeSpb * C;         // [kSeSpb][Cr]
+  const int n0 = blockIdx.x * kSeSpb;
+  for (int i = threadIdx.x; i < kSeSpb * Cm; i += blockDim.x) {
+    const int sidx = i / Cm, j = i - sidx * Cm;
+    mv[i] = (n0 + sidx < N) ? m2[size_t(n0 + sidx) * Cm + j] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int c = warp; c < C; c += nwarps) {          // s = a3 * (W3 . m2) + b3, one warp per output channel
+    float t[kSeSpb];
+#pragma unroll
+    for (int q = 0; q < kSeSpb; ++q) t[q] = 0.f;
+    const __half2* wr = reinterpret_cast<const __half2*>(w3 + size_t(c) * Cm);
+    for (int j = lane; j < Cm / 2; j += 32) {        // Cm is a multiple of 64 (checked by the wrapper)
+      const float2 w = __half22float2(wr[j]);
+#pragma unroll
+      for (int q = 0; q < kSeSpb; ++q) t[q] = fmaf(w.x, mv[q * Cm + 2 * j], fmaf(w.y, mv[q * Cm + 2 * j + 1], t[q]));
+    }
+#pragma unroll
+    for (int q = 0; q < kSeSpb; ++q) {
+      const float r = warp_sum(t[q]);
+      if (lane == 0) sv[q * C + c] = fmaf(a3[c], r, b3[c]);
+    }
+  }
+  __syncthreads();
+  for (int j = warp; j < Cr; j += nwarps) {          // hidden = relu(W1 s + b1)
+    float t[kSeSpb];
+#pragma unroll
+    for (int q = 0; q < kSeSpb; ++q) t[q] = 0.f;
+    const float* wr = w1 + size_t(j) * C;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 w = *reinterpret_cast<const float4*>(wr + c);
+#pragma unroll
+      for (int q = 0; q < kSeSpb; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(sv + q * C + c);
+        t[q] = fmaf(w.x, v.x, fmaf(w.y, v.y, fmaf(w.z, v.z, fmaf(w.w, v.w, t[q]))));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kSeSpb; ++q) {
+      const float r = warp_sum(t[q]);
+      if (lane == 0) hid[q * Cr + j] = fmaxf(r + (b1 ? b1[j] : 0.f), 0.f);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {   // gate = sigmoid(W2 hidden + b2) -> epilogue vectors
+    float t[kSeSpb];
+#pragma unroll
+    for (int q = 0; q < kSeSpb; ++q) t[q] = b2 ? b2[c] : 0.f;
+    for (int j = 0; j < Cr; ++j) {
+      const float w = w2t[size_t(j) * C + c];
+#pragma unroll
+      for (int q = 0; q < kSeSpb; ++q) t[q] = fmaf(w, hid[q * Cr + j], t[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < kSeSpb; ++q)
+      if (n0 + q < N) {
+        const float gate = 1.f / (1.f + __expf(-t[q]));
+        nc_scale[size_t(n0 + q) * C + c] = gate * a3[c];
+        nc_shift[size_t(n0 + q) * C + c] = gate * b3[c];
+      }
+  }
+}
+
 template <typename T>
 __global__ void se_excite_kernel(const T* __restrict__ u, const float* __restrict__ gate,
                                  const T* __restrict__ shortcut, int HW, int C, size_t total8, int relu,

@@ -664,6 +664,35 @@ extern "C" int xemo_op_se_gate(xemo_ctx* ctx, const float* s, int N, int C, int 
   return XEMO_OK;
 }
 
+// EXPERIMENTAL (default-off): SE block by linearity -- see se_gate_lin_kernel / conv_fprop_kernel<64, true>
+extern "C" int xemo_op_se_gate_lin(xemo_ctx* ctx, const float* m2, int N, int C, int Cm, int Cr, const void* w3_16, const float* a3,
+                                   const float* b3, const float* w1, const float* b1, const float* w2t, const float* b2,
+                                   float* nc_scale, float* nc_shift) {
+  XEMO_REQUIRE(ctx, m2 && w3_16 && a3 && b3 && w1 && w2t && nc_scale && nc_shift && C % 128 == 0 && Cm % 64 == 0 &&
+                        size_t(kSeSpb) * (Cm + C + Cr) * 4 <= 48 * 1024,
+               "se_gate_lin: C must be a multiple of 128, Cm of 64, and (Cm + C + Cr) <= 6144");
+  const int threads = C <= 512 ? 512 : 1024;
+  se_gate_lin_kernel<<<(N + kSeSpb - 1) / kSeSpb, threads, size_t(kSeSpb) * (Cm + C + Cr) * 4, ctx->stream>>>(
+      m2, N, C, Cm, Cr, static_cast<const __half*>(w3_16), a3, b3, w1, b1, w2t, b2, nc_scale, nc_shift);
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+// EXPERIMENTAL (default-off): 1x1 / general convolution whose epilogue applies per-(image, channel) scale / shift
+// ([N][Kout] fp32) + residual + ReLU:  out = act(nc_scale[n,k]*conv(x,w) + nc_shift[n,k] + residual)
+extern "C" int xemo_op_conv_fwd_nc(xemo_ctx* ctx, const void* x16, int N, int H, int W, int Cin, const void* w16, int Kout, int R,
+                                   int S, int sh, int sw, int pt, int pb, int pl, int pr, const float* nc_scale,
+                                   const float* nc_shift, const void* residual16, int relu, void* out16) {
+  XEMO_REQUIRE(ctx, x16 && w16 && out16 && nc_scale && nc_shift, "conv_fwd_nc: null pointer");
+  XEMO_REQUIRE(ctx, Cin % 64 == 0 && Kout % 16 == 0, "conv_fwd_nc: Cin=%d must be a multiple of 64 and Kout=%d of 16", Cin, Kout);
+  ConvGeom g{N, H, W, Cin, Kout, R, S, sh, sw, pt, pb, pl, pr};
+  XEMO_REQUIRE(ctx, g.OH() > 0 && g.OW() > 0 && g.OH() * g.OW() >= 43, "conv_fwd_nc: needs at least 43 output pixels per image");
+  ConvEpilogue e;
+  e.nc_scale = nc_scale; e.nc_shift = nc_shift; e.residual = static_cast<const __half*>(residual16); e.relu = relu;
+  e.out = static_cast<__half*>(out16); e.ldc = Kout;
+  return run_fprop(ctx, g, static_cast<const __half*>(x16), static_cast<const __half*>(w16), e);
+}
+
 extern "C" int xemo_op_se_excite(xemo_ctx* ctx, const void* u16, const float* gate, const void* shortcut16, int N, int HW,
                                  int C, int relu, void* y16) {
   XEMO_REQUIRE(ctx, u16 && gate && y16 && C % 8 == 0, "se_excite: bad arguments");

@@ -162,6 +162,10 @@ class TeacherProgram(_Base):
         self.face_size = face_size
         self.mean3 = self.upload(np.asarray(average_image, np.float32))
         self.graph = None
+        # EXPERIMENTAL, off by default, not yet run on a GPU: SE blocks by linearity -- squeeze of the
+        # C/4-channel 3x3 output, gate, and the excite folded into the expand convolution's epilogue; the expand output u is
+        # never materialised (2.5 C instead of 5.25 C bytes per pixel of SE traffic).  XEMO_SE_LIN=1 enables.
+        self.se_lin = os.environ.get("XEMO_SE_LIN", "0") == "1"
         self._load(params)
         self._alloc()
 
@@ -226,6 +230,8 @@ class TeacherProgram(_Base):
                 A[pre + "u"] = self.f16(N, ohw, ohw, cout)
                 A[pre + "s"] = self.f32(N, cout)
                 A[pre + "g"] = self.f32(N, cout)
+                if self.se_lin:
+                    A[pre + "m2"], A[pre + "gs"], A[pre + "gh"] = self.f32(N, mid), self.f32(N, cout), self.f32(N, cout)
             A[pre + "y"] = self.f16(N, ohw, ohw, cout)
             hw = ohw
         A["pool5"] = self.f16(N, 2048)
@@ -260,7 +266,13 @@ class TeacherProgram(_Base):
             else:
                 sc = cur
             a, b = W[pre + "bn3"]
-            if se:
+            if se and self.se_lin:
+                ctx.op_se_squeeze(_p(A[pre + "t2"]), N, ohw * ohw, mid, _p(A[pre + "m2"]))
+                ctx.op_se_gate_lin(_p(A[pre + "m2"]), N, cout, mid, cout // 16, _p(W[pre + "c3"]), _p(a), _p(b), _p(W[pre + "se1"]),
+                                   _p(W[pre + "se1b"]), _p(W[pre + "se2"]), _p(W[pre + "se2b"]), _p(A[pre + "gs"]), _p(A[pre + "gh"]))
+                ctx.op_conv_fwd_nc(_p(A[pre + "t2"]), N, ohw, ohw, mid, _p(W[pre + "c3"]), cout, 1, 1, 1, 1, 0, 0, 0, 0,
+                                   _p(A[pre + "gs"]), _p(A[pre + "gh"]), _p(sc), 1, _p(A[pre + "y"]))
+            elif se:
                 self.conv(A[pre + "t2"], N, ohw, ohw, mid, W[pre + "c3"], cout, 1, 1, (1, 1), (0, 0, 0, 0), a, b, None, 0, A[pre + "u"])
                 # (computing the squeeze by linearity from mean_hw(t2) -- 4x fewer bytes -- was measured: the extra tiny
                 # launches cost what the narrower read saves, so the direct form stays)
