@@ -57,12 +57,25 @@ typedef struct {
 
 /* ------------------------------------------------------------------ context */
 int xemo_version(void);
-/* `cuda_stream` is a cudaStream_t (NULL: the context creates its own non-blocking stream). */
+/* `cuda_stream` is a cudaStream_t (NULL: the context creates its own non-blocking stream).  A host whose other GPU work
+ * runs on the legacy default stream (MATLAB's gpuArray arithmetic) passes XEMO_STREAM_LEGACY (== cudaStreamLegacy) so that
+ * the library's kernels are stream-ordered with it; xemo_current_device reports the CUDA runtime's current device. */
+#define XEMO_STREAM_LEGACY ((void*)0x1)
+int xemo_current_device(int* device);
 int xemo_create(int device, void* cuda_stream, xemo_ctx** out);
 void xemo_destroy(xemo_ctx* ctx);
 const char* xemo_last_error(xemo_ctx* ctx);
 int xemo_sync(xemo_ctx* ctx);
 int xemo_num_sms(xemo_ctx* ctx);
+/* Operand precision of xemo_vl_nnconv (the reference computes in `single` end to end: cnn_train_dag at
+ * emoVoxCeleb/run_distillation.m:170-182 on gpuArray(single) batches, getBatchEmoVoxCeleb.m:197).
+ *   XEMO_CONV_F16   (default) fp16 operands, fp32 accumulation: ~2^-11 relative operand rounding
+ *   XEMO_CONV_F32X3 split operands: each single-precision operand is staged as hi + lo fp16 halves and every product
+ *                   as the three leading terms hi*hi + lo*hi + hi*lo on tcgen05 (one convolution over a 3x longer
+ *                   reduction), fp32 accumulation -- fp32-equivalent results (~2^-22 per product) at 3x the MMA work. */
+enum { XEMO_CONV_F16 = 0, XEMO_CONV_F32X3 = 1 };
+int xemo_set_conv_precision(xemo_ctx* ctx, int mode);
+int xemo_get_conv_precision(xemo_ctx* ctx);
 /* number of kernels this context has launched (graph replays count their kernel nodes) */
 uint64_t xemo_launch_count(xemo_ctx* ctx);
 /* async copies on the context stream (host memory should be pinned for true asynchrony) */
@@ -283,12 +296,30 @@ int xemo_op_logit_aggregate(xemo_ctx* ctx, const float* frame_logits, int ldl, c
 int xemo_op_softmaxce(xemo_ctx* ctx, const void* x16, int ldx, const float* t, int ldt, const float* w, int N, int C,
                       float T, int logit_targets, float dzdy, float grad_scale, void* dx16, float* scalars,
                       float* class_stats, int* max_label);
+/* the same kernel behind every `lossType` of emoVoxCeleb/emoVoxZoo.m:137-157 that compares {prediction, logitTarget}:
+ * loss_type 0 = softmax CE as above (logit_targets = 0, T = 1: dagnn.Loss('softmaxlog') on one-hot rows),
+ * 1 = dagnn.EuclideanLoss: loss = sum_n w_n/2 |x_n - t_n|^2, dx = dzdy w_n (x - t)          (emoVoxZoo.m:138-144)
+ * 2 = dagnn.HuberLoss('sigma', T): smooth-L1, linear where |x - t| > 1/sigma^2              (emoVoxZoo.m:145-147)
+ * x / dx are fp32 when x_f32 / dx_f32 are set (fp16 otherwise), with row pitches ldx / lddx; metrics as above. */
+int xemo_op_loss(xemo_ctx* ctx, const void* x, int x_f32, int ldx, const float* t, int ldt, const float* w, int N, int C,
+                 int loss_type, float T, int logit_targets, float dzdy, float grad_scale, void* dx, int dx_f32, int lddx,
+                 float* scalars, float* class_stats, int* max_label);
 /* cnn_train_dag update: m <- mu*m - (wd*w + g*inv_grad_scale/B); w <- w + lr*m; optional fp16 copy refresh.
  * hyper (device, fp32[4]) = {lr, momentum, weight_decay, 1/B}; lr_mult / wd_mult are per-parameter multipliers */
 int xemo_op_sgd_momentum(xemo_ctx* ctx, float* w, float* m, const float* g, size_t n, const float* hyper, float lr_mult,
                          float wd_mult, float inv_grad_scale, void* w16);
 /* dagnn.BatchNorm moments parameter: moments <- (1-rate)*moments + rate*batch_moments */
 int xemo_op_moments_average(xemo_ctx* ctx, float* moments, const float* batch_moments, int n, float rate);
+/* Overflow guard of the fp16 gradient chain (the fast programs carry activation gradients in fp16 under a fixed loss
+ * scale; the reference trains in single and cannot overflow there).  grad_guard scans the flat fp32 gradient: state
+ * (device, int[3], zero-initialised by the caller) gets state[0] = 1 if any element is inf / NaN this step (else 0) and
+ * state[1] += state[0] (steps skipped so far).  The *_guarded updates are no-ops while state[0] is set, so a poisoned
+ * gradient never reaches the master weights, the momentum, the fp16 mirror or the BN moments. */
+int xemo_op_grad_guard(xemo_ctx* ctx, const float* g, size_t n, int* state);
+int xemo_op_sgd_momentum_guarded(xemo_ctx* ctx, float* w, float* m, const float* g, size_t n, const float* hyper,
+                                 float lr_mult, float wd_mult, float inv_grad_scale, void* w16, const int* guard);
+int xemo_op_moments_average_guarded(xemo_ctx* ctx, float* moments, const float* batch_moments, int n, float rate,
+                                    const int* guard);
 int xemo_op_cast_f32_f16(xemo_ctx* ctx, const float* src, size_t n, void* dst16);
 int xemo_op_cast_f16_f32(xemo_ctx* ctx, const void* src16, size_t n, float scale, float* dst);
 /* dst[o*outer_stride + inner_off + i] = value for o < outer, i < inner (masks structurally-zero filter slots) */

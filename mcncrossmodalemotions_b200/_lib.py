@@ -32,6 +32,7 @@ _AP = P(XemoArray)
 # name -> (restype, argtypes); every symbol declared in include/xemo.h
 SIGNATURES = {
     "xemo_version": (c_int, []),
+    "xemo_current_device": (c_int, [P(c_int)]),
     "xemo_create": (c_int, [c_int, c_void_p, P(c_void_p)]),
     "xemo_destroy": (None, [c_void_p]),
     "xemo_last_error": (C.c_char_p, [c_void_p]),
@@ -110,7 +111,15 @@ SIGNATURES = {
     "xemo_op_logit_aggregate": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "xemo_op_softmaxce": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_int, c_float,
                                   c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "xemo_op_loss": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_int, c_float,
+                             c_float, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "xemo_set_conv_precision": (c_int, [c_void_p, c_int]),
+    "xemo_get_conv_precision": (c_int, [c_void_p]),
     "xemo_op_sgd_momentum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_float, c_float, c_float, c_void_p]),
+    "xemo_op_grad_guard": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "xemo_op_sgd_momentum_guarded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_float, c_float, c_float,
+                                             c_void_p, c_void_p]),
+    "xemo_op_moments_average_guarded": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
     "xemo_op_moments_average": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float]),
     "xemo_op_cast_f32_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "xemo_op_cast_f16_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p]),
@@ -178,7 +187,8 @@ class Context:
             raise XemoError(rc, self.lib.xemo_last_error(self.handle).decode())
 
     def __getattr__(self, name):
-        if name.startswith(("op_", "vl_")) or name in ("sync", "h2d", "d2h", "memset", "capture_begin", "graph_launch", "set_stream", "stream_wait"):
+        if name.startswith(("op_", "vl_")) or name in ("sync", "h2d", "d2h", "memset", "capture_begin", "graph_launch", "set_stream", "stream_wait",
+                                                     "set_conv_precision"):
             return lambda *a: self.call(name, *a)
         raise AttributeError(name)
 

@@ -95,6 +95,8 @@ def width_bucket(num_columns, buckets=(100, 200, 300, 400, 500, 600, 700, 800, 9
 
 
 def centre_crop(spec, width):
+    """external/compute_audio_feats.m:183-186: 1-based rstart = round((W - rsize) / 2) (MATLAB round: halves away from
+    zero), 0 mapped to 1; columns rstart : rstart + rsize - 1."""
     w = spec.shape[1]
-    s = (w - width) // 2
-    return spec[:, s : s + width]
+    rstart = max(int(np.floor((w - width) / 2.0 + 0.5)), 1)
+    return spec[:, rstart - 1 : rstart - 1 + width]

@@ -59,12 +59,13 @@ inline int conv_pick_bk(int cin) { return (cin % 64 == 0) ? 64 : (cin % 32 == 0)
 // 128-byte rows (BK = 64) and proportionally less with 64- / 32-byte rows, and every tile re-fetches its
 // block_n x K filter slice unless the filter is resident (one N tile, <= 112 KB).  The term only enters when there are
 // at least four full waves of M tiles (wave quantisation does not blur the comparison there; smaller problems keep the
-// measured fetch-blind choice).  XEMO_CONV_COSTMODEL=0 restores the fetch-blind model everywhere, =2 applies the fetch
-// term to every problem size (fc6's data gradient and the 7 x 7 teacher layers then move to 256-wide tiles: to be measured).
+// measured fetch-blind choice).  XEMO_CONV_COSTMODEL=0 restores the fetch-blind model everywhere.  (Applying the fetch term
+// to every problem size -- fc6's data gradient and the 7 x 7 teacher layers on 256-wide tiles -- was measured in round 2:
+// 5.57 vs 5.54 ms teacher forward, 9.00 vs 9.02 ms student step at batch 256, i.e. neutral; removed.)
 inline int conv_pick_block_n(int M, int Kout, int k_steps16, int num_sms, int bk = 64, int k_iters = 0) {
   static const int fetch_mode = [] { const char* e = getenv("XEMO_CONV_COSTMODEL"); return e ? (e[0] - '0') : 1; }();
   const bool fetch_aware = fetch_mode != 0;
-  const int min_m_tiles = fetch_mode == 2 ? 0 : 4 * num_sms;   // 2 (experimental, unmeasured): the fetch term for every size
+  const int min_m_tiles = 4 * num_sms;
   int best = 0;
   double best_cost = 1e300;
   const int m_tiles = (M + kConvBlockM - 1) / kConvBlockM;

@@ -1272,11 +1272,17 @@ static __global__ void logit_aggregate_kernel(const float* __restrict__ frame_lo
 // out_scalars: [0]=loss [1]=classerror ; class_stats: [C] correct, [C] count.
 // ============================================================================================
 constexpr int kLossMaxC = 16;
-static __global__ void softmaxce_fused_kernel(const __half* __restrict__ x, int ldx, const float* __restrict__ t, int ldt,
-                                       const float* __restrict__ w, int N, int C, float T, int logit_targets,
-                                       float dzdy, float grad_scale, __half* __restrict__ dx,
-                                       float* __restrict__ out_scalars, float* __restrict__ class_stats,
-                                       int* __restrict__ max_label) {
+// loss_type: 0 = temperature-softmax cross-entropy (mcnExtraLayers vl_nnsoftmaxceloss; logit_targets = 0 with T = 1 is
+// dagnn.Loss('softmaxlog') against a one-hot row), 1 = dagnn.EuclideanLoss (1/2 w_n |x - t|^2, dx = dzdy w_n (x - t)),
+// 2 = dagnn.HuberLoss('sigma', sigma): smooth-L1 per element, linear where |x - t| > 1/sigma^2 (`T` carries sigma) --
+// the three `lossType`s of emoVoxCeleb/emoVoxZoo.m:137-157 that take {prediction, logitTarget [, instanceWeights]}.
+// TX / TDX: storage type of the logits and of their gradient (fp16 in the fast programs, fp32 otherwise).
+template <typename TX, typename TDX>
+__global__ void loss_fused_kernel(const TX* __restrict__ x, int ldx, const float* __restrict__ t, int ldt,
+                                  const float* __restrict__ w, int N, int C, int loss_type, float T, int logit_targets,
+                                  float dzdy, float grad_scale, TDX* __restrict__ dx, int lddx,
+                                  float* __restrict__ out_scalars, float* __restrict__ class_stats,
+                                  int* __restrict__ max_label) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   float loss = 0.f, err = 0.f;
   if (n < N) {
@@ -1284,25 +1290,42 @@ static __global__ void softmaxce_fused_kernel(const __half* __restrict__ x, int 
     float xm = -INFINITY, tm = -INFINITY;
     int xa = 0, ta = 0;
     for (int c = 0; c < C; ++c) {
-      xv[c] = __half2float(x[size_t(n) * ldx + c]);
+      xv[c] = float(x[size_t(n) * ldx + c]);
       tv[c] = t[size_t(n) * ldt + c];
       if (xv[c] > xm) { xm = xv[c]; xa = c; }
       if (tv[c] > tm) { tm = tv[c]; ta = c; }
     }
-    const float invT = 1.f / T;
-    float xs = 0.f, ts = 0.f;
-    for (int c = 0; c < C; ++c) {
-      xv[c] = (xv[c] - xm) * invT;
-      xs += expf(xv[c]);
-      if (logit_targets) { tv[c] = expf((tv[c] - tm) * invT); ts += tv[c]; }
-    }
-    const float lse = logf(xs);
     const float wn = w ? w[n] : 1.f;
-    for (int c = 0; c < C; ++c) {
-      const float p = logit_targets ? tv[c] / ts : tv[c];
-      const float logq = xv[c] - lse;
-      loss -= p * logq;
-      if (dx) dx[size_t(n) * ldx + c] = __float2half_rn(grad_scale * dzdy * wn * (expf(logq) - p) * invT);
+    const float gsc = grad_scale * dzdy * wn;
+    if (loss_type == 0) {
+      const float invT = 1.f / T;
+      float xs = 0.f, ts = 0.f;
+      for (int c = 0; c < C; ++c) {
+        xv[c] = (xv[c] - xm) * invT;
+        xs += expf(xv[c]);
+        if (logit_targets) { tv[c] = expf((tv[c] - tm) * invT); ts += tv[c]; }
+      }
+      const float lse = logf(xs);
+      for (int c = 0; c < C; ++c) {
+        const float p = logit_targets ? tv[c] / ts : tv[c];
+        const float logq = xv[c] - lse;
+        loss -= p * logq;
+        if (dx) dx[size_t(n) * lddx + c] = from_f32<TDX>(gsc * (expf(logq) - p) * invT);
+      }
+    } else if (loss_type == 1) {
+      for (int c = 0; c < C; ++c) {
+        const float d = xv[c] - tv[c];
+        loss += 0.5f * d * d;
+        if (dx) dx[size_t(n) * lddx + c] = from_f32<TDX>(gsc * d);
+      }
+    } else {
+      const float s2 = T * T, knee = 1.f / s2;
+      for (int c = 0; c < C; ++c) {
+        const float d = xv[c] - tv[c], ad = fabsf(d);
+        const bool lin = ad > knee;
+        loss += lin ? ad - 0.5f * knee : 0.5f * s2 * ad * ad;
+        if (dx) dx[size_t(n) * lddx + c] = from_f32<TDX>(gsc * (lin ? (d > 0.f ? 1.f : -1.f) : s2 * d));
+      }
     }
     loss *= wn;
     err = (xa != ta) ? 1.f : 0.f;
@@ -1342,7 +1365,8 @@ static __global__ void sgd_momentum_kernel(float* __restrict__ w, float* __restr
 // BN moments moving average (dagnn.BatchNorm moments param: trainMethod 'average', learningRate 0.1):
 //   moments <- (1 - rate) * moments + rate * batch_moments
 static __global__ void moments_average_kernel(float* __restrict__ moments, const float* __restrict__ batch_moments, int n,
-                                       float rate) {
+                                       float rate, const int* __restrict__ guard = nullptr) {
+  if (guard && guard[0]) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) moments[i] = (1.f - rate) * moments[i] + rate * batch_moments[i];
 }

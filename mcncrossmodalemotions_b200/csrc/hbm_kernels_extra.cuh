@@ -61,15 +61,101 @@ static __global__ void dgrad_pack_kernel(const __half* __restrict__ w, DgradPack
 
 // dF [Kp][R][S][Cp] fp32 (device layout) -> FH x FW x FC x K column-major fp32 (MatConvNet)
 static __global__ void krsc_f32_to_filters_kernel(const float* __restrict__ src, int FH, int FW, int FC, int K, int Cp,
-                                           float* __restrict__ dst) {
+                                           float* __restrict__ dst, const float* __restrict__ mul = nullptr) {
   const size_t total = size_t(FH) * FW * FC * K;
+  const float m = mul ? *mul : 1.f;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
     const int r = int(i % FH);
     const int s = int((i / FH) % FW);
     const int c = int((i / (size_t(FH) * FW)) % FC);
     const int k = int(i / (size_t(FH) * FW * FC));
-    dst[i] = src[((size_t(k) * FH + r) * FW + s) * Cp + c];
+    dst[i] = m * src[((size_t(k) * FH + r) * FW + s) * Cp + c];
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split-operand ("f32x3") convolution staging: the fp32-equivalent mode of xemo_vl_nnconv
+// (xemo_set_conv_precision).  A single-precision operand v is written as v*s = hi + lo with hi = fp16(v*s),
+// lo = fp16(v*s - hi) (s a power of two taken from the tensor's max |v|, so that nothing under- or overflows in
+// fp16); the product of two such operands keeps the three leading terms
+//     a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo                        (dropped: a_lo*b_lo ~ 2^-22 |a b|)
+// which the tcgen05 kernels compute as ONE convolution over a 3x longer reduction axis: the activation-side
+// operand is staged as (hi | lo | hi), the filter-side operand as (hi | hi | lo) -- concatenated along the
+// channels for the forward / data-gradient convolutions and along the images for the filter gradient (whose
+// reduction runs over pixels).  Accumulation is the kernels' usual fp32 in TMEM.
+__device__ __forceinline__ float split_pow2_scale(unsigned amax_bits, bool inverse) {
+  // s = 2^(13 - floor(log2 amax)): max |v|*s lies in [2^13, 2^14); 1 for an all-zero / denormal / non-finite tensor
+  const int e = int((amax_bits >> 23) & 0xffu);
+  if (e <= 13 || e == 255) return 1.f;                 // (the same guard for s and 1/s)
+  const int se = inverse ? e - 13 : 254 - e + 13;      // biased exponents of 2^(e-127-13) / 2^(127-e+13)
+  return __uint_as_float(unsigned(se) << 23);
+}
+__device__ __forceinline__ void split_f16(float v, __half* hi, __half* lo) {
+  const __half h = __float2half_rn(v);
+  *hi = h;
+  *lo = __float2half_rn(v - __half2float(h));
+}
+
+static __global__ void absmax_f32_kernel(const float* __restrict__ x, size_t n, unsigned* __restrict__ amax) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
+}
+
+// HWCN fp32 -> three fp16 NHWC slots: dst[((n*H+h)*W+w)*row_pitch + c + j*slot_stride], j = 0..2, slot j holding the lo
+// part when bit j of lo_mask is set.  Channel concatenation: row_pitch = 3*Cp, slot_stride = Cp; image concatenation:
+// row_pitch = Cp, slot_stride = N*H*W*Cp.
+static __global__ void hwcn_f32_to_nhwc_split_kernel(const float* __restrict__ src, int H, int W, int C, int N, __half* __restrict__ dst,
+                                              int Cp, int row_pitch, size_t slot_stride, int lo_mask,
+                                              const unsigned* __restrict__ amax) {
+  __shared__ float tile[32][33];
+  const float sc = split_pow2_scale(*amax, false);
+  const int n = blockIdx.z / W, w = blockIdx.z % W;
+  const int h0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, h = h0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && h < H) ? src[h + size_t(H) * (w + size_t(W) * (c + size_t(C) * n))] * sc : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int h = h0 + j, c = c0 + threadIdx.x;
+    if (h < H && c < Cp) {
+      __half hi, lo;
+      split_f16(tile[threadIdx.x][j], &hi, &lo);
+      __half* d = dst + ((size_t(n) * H + h) * W + w) * row_pitch + c;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) d[s * slot_stride] = ((lo_mask >> s) & 1) ? lo : hi;
+    }
+  }
+}
+
+// filters FH x FW x FC x K (column-major fp32) -> (hi | hi | lo) fp16 KRSC: along the channels ([Kp][FH][FW][3*Cp],
+// forward / filter-side operand of a 3*Cp-channel convolution) or along the output channels ([3*Kp][FH][FW][Cp], what
+// the data gradient reduces over)
+static __global__ void filters_to_krsc_split_kernel(const float* __restrict__ f, int FH, int FW, int FC, int K, __half* __restrict__ dst,
+                                             int Kp, int Cp, int along_k, const unsigned* __restrict__ amax) {
+  const float sc = split_pow2_scale(*amax, false);
+  const int Cd = along_k ? Cp : 3 * Cp;
+  const size_t total = size_t(3) * Kp * FH * FW * Cp;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    int c = int(i % Cd);
+    const int s = int((i / Cd) % FW);
+    const int r = int((i / (size_t(Cd) * FW)) % FH);
+    int k = int(i / (size_t(Cd) * FW * FH));
+    int slot;
+    if (along_k) { slot = k / Kp; k %= Kp; } else { slot = c / Cp; c %= Cp; }
+    __half hi = __float2half_rn(0.f), lo = hi;
+    if (c < FC && k < K) split_f16(f[r + size_t(FH) * (s + size_t(FW) * (c + size_t(FC) * k))] * sc, &hi, &lo);
+    dst[i] = slot == 2 ? lo : hi;
+  }
+}
+
+// v[i] = 1 / (s_a * s_b): undoes the two operand scales (per-output-channel epilogue vector, or one scalar)
+static __global__ void split_unscale_kernel(const unsigned* __restrict__ amax_a, const unsigned* __restrict__ amax_b, int n,
+                                     float* __restrict__ v) {
+  const float inv = split_pow2_scale(*amax_a, true) * split_pow2_scale(*amax_b, true);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = inv;
 }
 
 // generic (slow-path, boundary only) NHWC <-> HWCN conversion for uint8 index tensors
@@ -310,7 +396,8 @@ static __global__ void spec_rownorm_kernel(float* __restrict__ spec, int H, int 
 // so that a captured CUDA graph follows the learning-rate schedule without re-capture.
 static __global__ void sgd_momentum_dev_kernel(float* __restrict__ w, float* __restrict__ m, const float* __restrict__ g,
                                         size_t n, const float* __restrict__ hyper, float lr_mult, float wd_mult,
-                                        float inv_grad_scale, __half* __restrict__ w16) {
+                                        float inv_grad_scale, __half* __restrict__ w16, const int* __restrict__ guard = nullptr) {
+  if (guard && guard[0]) return;   // non-finite gradient this step (grad_guard_kernel): leave w, m and the fp16 mirror alone
   const float lr = hyper[0] * lr_mult, momentum = hyper[1], wd = hyper[2] * wd_mult, inv_batch = hyper[3];
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
     const float wi = w[i];
@@ -320,6 +407,20 @@ static __global__ void sgd_momentum_dev_kernel(float* __restrict__ w, float* __r
     w[i] = wn;
     if (w16) w16[i] = __float2half_rn(wn);
   }
+}
+
+// Overflow guard of the fp16 gradient chain (fixed loss scale): state[0] <- 1 when any element of the flat gradient is
+// inf / NaN (0 otherwise), state[1] += that (skipped steps so far).  Two launches: scan, then publish.
+static __global__ void grad_guard_scan_kernel(const float* __restrict__ g, size_t n, int* __restrict__ state) {
+  int bad = 0;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    bad |= !isfinite(g[i]);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&state[2], 1);
+}
+static __global__ void grad_guard_publish_kernel(int* __restrict__ state) {
+  state[0] = state[2];
+  state[1] += state[2];
+  state[2] = 0;
 }
 
 // test-mode BN backward: dx = a * dz, dz = dy * [a*x+b > 0] when relu_mask

@@ -20,6 +20,7 @@ struct xemo_ctx {
   uint64_t launches = 0;        // kernels launched (eager) + kernel nodes replayed
   bool capturing = false;
   uint64_t capture_mark = 0;    // value of `launches` when the capture began
+  int conv_precision = 0;       // xemo_set_conv_precision: 0 = fp16 operands, 1 = split fp16 x 3 (fp32-equivalent)
 };
 
 struct xemo_graph {

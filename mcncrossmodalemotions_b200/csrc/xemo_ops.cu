@@ -12,6 +12,12 @@ using namespace xemo;
 // context
 extern "C" int xemo_version(void) { return 100; }
 
+// (XEMO_STREAM_LEGACY in xemo.h is cudaStreamLegacy, 0x1, spelled without the CUDA headers; checked in xemo_create)
+extern "C" int xemo_current_device(int* device) {
+  if (!device) return XEMO_ERR_INVALID;
+  return cudaGetDevice(device) == cudaSuccess ? XEMO_OK : XEMO_ERR_NO_DEVICE;
+}
+
 extern "C" int xemo_create(int device, void* cuda_stream, xemo_ctx** out) {
   if (!out) return XEMO_ERR_INVALID;
   *out = nullptr;
@@ -26,6 +32,7 @@ extern "C" int xemo_create(int device, void* cuda_stream, xemo_ctx** out) {
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   if (cuda_stream) {
+    if (cuda_stream == XEMO_STREAM_LEGACY) cuda_stream = reinterpret_cast<void*>(cudaStreamLegacy);
     ctx->stream = ctx->primary = reinterpret_cast<cudaStream_t>(cuda_stream);
   } else {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -52,6 +59,12 @@ extern "C" int xemo_sync(xemo_ctx* ctx) {
   return XEMO_OK;
 }
 extern "C" int xemo_num_sms(xemo_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+extern "C" int xemo_set_conv_precision(xemo_ctx* ctx, int mode) {
+  XEMO_REQUIRE(ctx, ctx && (mode == XEMO_CONV_F16 || mode == XEMO_CONV_F32X3), "set_conv_precision: mode must be 0 (fp16 operands) or 1 (split fp16 x 3)");
+  ctx->conv_precision = mode;
+  return XEMO_OK;
+}
+extern "C" int xemo_get_conv_precision(xemo_ctx* ctx) { return ctx ? ctx->conv_precision : -1; }
 extern "C" uint64_t xemo_launch_count(xemo_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int xemo_h2d(xemo_ctx* ctx, void* dst, const void* src, size_t bytes) {
@@ -331,7 +344,8 @@ extern "C" int xemo_op_pack_dgrad_filters(xemo_ctx* ctx, const void* w16_krsc, i
 
 // shared by xemo_op_conv_dgrad (fp16 out) and the vl_nnconv boundary (fp32 out)
 int xemo_conv_dgrad_impl(xemo_ctx* ctx, const void* dy16, int N, int H, int W, int Cin, const void* packed16, int Kout, int R,
-                         int S, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16, float* dx32) {
+                         int S, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16, float* dx32,
+                         const float* out_scale = nullptr) {
   XEMO_REQUIRE(ctx, dy16 && packed16 && (dx16 || dx32), "conv_dgrad: null pointer");
   XEMO_REQUIRE(ctx, Cin % 16 == 0 && Kout % 16 == 0, "conv_dgrad: Cin=%d and Kout=%d must be multiples of 16", Cin, Kout);
   const int OH = (H + pt + pb - R) / sh + 1, OW = (W + pl + pr - S) / sw + 1;
@@ -362,6 +376,7 @@ int xemo_conv_dgrad_impl(xemo_ctx* ctx, const void* dy16, int N, int H, int W, i
       g.oh_override = sub_h;
       g.ow_override = sub_w;
       ConvEpilogue e;
+      e.scale = out_scale;   // per-input-channel factor (split-operand mode of the boundary operator)
       const size_t base = (size_t(ph) * W + pw) * Cin;
       if (sh == 1 && sw == 1) {
         e.out = static_cast<__half*>(dx16);
@@ -786,33 +801,65 @@ extern "C" int xemo_op_logit_aggregate(xemo_ctx* ctx, const float* frame_logits,
   return XEMO_OK;
 }
 
+extern "C" int xemo_op_loss(xemo_ctx* ctx, const void* x, int x_f32, int ldx, const float* t, int ldt, const float* w, int N, int C,
+                            int loss_type, float T, int logit_targets, float dzdy, float grad_scale, void* dx, int dx_f32, int lddx,
+                            float* scalars, float* class_stats, int* max_label) {
+  XEMO_REQUIRE(ctx, x && t && scalars && C >= 1 && C <= kLossMaxC && C <= ldx && C <= ldt && (!dx || C <= lddx), "loss: bad arguments");
+  XEMO_REQUIRE(ctx, loss_type >= 0 && loss_type <= 2 && T > 0.f, "loss: loss_type must be 0 (softmax CE), 1 (euclidean) or 2 (huber), T / sigma > 0");
+  const int grid = (N + 127) / 128;
+#define XEMO_LOSS(TX, TDX)                                                                                                     \
+  loss_fused_kernel<TX, TDX><<<grid, 128, 0, ctx->stream>>>(static_cast<const TX*>(x), ldx, t, ldt, w, N, C, loss_type, T,     \
+                                                           logit_targets, dzdy, grad_scale, static_cast<TDX*>(dx), lddx, scalars, \
+                                                           class_stats, max_label)
+  if (x_f32 && dx_f32) XEMO_LOSS(float, float);
+  else if (x_f32) XEMO_LOSS(float, __half);
+  else if (dx_f32) XEMO_LOSS(__half, float);
+  else XEMO_LOSS(__half, __half);
+#undef XEMO_LOSS
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
 extern "C" int xemo_op_softmaxce(xemo_ctx* ctx, const void* x16, int ldx, const float* t, int ldt, const float* w, int N, int C,
                                  float T, int logit_targets, float dzdy, float grad_scale, void* dx16, float* scalars,
                                  float* class_stats, int* max_label) {
-  XEMO_REQUIRE(ctx, x16 && t && scalars && C <= kLossMaxC && C <= ldx && C <= ldt && T > 0.f, "softmaxce: bad arguments");
-  softmaxce_fused_kernel<<<(N + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const __half*>(x16), ldx, t, ldt, w, N, C, T,
-                                                                  logit_targets, dzdy, grad_scale,
-                                                                  static_cast<__half*>(dx16), scalars, class_stats,
-                                                                  max_label);
+  return xemo_op_loss(ctx, x16, 0, ldx, t, ldt, w, N, C, 0, T, logit_targets, dzdy, grad_scale, dx16, 0, ldx, scalars, class_stats,
+                      max_label);
+}
+
+extern "C" int xemo_op_grad_guard(xemo_ctx* ctx, const float* g, size_t n, int* state) {
+  XEMO_REQUIRE(ctx, g && state, "grad_guard: null pointer");
+  grad_guard_scan_kernel<<<grid_for(n, 256, ctx->num_sms, 8), 256, 0, ctx->stream>>>(g, n, state);
+  grad_guard_publish_kernel<<<1, 1, 0, ctx->stream>>>(state);
+  XEMO_LAUNCHED(ctx, 2);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_sgd_momentum_guarded(xemo_ctx* ctx, float* w, float* m, const float* g, size_t n, const float* hyper,
+                                            float lr_mult, float wd_mult, float inv_grad_scale, void* w16, const int* guard) {
+  XEMO_REQUIRE(ctx, w && m && g && hyper, "sgd_momentum: null pointer");
+  sgd_momentum_dev_kernel<<<grid_for(n, 256, ctx->num_sms, 8), 256, 0, ctx->stream>>>(w, m, g, n, hyper, lr_mult, wd_mult,
+                                                                                     inv_grad_scale,
+                                                                                     static_cast<__half*>(w16), guard);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }
 
 extern "C" int xemo_op_sgd_momentum(xemo_ctx* ctx, float* w, float* m, const float* g, size_t n, const float* hyper,
                                     float lr_mult, float wd_mult, float inv_grad_scale, void* w16) {
-  XEMO_REQUIRE(ctx, w && m && g && hyper, "sgd_momentum: null pointer");
-  sgd_momentum_dev_kernel<<<grid_for(n, 256, ctx->num_sms, 8), 256, 0, ctx->stream>>>(w, m, g, n, hyper, lr_mult, wd_mult,
-                                                                                     inv_grad_scale,
-                                                                                     static_cast<__half*>(w16));
+  return xemo_op_sgd_momentum_guarded(ctx, w, m, g, n, hyper, lr_mult, wd_mult, inv_grad_scale, w16, nullptr);
+}
+
+extern "C" int xemo_op_moments_average_guarded(xemo_ctx* ctx, float* moments, const float* batch_moments, int n, float rate,
+                                               const int* guard) {
+  XEMO_REQUIRE(ctx, moments && batch_moments, "moments_average: null pointer");
+  moments_average_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(moments, batch_moments, n, rate, guard);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }
 
 extern "C" int xemo_op_moments_average(xemo_ctx* ctx, float* moments, const float* batch_moments, int n, float rate) {
-  XEMO_REQUIRE(ctx, moments && batch_moments, "moments_average: null pointer");
-  moments_average_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(moments, batch_moments, n, rate);
-  XEMO_LAUNCHED(ctx, 1);
-  return XEMO_OK;
+  return xemo_op_moments_average_guarded(ctx, moments, batch_moments, n, rate, nullptr);
 }
 
 extern "C" int xemo_op_cast_f32_f16(xemo_ctx* ctx, const float* src, size_t n, void* dst16) {

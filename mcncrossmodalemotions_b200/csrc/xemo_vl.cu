@@ -18,7 +18,8 @@
 using namespace xemo;
 
 int xemo_conv_dgrad_impl(xemo_ctx* ctx, const void* dy16, int N, int H, int W, int Cin, const void* packed16, int Kout, int R,
-                         int S, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16, float* dx32);
+                         int S, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16, float* dx32,
+                         const float* out_scale = nullptr);
 template <typename T>
 int bn_stats_launch(xemo_ctx* ctx, const T* x, size_t P, int C, double* ws);
 
@@ -93,6 +94,106 @@ float* padded_vec(Arena& ar, const float* src, int n, int np, float fill = 0.f) 
   return d;
 }
 
+// ---- split-operand (fp32-equivalent) staging, see hbm_kernels_extra.cuh
+unsigned* absmax_of(Arena& ar, const float* x, size_t n) {
+  unsigned* a = ar.alloc_n<unsigned>(1, true);
+  if (!a) return nullptr;
+  absmax_f32_kernel<<<grid_for(n, 256, ar.ctx->num_sms, 8), 256, 0, ar.ctx->stream>>>(x, n, a);
+  ar.ctx->launches++;
+  return a;
+}
+
+// HWCN fp32 -> (hi|lo|hi) [lo_mask = 2] or (hi|hi|lo) [lo_mask = 4] fp16 NHWC, concatenated along channels or images
+int stage_split(xemo_ctx* ctx, const float* src, int H, int W, int C, int N, __half* dst, int Cp, bool image_concat, int lo_mask,
+                const unsigned* amax) {
+  dim3 block(32, 8), grid((H + 31) / 32, (Cp + 31) / 32, 1);
+  const int per = 65535 / W;
+  const int row_pitch = image_concat ? Cp : 3 * Cp;
+  const size_t slot_stride = image_concat ? size_t(N) * H * W * Cp : size_t(Cp);
+  for (int n0 = 0; n0 < N; n0 += per) {
+    const int nn = N - n0 < per ? N - n0 : per;
+    grid.z = unsigned(nn) * W;
+    hwcn_f32_to_nhwc_split_kernel<<<grid, block, 0, ctx->stream>>>(src + size_t(n0) * H * W * C, H, W, C, nn,
+                                                                   dst + size_t(n0) * H * W * row_pitch, Cp, row_pitch, slot_stride,
+                                                                   lo_mask, amax);
+    XEMO_LAUNCHED(ctx, 1);
+  }
+  return XEMO_OK;
+}
+
+// vl_nnconv with split operands: every product carries ~22 mantissa bits, accumulation in fp32 (TMEM) -- the arithmetic
+// of the reference's single-precision path (MatConvNet CPU: im2row + SGEMM) up to summation order.
+int vl_nnconv_split(xemo_ctx* ctx, Arena& ar, const float* xd, const float* fd, const xemo_array* b, const xemo_array* dzdy,
+                    const int pad[4], const int stride[2], xemo_array* y, xemo_array* dx, xemo_array* df, int H, int W, int C, int N,
+                    int FH, int FW, int K, int OH, int OW) {
+  const int Cp = pad_to(C, 16), Kp = pad_to(K, 16);
+  const size_t nx = size_t(H) * W * C * N, nf = size_t(FH) * FW * C * K, ny = size_t(OH) * OW * K * N;
+  int rc;
+  unsigned* ax = absmax_of(ar, xd, nx);
+  unsigned* af = absmax_of(ar, fd, nf);
+  if (ar.failed) return ar.finish();
+  if (!dzdy || !dzdy->data) {
+    __half* x3 = ar.alloc_n<__half>(size_t(N) * H * W * 3 * Cp);
+    __half* w3 = ar.alloc_n<__half>(size_t(Kp) * FH * FW * 3 * Cp);
+    float* unscale = ar.alloc_n<float>(Kp);
+    const float* bias = (b && b->data) ? padded_vec(ar, static_cast<const float*>(b->data), K, Kp) : nullptr;
+    float* out32 = ar.alloc_n<float>(size_t(N) * OH * OW * Kp);
+    float* yd = static_cast<float*>(ar.out(y->data, ny * 4));
+    if (ar.failed) return ar.finish();
+    if ((rc = stage_split(ctx, xd, H, W, C, N, x3, Cp, false, 2, ax))) return rc;
+    filters_to_krsc_split_kernel<<<grid_for(size_t(3) * Kp * FH * FW * Cp, 256, ctx->num_sms), 256, 0, ctx->stream>>>(fd, FH, FW, C, K, w3, Kp, Cp, 0, af);
+    split_unscale_kernel<<<1, 256, 0, ctx->stream>>>(ax, af, Kp, unscale);
+    XEMO_LAUNCHED(ctx, 2);
+    if ((rc = xemo_op_conv_fwd(ctx, x3, N, H, W, 3 * Cp, w3, Kp, FH, FW, stride[0], stride[1], pad[0], pad[1], pad[2], pad[3], unscale,
+                               bias, nullptr, 0, nullptr, out32, Kp)))
+      return rc;
+    if ((rc = xemo_op_nhwc_to_hwcn(ctx, out32, 1, OH, OW, K, N, Kp, yd))) return rc;
+    return ar.finish();
+  }
+  const float* dyd = static_cast<const float*>(ar.in(dzdy->data, ny * 4));
+  if (ar.failed) return ar.finish();
+  unsigned* ay = absmax_of(ar, dyd, ny);
+  if (ar.failed) return ar.finish();
+  if (dx && dx->data) {
+    // dX = corr(dY, flipped F^T): reduction over the 3*Kp split output channels of dY (hi|lo|hi) x F (hi|hi|lo along K)
+    __half* dy3 = ar.alloc_n<__half>(size_t(N) * OH * OW * 3 * Kp);
+    __half* w3k = ar.alloc_n<__half>(size_t(3) * Kp * FH * FW * Cp);
+    __half* packed = ar.alloc_n<__half>(xemo_dgrad_pack_elems(Cp, 3 * Kp, FH, FW, stride[0], stride[1]));
+    float* unscale = ar.alloc_n<float>(Cp);
+    float* dx32 = ar.alloc_n<float>(size_t(N) * H * W * Cp);
+    float* dxd = static_cast<float*>(ar.out(dx->data, nx * 4));
+    if (ar.failed) return ar.finish();
+    if ((rc = stage_split(ctx, dyd, OH, OW, K, N, dy3, Kp, false, 2, ay))) return rc;
+    filters_to_krsc_split_kernel<<<grid_for(size_t(3) * Kp * FH * FW * Cp, 256, ctx->num_sms), 256, 0, ctx->stream>>>(fd, FH, FW, C, K, w3k, Kp, Cp, 1, af);
+    split_unscale_kernel<<<1, 256, 0, ctx->stream>>>(ay, af, Cp, unscale);
+    XEMO_LAUNCHED(ctx, 2);
+    if ((rc = xemo_op_pack_dgrad_filters(ctx, w3k, 3 * Kp, FH, FW, Cp, stride[0], stride[1], pad[0], pad[2], packed))) return rc;
+    if ((rc = xemo_conv_dgrad_impl(ctx, dy3, N, H, W, Cp, packed, 3 * Kp, FH, FW, stride[0], stride[1], pad[0], pad[1], pad[2], pad[3],
+                                   nullptr, dx32, unscale)))
+      return rc;
+    if ((rc = xemo_op_nhwc_to_hwcn(ctx, dx32, 1, H, W, C, N, Cp, dxd))) return rc;
+  }
+  if (df && df->data) {
+    // dF = sum over pixels of x (x) dY: the three split terms as 3N images, x (hi;lo;hi) against dY (hi;hi;lo)
+    __half* x3 = ar.alloc_n<__half>(size_t(3) * N * H * W * Cp);
+    __half* dy3 = ar.alloc_n<__half>(size_t(3) * N * OH * OW * Kp);
+    float* dF = ar.alloc_n<float>(size_t(Kp) * FH * FW * Cp, true);
+    float* unscale = ar.alloc_n<float>(1);
+    float* dfd = static_cast<float*>(ar.out(df->data, nf * 4));
+    if (ar.failed) return ar.finish();
+    if ((rc = stage_split(ctx, xd, H, W, C, N, x3, Cp, true, 2, ax))) return rc;
+    if ((rc = stage_split(ctx, dyd, OH, OW, K, N, dy3, Kp, true, 4, ay))) return rc;
+    split_unscale_kernel<<<1, 32, 0, ctx->stream>>>(ax, ay, 1, unscale);
+    XEMO_LAUNCHED(ctx, 1);
+    if ((rc = xemo_op_conv_wgrad(ctx, x3, 3 * N, H, W, Cp, dy3, Kp, Kp, FH, FW, stride[0], stride[1], pad[0], pad[1], pad[2], pad[3],
+                                 dF, 1.f)))
+      return rc;
+    krsc_f32_to_filters_kernel<<<grid_for(nf, 256, ctx->num_sms), 256, 0, ctx->stream>>>(dF, FH, FW, C, K, Cp, dfd, unscale);
+    XEMO_LAUNCHED(ctx, 1);
+  }
+  return XEMO_OK;
+}
+
 }  // namespace
 
 extern "C" int xemo_out_size(int64_t h, int64_t w, int fh, int fw, const int pad[4], const int stride[2], int64_t* oh,
@@ -122,56 +223,68 @@ extern "C" int xemo_vl_nnconv(xemo_ctx* ctx, const xemo_array* x, const xemo_arr
   Arena ar(ctx);
   const float* xd = static_cast<const float*>(ar.in(x->data, numel(x) * 4));
   const float* fd = static_cast<const float*>(ar.in(f->data, numel(f) * 4));
-  __half* x16 = ar.alloc_n<__half>(size_t(N) * H * W * Cp);
-  __half* w16 = ar.alloc_n<__half>(size_t(Kp) * FH * FW * Cp);
-  if (ar.failed) return ar.finish();
-  int rc;
-  if ((rc = xemo_op_hwcn_to_nhwc(ctx, xd, H, W, C, N, x16, Cp, 0))) return rc;
-  if ((rc = xemo_op_filters_to_krsc(ctx, fd, FH, FW, C, K, w16, Kp, Cp, 0))) return rc;
-
-  if (!dzdy || !dzdy->data) {
+  const bool backward = dzdy && dzdy->data;
+  if (backward) {
+    XEMO_REQUIRE(ctx, dzdy->h == OH && dzdy->w == OW && dzdy->c == K && dzdy->n == N, "vl_nnconv: DZDY must be %d x %d x %d x %d",
+                 OH, OW, K, N);
+    XEMO_REQUIRE(ctx, !(dx && dx->data) || (dx->h == H && dx->w == W && dx->c == C && dx->n == N), "vl_nnconv: DX must have the size of X");
+    XEMO_REQUIRE(ctx, !(df && df->data) || (df->h == FH && df->w == FW && df->c == C && df->n == K), "vl_nnconv: DF must have the size of F");
+  } else {
     XEMO_REQUIRE(ctx, y && y->data, "vl_nnconv: forward needs Y");
     XEMO_REQUIRE(ctx, y->h == OH && y->w == OW && y->c == K && y->n == N, "vl_nnconv: Y must be %d x %d x %d x %d", OH, OW, K, N);
-    const float* bias = (b && b->data) ? padded_vec(ar, static_cast<const float*>(b->data), K, Kp) : nullptr;
-    float* out32 = ar.alloc_n<float>(size_t(N) * OH * OW * Kp);
-    float* yd = static_cast<float*>(ar.out(y->data, numel(y) * 4));
-    if (ar.failed) return ar.finish();
-    if ((rc = xemo_op_conv_fwd(ctx, x16, N, H, W, Cp, w16, Kp, FH, FW, stride[0], stride[1], pad[0], pad[1], pad[2], pad[3],
-                               nullptr, bias, nullptr, 0, nullptr, out32, Kp)))
-      return rc;
-    if ((rc = xemo_op_nhwc_to_hwcn(ctx, out32, 1, OH, OW, K, N, Kp, yd))) return rc;
-    return ar.finish();
   }
+  const bool split = ctx->conv_precision == 1;
+  if (split) {
+    if (ar.failed) return ar.finish();
+    const int rc = vl_nnconv_split(ctx, ar, xd, fd, b, dzdy, pad, stride, y, dx, df, H, W, C, N, FH, FW, K, OH, OW);
+    if (rc || !backward) return rc;   // (backward: the bias gradient below is shared -- it is fp32 arithmetic on dzdy)
+  }
+  int rc;
+  const float* dyd = backward ? static_cast<const float*>(ar.in(dzdy->data, numel(dzdy) * 4)) : nullptr;
+  if (!split) {
+    __half* x16 = ar.alloc_n<__half>(size_t(N) * H * W * Cp);
+    __half* w16 = ar.alloc_n<__half>(size_t(Kp) * FH * FW * Cp);
+    if (ar.failed) return ar.finish();
+    if ((rc = xemo_op_hwcn_to_nhwc(ctx, xd, H, W, C, N, x16, Cp, 0))) return rc;
+    if ((rc = xemo_op_filters_to_krsc(ctx, fd, FH, FW, C, K, w16, Kp, Cp, 0))) return rc;
 
-  XEMO_REQUIRE(ctx, dzdy->h == OH && dzdy->w == OW && dzdy->c == K && dzdy->n == N, "vl_nnconv: DZDY must be %d x %d x %d x %d",
-               OH, OW, K, N);
-  const float* dyd = static_cast<const float*>(ar.in(dzdy->data, numel(dzdy) * 4));
-  __half* dy16 = ar.alloc_n<__half>(size_t(N) * OH * OW * Kp);
-  if (ar.failed) return ar.finish();
-  if ((rc = xemo_op_hwcn_to_nhwc(ctx, dyd, OH, OW, K, N, dy16, Kp, 0))) return rc;
-  if (dx && dx->data) {
-    XEMO_REQUIRE(ctx, dx->h == H && dx->w == W && dx->c == C && dx->n == N, "vl_nnconv: DX must have the size of X");
-    __half* packed = ar.alloc_n<__half>(xemo_dgrad_pack_elems(Cp, Kp, FH, FW, stride[0], stride[1]));
-    float* dx32 = ar.alloc_n<float>(size_t(N) * H * W * Cp);
-    float* dxd = static_cast<float*>(ar.out(dx->data, numel(dx) * 4));
+    if (!backward) {
+      const float* bias = (b && b->data) ? padded_vec(ar, static_cast<const float*>(b->data), K, Kp) : nullptr;
+      float* out32 = ar.alloc_n<float>(size_t(N) * OH * OW * Kp);
+      float* yd = static_cast<float*>(ar.out(y->data, numel(y) * 4));
+      if (ar.failed) return ar.finish();
+      if ((rc = xemo_op_conv_fwd(ctx, x16, N, H, W, Cp, w16, Kp, FH, FW, stride[0], stride[1], pad[0], pad[1], pad[2], pad[3],
+                                 nullptr, bias, nullptr, 0, nullptr, out32, Kp)))
+        return rc;
+      if ((rc = xemo_op_nhwc_to_hwcn(ctx, out32, 1, OH, OW, K, N, Kp, yd))) return rc;
+      return ar.finish();
+    }
+
+    __half* dy16 = ar.alloc_n<__half>(size_t(N) * OH * OW * Kp);
     if (ar.failed) return ar.finish();
-    if ((rc = xemo_op_pack_dgrad_filters(ctx, w16, Kp, FH, FW, Cp, stride[0], stride[1], pad[0], pad[2], packed))) return rc;
-    if ((rc = xemo_conv_dgrad_impl(ctx, dy16, N, H, W, Cp, packed, Kp, FH, FW, stride[0], stride[1], pad[0], pad[1], pad[2],
-                                   pad[3], nullptr, dx32)))
-      return rc;
-    if ((rc = xemo_op_nhwc_to_hwcn(ctx, dx32, 1, H, W, C, N, Cp, dxd))) return rc;
-  }
-  if (df && df->data) {
-    XEMO_REQUIRE(ctx, df->h == FH && df->w == FW && df->c == C && df->n == K, "vl_nnconv: DF must have the size of F");
-    float* dF = ar.alloc_n<float>(size_t(Kp) * FH * FW * Cp, true);
-    float* dfd = static_cast<float*>(ar.out(df->data, numel(df) * 4));
-    if (ar.failed) return ar.finish();
-    if ((rc = xemo_op_conv_wgrad(ctx, x16, N, H, W, Cp, dy16, Kp, Kp, FH, FW, stride[0], stride[1], pad[0], pad[1], pad[2],
-                                 pad[3], dF, 1.f)))
-      return rc;
-    const size_t total = size_t(FH) * FW * C * K;
-    krsc_f32_to_filters_kernel<<<grid_for(total, 256, ctx->num_sms), 256, 0, ctx->stream>>>(dF, FH, FW, C, K, Cp, dfd);
-    XEMO_LAUNCHED(ctx, 1);
+    if ((rc = xemo_op_hwcn_to_nhwc(ctx, dyd, OH, OW, K, N, dy16, Kp, 0))) return rc;
+    if (dx && dx->data) {
+      __half* packed = ar.alloc_n<__half>(xemo_dgrad_pack_elems(Cp, Kp, FH, FW, stride[0], stride[1]));
+      float* dx32 = ar.alloc_n<float>(size_t(N) * H * W * Cp);
+      float* dxd = static_cast<float*>(ar.out(dx->data, numel(dx) * 4));
+      if (ar.failed) return ar.finish();
+      if ((rc = xemo_op_pack_dgrad_filters(ctx, w16, Kp, FH, FW, Cp, stride[0], stride[1], pad[0], pad[2], packed))) return rc;
+      if ((rc = xemo_conv_dgrad_impl(ctx, dy16, N, H, W, Cp, packed, Kp, FH, FW, stride[0], stride[1], pad[0], pad[1], pad[2],
+                                     pad[3], nullptr, dx32)))
+        return rc;
+      if ((rc = xemo_op_nhwc_to_hwcn(ctx, dx32, 1, H, W, C, N, Cp, dxd))) return rc;
+    }
+    if (df && df->data) {
+      float* dF = ar.alloc_n<float>(size_t(Kp) * FH * FW * Cp, true);
+      float* dfd = static_cast<float*>(ar.out(df->data, numel(df) * 4));
+      if (ar.failed) return ar.finish();
+      if ((rc = xemo_op_conv_wgrad(ctx, x16, N, H, W, Cp, dy16, Kp, Kp, FH, FW, stride[0], stride[1], pad[0], pad[1], pad[2],
+                                   pad[3], dF, 1.f)))
+        return rc;
+      const size_t total = size_t(FH) * FW * C * K;
+      krsc_f32_to_filters_kernel<<<grid_for(total, 256, ctx->num_sms), 256, 0, ctx->stream>>>(dF, FH, FW, C, K, Cp, dfd);
+      XEMO_LAUNCHED(ctx, 1);
+    }
   }
   if (db && db->data) {
     XEMO_REQUIRE(ctx, int64_t(numel(db)) == K, "vl_nnconv: DB must have K elements");

@@ -1,0 +1,217 @@
+"""The student in fp32-equivalent arithmetic: one cnn_train_dag iteration as dagnn would run it -- a chain of the
+MatConvNet-boundary operators (`vl_nn*` on gpuArrays, single, H x W x C x N) -- with the convolutions in the
+split-operand mode of libxemo (XEMO_CONV_F32X3: three tcgen05 products per single-precision product, fp32 accumulation)
+and every other operator in fp32.
+
+This is the parity mode of the hot path: the reference trains in `single` end to end (gpuArray(single) batches,
+emoVoxCeleb/getBatchEmoVoxCeleb.m:197; cnn_train_dag, emoVoxCeleb/run_distillation.m:170-182; loss
+emoVoxCeleb/emoVoxZoo.m:137-157), and the fp16-operand fast programs (programs.StudentProgram) cannot hold a 1e-3
+tolerance on train-mode logits and gradients (ReLU masks / pooling winners flip under 2^-11 perturbations).  Same
+interface as StudentProgram (train_step / grad_step / update / forward / metrics / export_*), no CUDA graphs, activations
+kept as fp32 gpuArrays on the tape; throughput is not the point (bench.py --precision f32x3 reports it beside the fast
+mode).  All arithmetic runs in libxemo.so on the GPU; nothing here computes on the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import vl_nn
+from .programs import BN_EPS, LOSS_TYPES, STUDENT_CONVS, STUDENT_POOLS, _out
+from .vl_nn import GpuArray, gather, gpuArray
+
+VP = C.c_void_p
+
+
+def _ptr(t):
+    return VP(t.data_ptr()) if t is not None else None
+
+
+class StudentProgramF32:
+    def __init__(self, params, batch, width=300, num_classes=8, temperature=2.0, loss_type="hot-cross-ent"):
+        if loss_type not in LOSS_TYPES:
+            raise ValueError("unrecognised regression loss: %s" % (loss_type,))
+        self.ctx = vl_nn.default_context()
+        self.N, self.W, self.K, self.T, self.loss_type = batch, width, num_classes, float(temperature), loss_type
+        self.layers = []
+        h, w = 512, width
+        for name, fh, fw, cin, cout, stride, pad, has_bn in STUDENT_CONVS:
+            cout = num_classes if name == "fc8" else cout
+            oh, ow = _out(h, w, fh, fw, stride, pad)
+            L = dict(name=name, stride=stride, pad=pad, bn="bn" + name[-1] if has_bn else None, pool=None)
+            h, w = oh, ow
+            if name in STUDENT_POOLS:
+                method, win, ps = STUDENT_POOLS[name]
+                win = win or (1, w)      # pool6 averages the whole remaining width (emoVoxZoo.m:258-269)
+                L["pool"] = (method, win, ps)
+                h, w = _out(h, w, win[0], win[1], ps, (0, 0, 0, 0))
+            self.layers.append(L)
+        assert (h, w) == (1, 1), "student graph must reduce to 1 x 1 (got %d x %d)" % (h, w)
+        self.p, self.m, self.moments = {}, {}, {}
+        for k, v in params.items():
+            if k.startswith("bn") and k.endswith("x"):
+                self.moments[k] = np.asarray(v, np.float32).copy()      # C x 2 = [mu sigma]
+            elif isinstance(v, np.ndarray):
+                self.p[k] = gpuArray(v.reshape(-1, 1) if v.ndim == 1 else v)
+                self.m[k] = torch.zeros_like(self.p[k].tensor)
+        dev = self.p["conv1f"].tensor.device
+        self.hyper = torch.tensor([1e-4, 0.9, 5e-4, 1.0 / batch], dtype=torch.float32, device=dev)
+        self.scalars = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.class_stats = torch.zeros(2 * num_classes, dtype=torch.float32, device=dev)
+        self.max_label = torch.zeros(batch, dtype=torch.int32, device=dev)
+        self.weights = torch.ones(batch, dtype=torch.float32, device=dev)
+        self.target = torch.zeros(batch * num_classes, dtype=torch.float32, device=dev)
+        self.grads, self.batch_moments, self.tape = {}, {}, {}
+        self.spec = self.pred = None
+        torch.cuda.synchronize()
+
+    # ---- inputs
+    def set_hyper(self, lr=None, momentum=None, weight_decay=None, batch_size=None):
+        h = self.hyper.cpu().numpy()
+        for i, v in enumerate((lr, momentum, weight_decay, None if batch_size is None else 1.0 / batch_size)):
+            if v is not None:
+                h[i] = v
+        self.hyper.copy_(torch.from_numpy(h))
+        torch.cuda.synchronize()
+
+    def set_input(self, spec, target=None, weights=None):
+        self.spec = spec if isinstance(spec, GpuArray) else gpuArray(spec)
+        if target is not None:
+            if self.loss_type == "softmaxlog":   # maxLabel (1-based) -> one-hot rows
+                lab = np.asarray(target).reshape(-1).astype(np.int64)
+                t = np.zeros((self.N, self.K), np.float32)
+                t[np.arange(self.N), lab - 1] = 1.0
+            else:
+                t = np.ascontiguousarray(np.asarray(target, np.float32).reshape(self.K, self.N).T)
+            self.target.copy_(torch.from_numpy(t.reshape(-1)))
+        if weights is not None:
+            self.weights.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(weights, np.float32).reshape(self.N))))
+        torch.cuda.synchronize()
+
+    # ---- forward / backward as dagnn.DagNN.eval sequences the blocks
+    def _forward(self, train, keep):
+        p, tape = self.p, {}
+        cur = self.spec
+        prev = self.ctx.lib.xemo_get_conv_precision(self.ctx.handle)
+        self.ctx.set_conv_precision(1)
+        try:
+            for L in self.layers:
+                n = L["name"]
+                if keep:
+                    tape[n + ":x"] = cur
+                cur = vl_nn.vl_nnconv(cur, p[n + "f"], p[n + "b"], pad=L["pad"], stride=L["stride"])
+                if L["bn"]:
+                    bn = L["bn"]
+                    if keep:
+                        tape[bn + ":x"] = cur
+                    cur, mom = vl_nn.vl_nnbnorm(cur, p[bn + "m"], p[bn + "b"], epsilon=BN_EPS, moments=None if train else self.moments[bn + "x"])
+                    if train:
+                        self.batch_moments[bn + "x"] = mom
+                    if keep:
+                        tape[bn + ":relu"] = cur
+                    cur = vl_nn.vl_nnrelu(cur)
+                if L["pool"]:
+                    method, win, ps = L["pool"]
+                    if keep:
+                        tape[n + ":pool"] = cur
+                    cur = vl_nn.vl_nnpool(cur, win, stride=ps, method=method)
+        finally:
+            self.ctx.set_conv_precision(prev)
+        self.tape = tape
+        self.pred = cur      # 1 x 1 x K x N == [N][K] row-major
+        return cur
+
+    def _loss(self, backward):
+        lt, soft = LOSS_TYPES[self.loss_type], self.loss_type == "hot-cross-ent"
+        dpred = GpuArray(self.pred.shape, torch.empty_like(self.pred.tensor)) if backward else None
+        torch.cuda.synchronize()
+        self.ctx.memset(_ptr(self.scalars), 0, 8)
+        self.ctx.op_loss(VP(self.pred.ptr), 1, self.K, _ptr(self.target), self.K, _ptr(self.weights) if lt else None, self.N, self.K, lt,
+                         self.T if soft else 1.0, 1 if soft else 0, 1.0, 1.0, VP(dpred.ptr) if backward else None, 1, self.K,
+                         _ptr(self.scalars), _ptr(self.class_stats), _ptr(self.max_label))
+        return dpred
+
+    def _backward(self, dzdy):
+        p, tape, g = self.p, self.tape, {}
+        cur = dzdy
+        prev = self.ctx.lib.xemo_get_conv_precision(self.ctx.handle)
+        self.ctx.set_conv_precision(1)
+        try:
+            for L in reversed(self.layers):
+                n = L["name"]
+                if L["pool"]:
+                    method, win, ps = L["pool"]
+                    cur = vl_nn.vl_nnpool(tape[n + ":pool"], win, cur, stride=ps, method=method)
+                if L["bn"]:
+                    bn = L["bn"]
+                    cur = vl_nn.vl_nnrelu(tape[bn + ":relu"], cur)
+                    cur, dg, db, _ = vl_nn.vl_nnbnorm(tape[bn + ":x"], p[bn + "m"], p[bn + "b"], cur, epsilon=BN_EPS)
+                    g[bn + "m"], g[bn + "b"] = gpuArray(dg.reshape(-1, 1)), gpuArray(db.reshape(-1, 1))
+                dx, df, dbias = vl_nn.vl_nnconv(tape[n + ":x"], p[n + "f"], p[n + "b"], cur, pad=L["pad"], stride=L["stride"])
+                g[n + "f"], g[n + "b"] = df, dbias
+                cur = dx
+        finally:
+            self.ctx.set_conv_precision(prev)
+        self.grads = g
+        self.tape = {}
+
+    # ---- StudentProgram interface
+    def forward(self, spec, mode="test"):
+        """dag.eval({'data', spec}) -> N x K numpy predictions."""
+        self.set_input(spec)
+        pred = self._forward(mode != "test", keep=False)
+        return gather(pred).reshape(self.K, self.N).T.copy()
+
+    def grad_step(self):
+        self._forward(True, keep=True)
+        self._backward(self._loss(True))
+
+    def update(self):
+        """cnn_train_dag accumulateGradients: m <- mu m - (wd w + g / B); w <- w + lr m; BN moments moving average."""
+        for k, w in self.p.items():
+            gk = self.grads[k]
+            self.ctx.op_sgd_momentum(VP(w.ptr), _ptr(self.m[k]), VP(gk.ptr), w.tensor.numel(), _ptr(self.hyper), 1.0, 1.0, 1.0, None)
+        self.ctx.sync()
+        for k, mom in self.batch_moments.items():
+            # (2 x C numbers per layer; the fast program's moments_average kernel computes the same expression)
+            dev = gpuArray(self.moments[k]), gpuArray(mom)
+            self.ctx.op_moments_average(VP(dev[0].ptr), VP(dev[1].ptr), dev[0].tensor.numel(), 0.1)
+            self.moments[k] = gather(dev[0]).reshape(self.moments[k].shape)
+
+    def train_step(self, spec, target, allreduce=None, weights=None):
+        self.set_input(spec, target, weights)
+        self.grad_step()
+        if allreduce is not None:
+            for k in self.grads:
+                allreduce(self.grads[k].tensor)
+        self.update()
+
+    def reset_metrics(self):
+        self.ctx.memset(_ptr(self.scalars), 0, 8)
+        self.ctx.memset(_ptr(self.class_stats), 0, 8 * self.K)
+
+    def metrics(self):
+        self.ctx.sync()
+        s, cs = self.scalars.cpu(), self.class_stats.cpu()
+        return dict(objective=float(s[0]), classerror=float(s[1]), correct=cs[: self.K].numpy(), count=cs[self.K :].numpy())
+
+    def prediction(self):
+        return gather(self.pred).reshape(self.K, self.N).T.copy()
+
+    def _export(self, d):
+        out = {}
+        for k, v in d.items():
+            a = gather(v)
+            out[k] = a.copy() if k.endswith("f") else a.reshape(-1).copy()   # filters FH x FW x FC x K; vectors flat
+        return out
+
+    def export_params(self):
+        out = self._export(self.p)
+        out.update({k: v.copy() for k, v in self.moments.items()})
+        return out
+
+    def export_grads(self):
+        out = self._export(self.grads)
+        out.update({k: v.copy() for k, v in self.batch_moments.items()})
+        return out

@@ -24,6 +24,7 @@ import torch
 from . import _lib
 
 BN_EPS = 1e-5  # dagnn.BatchNorm default
+LOSS_TYPES = {"hot-cross-ent": 0, "softmaxlog": 0, "euclidean": 1, "huber": 2}   # -> loss_type of xemo_op_loss
 VP = C.c_void_p
 
 # VGGVox student: name, FH, FW, Cin, Cout, stride, pad, has_bn
@@ -335,9 +336,10 @@ class StudentProgram(_Base):
         (getBatchEmoVoxCeleb.m:162-169) then run on the device ahead of the graph."""
         # emoVoxZoo.m:137-157: 'hot-cross-ent' = SoftmaxCELoss(temperature, logitTargets) on {prediction, logitTarget};
         # 'softmaxlog' = dagnn.Loss('softmaxlog') on {prediction, maxLabel}, i.e. the same cross-entropy against a one-hot
-        # distribution at T = 1 (the fused kernel's logit_targets = 0 mode).  'euclidean' / 'huber' are not on the hot path.
-        if loss_type not in ("hot-cross-ent", "softmaxlog"):
-            raise NotImplementedError("loss type %r is not on the hot path (hot-cross-ent, softmaxlog)" % (loss_type,))
+        # distribution at T = 1 (the fused kernel's logit_targets = 0 mode); 'euclidean' = dagnn.EuclideanLoss and
+        # 'huber' = dagnn.HuberLoss('sigma', 1) on {prediction, logitTarget, instanceWeights} -- all one fused kernel.
+        if loss_type not in LOSS_TYPES:
+            raise ValueError("unrecognised regression loss: %s" % (loss_type,))   # emoVoxZoo.m:154
         super().__init__(device, stream, ctx)
         self.audio_input = audio_input
         self.loss_type = loss_type
@@ -363,10 +365,6 @@ class StudentProgram(_Base):
         # Rides on the stem path (its pooling kernels take a pooled-side pitch).  XEMO_CONV2_PAD=0 disables.
         self.conv2_pad = self.stem_algebra and os.environ.get("XEMO_CONV2_PAD", "1") != "0"
         self.stem_wgrad_pairs = os.environ.get("XEMO_STEM_WGRAD_PAIRS", "0") != "0"
-        # EXPERIMENTAL, off by default, not yet measured: run conv1 -> pool1 (and pool1-backward -> conv1 filter gradient) in
-        # sub-batches of this many clips through the first images of the conv1 buffers, so that the 1.85 GB activation /
-        # gradient is produced and consumed out of the 126 MB L2 instead of HBM (8 clips = 58 MB).  Same kernels, same results.
-        self.stem_chunk = int(os.environ.get("XEMO_STEM_CHUNK", "0")) if (self.stem_algebra and not self.stem_wgrad_pairs) else 0
         self.side_stream = None   # torch.cuda.Stream: filter gradients run there, off the dgrad critical path
         self._geometry()
         self._load(params)
@@ -441,6 +439,8 @@ class StudentProgram(_Base):
                 self.moments[bn] = self.upload(np.concatenate([m[:, 0], m[:, 1]]))
                 self.batch_moments[bn] = self.f32(2 * L["cout"])
         self.hyper = self.upload(np.array([1e-4, 0.9, 5e-4, 1.0 / self.N], np.float32))
+        with torch.cuda.stream(self.stream):
+            self.guard = torch.zeros(3, dtype=torch.int32, device=self.device)   # xemo_op_grad_guard state
 
     def view(self, buf, name):
         o, shape = self.segs[name]
@@ -461,6 +461,8 @@ class StudentProgram(_Base):
         if self.stem_algebra:
             A["stem:ws"] = torch.zeros(int(self.ctx.lib.xemo_stem_ws_doubles()), dtype=torch.float64, device=self.device)
         A["target"] = self.f32(N, self.K)                        # aggregated teacher logits
+        with torch.cuda.stream(self.stream):
+            A["weights"] = torch.ones(N, dtype=torch.float32, device=self.device)   # instanceWeights (getBatchEmoVoxCeleb.m:37)
         for L in self.layers:
             n = L["name"]
             A[n + ":raw"] = self.f16(N, L["oh"], L["ow"], L["kp"])
@@ -505,10 +507,6 @@ class StudentProgram(_Base):
             n = L["name"]
             wt, bias = self.view(self.w16, n + "f"), self.view(self.master, n + "b")
             last = n == "fc8"
-            if n == "conv1" and self.stem_chunk > 0:
-                self._stem_forward_chunked(L, wt, bias)
-                cur = A[n + ":out"]
-                continue
             if n == "conv1":
                 self._stem_conv(wt, None, bias, 0, A[n + ":raw"])
             else:
@@ -560,22 +558,6 @@ class StudentProgram(_Base):
                 ctx.op_tile_f32(_p(scale), kp, 2, 1.0, _p(A["stem:scale2"]))
         self.conv(x, N, self.s2d_hp, self.s2d_ow // 2, 32, A["stem:w2"], 2 * kp, 4, 1, (1, 1), (0, 0, 0, 0),
                   A["stem:scale2"] if scale is not None else None, A["stem:shift2"], None, relu, dst)
-
-    def _stem_forward_chunked(self, L, wt, bias):
-        """EXPERIMENTAL (XEMO_STEM_CHUNK): statistics first (they come from the patch autocorrelation, not from the
-        activation), then conv1 -> pool1 per sub-batch through the head of the conv1 buffer (L2-resident)."""
-        N, A, ctx, n = self.N, self.a, self.ctx, "conv1"
-        P = L["pool"]
-        g, beta = self.view(self.master, "bn1m"), self.view(self.master, "bn1b")
-        ctx.op_stem_bn_train(_p(A["stem:ws"]), _p(wt), _p(bias), N * L["oh"] * L["ow"], L["cout"], _p(g), _p(beta), BN_EPS,
-                             _p(self.batch_moments["bn1"]), _p(A[n + ":a"]), _p(A[n + ":b"]))
-        for i0 in range(0, N, self.stem_chunk):
-            nb = min(self.stem_chunk, N - i0)
-            raw = A[n + ":raw"][:nb]
-            self._stem_conv(wt, None, bias, 0, raw, x=A["s2d"][i0 : i0 + nb], n=nb, prepare=(i0 == 0))
-            ctx.op_maxpool_fwd_win(_p(raw), nb, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1], P["stride"][0], P["stride"][1],
-                                   0, 0, 0, 0, _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":out"][i0 : i0 + nb]),
-                                   _p(A[n + ":arg"][i0 : i0 + nb]), _p(A[n + ":xwin"][i0 : i0 + nb]), self.pool1_ld)
 
     def _record_forward_test(self):
         """dag.mode = 'test' (external/compute_audio_feats.m:106): BN uses the stored moments, so it folds -- together
@@ -638,9 +620,12 @@ class StudentProgram(_Base):
             ctx.memset(_p(self.grad), 0, self.nparam * 4)
             ctx.memset(_p(A["fc8:draw"]), 0, A["fc8:draw"].numel() * 2)
             ctx.memset(_p(A["scalars"]), 0, 8)  # objective / classerror of THIS batch (class_stats keep accumulating)
-            soft = self.loss_type == "hot-cross-ent"
-            ctx.op_softmaxce(_p(A["fc8:raw"]), last["kp"], _p(A["target"]), self.K, None, N, self.K, self.T if soft else 1.0,
-                             1 if soft else 0, 1.0, gs, _p(A["fc8:draw"]), _p(A["scalars"]), _p(A["class_stats"]), _p(A["max_label"]))
+            soft, lt = self.loss_type == "hot-cross-ent", LOSS_TYPES[self.loss_type]
+            # the loss reads the fp32 logits the fc8 convolution writes beside its fp16 output (T of the non-softmax losses:
+            # huber's sigma = 1, emoVoxZoo.m:146)
+            ctx.op_loss(_p(A["pred32"]), 1, last["kp"], _p(A["target"]), self.K, _p(A["weights"]) if lt else None, N, self.K, lt,
+                        self.T if soft else 1.0, 1 if soft else 0, 1.0, gs, _p(A["fc8:draw"]), 0, last["kp"], _p(A["scalars"]),
+                        _p(A["class_stats"]), _p(A["max_label"]))
         for i in range(hi - 1, lo - 1, -1):
             L = self.layers[i]
             n = L["name"]
@@ -655,9 +640,8 @@ class StudentProgram(_Base):
                 ld = self.pool1_ld
                 ctx.op_stem_pool_bn_reduce(_p(A[n + ":xwin"]), _p(A[n + ":dout"]), prow, L["cout"], ld, _p(self.batch_moments[bn]),
                                            _p(A[n + ":a"]), _p(A[n + ":b"]), _p(A[n + ":ws"]))
-                if self.stem_chunk == 0:
-                    ctx.op_maxpool_bwd_ld(_p(A[n + ":dout"]), _p(A[n + ":arg"]), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1],
-                                          P["stride"][0], P["stride"][1], 0, 0, 0, 0, _p(A[n + ":draw"]), ld)
+                ctx.op_maxpool_bwd_ld(_p(A[n + ":dout"]), _p(A[n + ":arg"]), N, L["oh"], L["ow"], L["cout"], P["win"][0], P["win"][1],
+                                      P["stride"][0], P["stride"][1], 0, 0, 0, 0, _p(A[n + ":draw"]), ld)
                 fused_bias = True
             elif L["bn"]:
                 bn = "bn" + n[-1]
@@ -699,16 +683,6 @@ class StudentProgram(_Base):
                     ctx.memset(_p(g1p), 0, g1p.numel() * 4)
                     ctx.op_conv_wgrad(_p(x), N, self.s2d_hp, self.s2d_ow // 2, 32, _p(dy), 2 * L["kp"], 2 * L["kp"], 4, 1, 1, 1,
                                       0, 0, 0, 0, _p(g1p), inv)
-                elif self.stem_chunk > 0:
-                    # EXPERIMENTAL: pool1 backward -> filter gradient per sub-batch through the head of the dz buffer
-                    g1p, P = None, L["pool"]
-                    for i0 in range(0, N, self.stem_chunk):
-                        nb = min(self.stem_chunk, N - i0)
-                        ctx.op_maxpool_bwd_ld(_p(A[n + ":dout"][i0 : i0 + nb]), _p(A[n + ":arg"][i0 : i0 + nb]), nb, L["oh"], L["ow"],
-                                              L["cout"], P["win"][0], P["win"][1], P["stride"][0], P["stride"][1], 0, 0, 0, 0,
-                                              _p(A[n + ":draw"][:nb]), self.pool1_ld)
-                        ctx.op_conv_wgrad(_p(A["s2d"][i0 : i0 + nb]), nb, self.s2d_hp, self.s2d_ow, 16, _p(A[n + ":draw"][:nb]), L["kp"],
-                                          L["kp"], 4, 1, 1, 1, 0, 0, 0, 0, _p(gf), inv)
                 else:
                     g1p = None
                     ctx.op_conv_wgrad(_p(x), N, self.s2d_hp, self.s2d_ow, 16, _p(dy), L["kp"], L["kp"], 4, 1, 1, 1, 0, 0, 0, 0, _p(gf), inv)
@@ -750,9 +724,14 @@ class StudentProgram(_Base):
         this graph (dag.initParams defaults), so the whole flat master buffer is updated by ONE launch that also
         refreshes the fp16 mirror the tensor-core kernels read (alignment padding stays zero: g = w = m = 0)."""
         ctx = self.ctx
-        ctx.op_sgd_momentum(_p(self.master), _p(self.momentum), _p(self.grad), self.nparam, _p(self.hyper), 1.0, 1.0, 1.0, _p(self.w16))
+        # the activation gradients travel in fp16 under a fixed loss scale: a non-finite element in the (all-reduced) flat
+        # gradient sets the guard, the update of this step is skipped and counted (metrics()['skipped_steps'])
+        guard = _p(self.guard)
+        ctx.op_grad_guard(_p(self.grad), self.nparam, guard)
+        ctx.op_sgd_momentum_guarded(_p(self.master), _p(self.momentum), _p(self.grad), self.nparam, _p(self.hyper), 1.0, 1.0, 1.0,
+                                    _p(self.w16), guard)
         for bn, m in self.moments.items():
-            ctx.op_moments_average(_p(m), _p(self.batch_moments[bn]), m.numel(), 0.1)
+            ctx.op_moments_average_guarded(_p(m), _p(self.batch_moments[bn]), m.numel(), 0.1, guard)
 
     # ---- graph plumbing
     def _run(self, key, record):
@@ -777,8 +756,9 @@ class StudentProgram(_Base):
         with torch.cuda.stream(self.stream):
             self.hyper.copy_(torch.from_numpy(h))
 
-    def set_input(self, spec, target=None):
-        """spec: 512 x W x 1 x N spectrograms, or N x L waveforms when audio_input == 'wav'."""
+    def set_input(self, spec, target=None, weights=None):
+        """spec: 512 x W x 1 x N spectrograms, or N x L waveforms when audio_input == 'wav'; target: logitTarget
+        (1 x 1 x K x N) or maxLabel (softmaxlog); weights: instanceWeights 1 x 1 x 1 x N (euclidean / huber)."""
         key = "wav" if self.audio_input == "wav" else "spec"
         if isinstance(spec, np.ndarray):
             if key == "wav":
@@ -798,6 +778,9 @@ class StudentProgram(_Base):
                 elif isinstance(target, np.ndarray):
                     target = torch.from_numpy(np.ascontiguousarray(target.astype(np.float32).reshape(self.K, self.N).T))
                 self.a["target"].copy_(target.reshape(self.N, self.K), non_blocking=True)
+            if weights is not None:
+                self.a["weights"].copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(weights, np.float32).reshape(self.N))),
+                                        non_blocking=True)
 
     def forward(self, spec, mode="test"):
         """dag.eval({'data', spec}) -> N x K numpy predictions."""
@@ -845,10 +828,10 @@ class StudentProgram(_Base):
         self.ctx.memset(_p(self.a["scalars"]), 0, 8)
         self.ctx.memset(_p(self.a["class_stats"]), 0, 8 * self.K)
 
-    def train_step(self, spec, target, allreduce=None):
+    def train_step(self, spec, target, allreduce=None, weights=None):
         """One cnn_train_dag iteration.  `allreduce(flat_grad_tensor)` (optional) sums gradients across
         data-parallel ranks between the backward pass and the update."""
-        self.set_input(spec, target)
+        self.set_input(spec, target, weights)
         self.grad_step()
         if allreduce is not None:
             with torch.cuda.stream(self.stream):
@@ -859,8 +842,10 @@ class StudentProgram(_Base):
         with torch.cuda.stream(self.stream):
             s = self.a["scalars"].cpu()
             cs = self.a["class_stats"].cpu()
+            gd = self.guard.cpu()
         self.sync()
-        return dict(objective=float(s[0]), classerror=float(s[1]), correct=cs[: self.K].numpy(), count=cs[self.K :].numpy())
+        return dict(objective=float(s[0]), classerror=float(s[1]), correct=cs[: self.K].numpy(), count=cs[self.K :].numpy(),
+                    nonfinite_grad=bool(gd[0]), skipped_steps=int(gd[1]))
 
     # ---- export in MatConvNet layouts (parity checks, checkpoints)
     def _export(self, buf):
@@ -904,6 +889,24 @@ class StudentProgram(_Base):
         for bn, m in self.moments.items():
             c = m.numel() // 2
             out[bn + "x"] = m.cpu().numpy().reshape(2, c).T.copy()
+        return out
+
+    def export_decisions(self):
+        """The discrete decisions of the last train-mode forward, in MatConvNet layout (H x W x C x N): the ReLU masks
+        `a x + b > 0` the backward kernels recompute from the raw convolution outputs ('relu<i>') and the uint8 window-local
+        arg-max dw*PH + dh of every max pool ('pool<i>').  Diagnostics / parity tests: running a reference backward under
+        these decisions separates arithmetic error from decision flips."""
+        self.sync()
+        out = {}
+        for L in self.layers:
+            n, i = L["name"], L["name"][-1]
+            if not L["bn"]:
+                continue
+            raw = self.a[n + ":raw"].cpu().numpy()[..., : L["cout"]].astype(np.float32)
+            a, b = self.a[n + ":a"].cpu().numpy(), self.a[n + ":b"].cpu().numpy()
+            out["relu" + i] = np.transpose(a * raw + b > 0, (1, 2, 3, 0))
+            if L["pool"] and L["pool"]["method"] == "max":
+                out["pool" + i] = np.transpose(self.a[n + ":arg"].cpu().numpy()[..., : L["cout"]], (1, 2, 3, 0))
         return out
 
     def export_grads(self):

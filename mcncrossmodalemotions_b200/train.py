@@ -103,7 +103,7 @@ def cnn_train_dag(params, imdb, get_batch, *, learning_rate, batch_size=64, num_
         for it in range(steps):
             idx = order[it * batch_size : (it + 1) * batch_size][rank::world]   # labindex:numlabs:end
             inputs = get_batch(imdb, idx)
-            prog.train_step(inputs["data"], inputs[tkey], allreduce)
+            prog.train_step(inputs["data"], inputs[tkey], allreduce, weights=inputs.get("instanceWeights"))
             m = prog.metrics()   # objective / classerror of this batch; class counters accumulate
             obj += m["objective"]; err += m["classerror"]; seen += len(idx)
         m = prog.metrics()
@@ -160,8 +160,6 @@ def run_distillation(imdb, get_batch, root="data/xEmo18", **overrides):
     opts.update(overrides)
     opts["miniEpochRatio"] = extra.get("miniEpochRatio", 0.05 * len(opts["gpus"]))
     opts["learningRate"] = extra.get("learningRate", learning_rate_schedule(opts["numEpochs"]))
-    if opts["lossType"] not in ("hot-cross-ent", "softmaxlog"):
-        raise NotImplementedError("loss type %r is not on the hot path (hot-cross-ent, softmaxlog)" % (opts["lossType"],))
     exp_dir = os.path.join(root, exp_dir_name(opts["teacher"], opts["student"], opts["lossType"], opts["numSeconds"],
                                               opts["numPredEmotions"], opts["logitAggregator"], opts["temperature"], opts["fromScratch"]))
     os.makedirs(exp_dir, exist_ok=True)

@@ -90,7 +90,7 @@ class _Block:
         self.__dict__.update(attrs)
 
     def isa(self, cls):
-        loss_family = ("dagnn.Loss", "dagnn.SoftmaxCELoss", "dagnn.VerboseLoss", "dagnn.ErrorStats")
+        loss_family = ("dagnn.Loss", "dagnn.SoftmaxCELoss", "dagnn.EuclideanLoss", "dagnn.HuberLoss", "dagnn.VerboseLoss", "dagnn.ErrorStats")
         return self.type == cls or (cls == "dagnn.Loss" and self.type in loss_family)
 
 
@@ -147,8 +147,19 @@ class Model:
                     self._add(pool[0], _Block("dagnn.Pooling", method=pool[1], poolSize=tuple(pool[2]), stride=pool[3], pad=(0, 0, 0, 0)),
                               [prev], ["x_" + pool[0]])
                     prev = "x_" + pool[0]
-            if loss_type == "hot-cross-ent":   # configureForRegression, emoVoxZoo.m:151-169
-                self._add("loss", _Block("dagnn.SoftmaxCELoss", temperature=2, logitTargets=True), ["prediction", "logitTarget"], ["objective"])
+            if loss_type is not None:   # configureForRegression, emoVoxZoo.m:137-169
+                if loss_type == "hot-cross-ent":
+                    self._add("loss", _Block("dagnn.SoftmaxCELoss", temperature=2, logitTargets=True), ["prediction", "logitTarget"], ["objective"])
+                elif loss_type == "softmaxlog":
+                    self._add("loss", _Block("dagnn.Loss", loss="softmaxlog"), ["prediction", "maxLabel"], ["objective"])
+                elif loss_type == "euclidean":
+                    self._add("loss", _Block("dagnn.EuclideanLoss"), ["prediction", "logitTarget", "instanceWeights"], ["objective"])
+                    # "scale down a lot to prevent exploding gradients" (emoVoxZoo.m:141-144): the head filters / 10
+                    self.params["fc8f"] = (self.params["fc8f"] / 10).astype(self.params["fc8f"].dtype)
+                elif loss_type == "huber":
+                    self._add("loss", _Block("dagnn.HuberLoss", sigma=1), ["prediction", "logitTarget", "instanceWeights"], ["objective"])
+                else:
+                    raise ValueError("unrecognised regression loss: %s" % loss_type)
                 self._add("error", _Block("dagnn.VerboseLoss", loss="classerror"), ["prediction", "maxLabel"], ["classerror"])
                 self._add("errorStats", _Block("dagnn.ErrorStats", numClasses=8), ["prediction", "maxLabel"], ["errorStats"])
         else:

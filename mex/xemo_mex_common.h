@@ -20,9 +20,15 @@ static void xm_at_exit(void) { if (g_ctx) { xemo_destroy(g_ctx); g_ctx = NULL; }
 
 static xemo_ctx* xm_ctx(void) {
   if (!g_ctx) {
+    int dev = 0;
     mxInitGPU();
-    /* NULL stream: the library creates its own; MEX calls that return CPU arrays synchronise inside the library */
-    if (xemo_create(0 /* the device gpuDevice() selected is device 0 of this process' visible set */, NULL, &g_ctx))
+    /* The device MATLAB selected (gpuDevice(opts.gpus(labindex)) under cnn_train_dag's spmd) is the CUDA runtime's
+     * current device of this thread.  The context runs on MATLAB's own stream -- the legacy default stream, which is what
+     * gpuArray arithmetic uses -- so that the library's kernels are ordered after the producers of its gpuArray inputs and
+     * before the consumers of its gpuArray outputs without any extra synchronisation; calls that return CPU arrays
+     * synchronise inside the library. */
+    xemo_current_device(&dev);
+    if (xemo_create(dev, XEMO_STREAM_LEGACY, &g_ctx))
       mexErrMsgIdAndTxt("xemo:nodevice", "libxemo needs an sm_100 (B200) device; there is no CPU fallback");
     mexAtExit(xm_at_exit);
   }

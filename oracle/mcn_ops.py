@@ -118,7 +118,7 @@ def vl_nnconv(x, f, b=None, dzdy=None, pad=0, stride=1):
 #   external/compute_audio_feats.m:121-125.
 
 
-def vl_nnpool(x, pool, dzdy=None, pad=0, stride=1, method="max", return_index=False):
+def vl_nnpool(x, pool, dzdy=None, pad=0, stride=1, method="max", return_index=False, index=None):
     """Max / average pooling.
 
     max: padding behaves as -inf.  The backward pass routes dzdy to the FIRST element attaining the
@@ -127,6 +127,8 @@ def vl_nnpool(x, pool, dzdy=None, pad=0, stride=1, method="max", return_index=Fa
     avg: divides by the number of in-bounds elements of the window.
     `return_index` (forward, max only) additionally returns the window-local arg-max index
     idx = dw * PH + dh as uint8 -- the quantity the CUDA kernels emit and the tests compare exactly.
+    `index` (backward, max only; test instrumentation): route dzdy through THESE window-local indices instead of the
+    arg-max of x -- the oracle's arithmetic under another implementation's discrete choices.
     """
     x = np.asarray(x)
     H, W, C, N = x.shape
@@ -149,6 +151,8 @@ def vl_nnpool(x, pool, dzdy=None, pad=0, stride=1, method="max", return_index=Fa
         if dzdy is None:
             return (best, arg) if return_index else best
         dzdy = np.asarray(dzdy)
+        if index is not None:
+            arg = np.asarray(index).reshape(arg.shape)
         dxp = np.zeros(xp.shape, dtype=dzdy.dtype)
         for dw in range(PW):
             for dh in range(PH):
@@ -321,6 +325,34 @@ def vl_nnsoftmaxceloss(x, p, dzdy=None, temperature=1.0, logitTargets=False, ins
         return (w * (-(p * logq).sum(axis=2, keepdims=True))).sum()
     q = np.exp(logq)
     return np.asarray(dzdy) * w * (q - p) / T
+
+
+def vl_nneuclideanloss(x, t, dzdy=None, instanceWeights=None):
+    """dagnn.EuclideanLoss -> vl_nneuclideanloss [UPSTREAM mcnExtraLayers, restated from recollection; wired at
+    /root/reference/emoVoxCeleb/emoVoxZoo.m:138-144 on {prediction, logitTarget, instanceWeights}].
+    forward : y = 1/2 * sum(w .* (x - t).^2)      (w broadcast over dims 1-3: getBatchEmoVoxCeleb.m:37 passes 1 x 1 x 1 x N)
+    backward: dx = dzdy * w .* (x - t)"""
+    x = np.asarray(x)
+    d = x - np.asarray(t, dtype=x.dtype)
+    w = 1.0 if instanceWeights is None else np.asarray(instanceWeights, dtype=x.dtype).reshape(1, 1, 1, -1)
+    if dzdy is None:
+        return 0.5 * (w * d * d).sum()
+    return np.asarray(dzdy) * w * d
+
+
+def vl_nnhuberloss(x, t, dzdy=None, sigma=1.0, instanceWeights=None):
+    """dagnn.HuberLoss('sigma', s) -> vl_nnhuberloss [UPSTREAM mcnExtraLayers, restated from recollection: the smooth-L1
+    of Fast R-CNN; wired at /root/reference/emoVoxCeleb/emoVoxZoo.m:145-147].  With s2 = sigma^2 and d = x - t:
+    forward : y = sum w .* ( |d| - 0.5/s2  where |d| > 1/s2,  0.5*s2*d^2 elsewhere )
+    backward: dx = dzdy * w .* ( sign(d)   where |d| > 1/s2,  s2*d       elsewhere )"""
+    x = np.asarray(x)
+    d = x - np.asarray(t, dtype=x.dtype)
+    w = 1.0 if instanceWeights is None else np.asarray(instanceWeights, dtype=x.dtype).reshape(1, 1, 1, -1)
+    s2 = float(sigma) ** 2
+    lin = np.abs(d) > 1.0 / s2
+    if dzdy is None:
+        return (w * np.where(lin, np.abs(d) - 0.5 / s2, 0.5 * s2 * d * d)).sum()
+    return np.asarray(dzdy) * w * np.where(lin, np.sign(d), s2 * d)
 
 
 def vl_nnloss(x, c, dzdy=None, loss="classerror"):

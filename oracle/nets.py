@@ -207,18 +207,27 @@ def student_forward(p, x, mode="train", ops=NumpyOps, keep=False):
     return cur, tape
 
 
-def student_backward(p, tape, dzdy, ops=NumpyOps):
+def student_backward(p, tape, dzdy, ops=NumpyOps, relu_masks=None, pool_index=None):
     """Reverse sweep (derOutputs = {'objective', 1}).  Returns the gradient dict keyed like `p`
-    (BN moments entries hold the batch moments, which cnn_train_dag averages in)."""
+    (BN moments entries hold the batch moments, which cnn_train_dag averages in).
+    Test instrumentation: `relu_masks` {'relu<i>': bool H x W x C x N} and `pool_index` {'pool<i>': uint8 window-local
+    indices} replace the oracle's own discrete decisions (x > 0, first arg-max) by another implementation's, so that
+    what remains of a gradient difference is arithmetic, not decision flips."""
     g = {}
     cur = dzdy
     for name, fh, fw, cin, cout, stride, pad, has_bn in reversed(STUDENT_CONVS):
         if name in STUDENT_POOLS:
             pname, method, _, pstride = STUDENT_POOLS[name]
-            cur = ops.pool(tape[pname + ":x"], tape[pname + ":win"], cur, pad=0, stride=pstride, method=method)
+            if pool_index is not None and pname in pool_index:
+                cur = M.vl_nnpool(tape[pname + ":x"], tape[pname + ":win"], cur, pad=0, stride=pstride, method=method, index=pool_index[pname])
+            else:
+                cur = ops.pool(tape[pname + ":x"], tape[pname + ":win"], cur, pad=0, stride=pstride, method=method)
         if has_bn:
             bn = "bn" + name[-1]
-            cur = ops.relu(tape["relu" + name[-1] + ":x"], cur)
+            if relu_masks is not None and "relu" + name[-1] in relu_masks:
+                cur = cur * relu_masks["relu" + name[-1]]
+            else:
+                cur = ops.relu(tape["relu" + name[-1] + ":x"], cur)
             cur, dg, db, mom = ops.bnorm(tape[bn + ":x"], p[bn + "m"], p[bn + "b"], cur, epsilon=BN_EPS)
             g[bn + "m"], g[bn + "b"], g[bn + "x"] = dg, db, mom
         dx, df, dbias = ops.conv(tape[name + ":x"], p[name + "f"], p[name + "b"], cur, pad=pad, stride=stride)
@@ -253,16 +262,28 @@ def sgd_momentum(p, state, g, lr, batch_size, momentum=0.9, weight_decay=5e-4, b
     return p, state
 
 
-def distillation_student_step(p, state, spec, logit_target, lr=1e-4, T=2.0, ops=NumpyOps, update=True):
+def distillation_student_step(p, state, spec, logit_target, lr=1e-4, T=2.0, ops=NumpyOps, update=True, loss_type="hot-cross-ent",
+                              instance_weights=None):
     """One cnn_train_dag iteration on the student (emoVoxCeleb/run_distillation.m:170-182) with the
-    loss wired at emoVoxCeleb/emoVoxZoo.m:151-157.  logit_target: 1 x 1 x 8 x N teacher logits.
-    Returns dict(prediction, objective, classerror, grads)."""
+    loss wired at emoVoxCeleb/emoVoxZoo.m:137-157 (`loss_type`: hot-cross-ent [default, :151-152], softmaxlog, euclidean,
+    huber).  logit_target: 1 x 1 x 8 x N teacher logits.  Returns dict(prediction, objective, classerror, grads)."""
     N = spec.shape[3]
     pred, tape = student_forward(p, spec, "train", ops, keep=True)
-    objective = M.vl_nnsoftmaxceloss(pred, logit_target, temperature=T, logitTargets=True)
     max_label = logit_target.argmax(axis=2).reshape(1, 1, 1, N) + 1  # getBatchEmoVoxCeleb.m:32
+    one = np.array(1.0, pred.dtype)
+    if loss_type == "hot-cross-ent":
+        loss = lambda *dz: M.vl_nnsoftmaxceloss(pred, logit_target, *dz, temperature=T, logitTargets=True)
+    elif loss_type == "softmaxlog":
+        loss = lambda *dz: M.vl_nnloss(pred, max_label, *dz, loss="softmaxlog")
+    elif loss_type == "euclidean":
+        loss = lambda *dz: M.vl_nneuclideanloss(pred, logit_target, *dz, instanceWeights=instance_weights)
+    elif loss_type == "huber":
+        loss = lambda *dz: M.vl_nnhuberloss(pred, logit_target, *dz, sigma=1.0, instanceWeights=instance_weights)
+    else:
+        raise ValueError("unrecognised regression loss: %s" % loss_type)
+    objective = loss()
     classerror = M.vl_nnloss(pred, max_label, loss="classerror")
-    dpred = M.vl_nnsoftmaxceloss(pred, logit_target, np.array(1.0, pred.dtype), temperature=T, logitTargets=True)
+    dpred = loss(one)
     grads = student_backward(p, tape, dpred.astype(pred.dtype), ops)
     if update:
         sgd_momentum(p, state, grads, lr, N)

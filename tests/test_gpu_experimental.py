@@ -13,29 +13,6 @@ pytestmark = [pytest.mark.gpu_experimental,
               pytest.mark.skipif(os.environ.get("XEMO_EXPERIMENTAL") != "1", reason="experimental GPU option: set XEMO_EXPERIMENTAL=1")]
 
 
-def test_stem_chunking_reproduces_the_whole_batch_step():
-    """XEMO_STEM_CHUNK: conv1 -> pool1 and pool1-backward -> wgrad per sub-batch (L2-resident) use the same kernels on
-    slices: identical activations, gradients equal up to the summation order of the filter-gradient atomics."""
-    from oracle import nets
-    from mcncrossmodalemotions_b200.programs import StudentProgram
-
-    n, width = 12, 100
-    p = nets.student_randomize_bn(nets.student_init())
-    spec, tgt = nets.synth_spectrograms(n, width), nets.synth_teacher_logits(n)
-    out = []
-    for chunk in (0, 5):        # 5 does not divide 12: exercises the tail sub-batch
-        prog = StudentProgram(p, n, width, use_graph=False)
-        prog.stem_chunk = chunk
-        prog.reset_metrics()
-        prog.set_input(spec, tgt)
-        prog.grad_step()
-        out.append((prog.export_grads(), prog.metrics()))
-    (g0, m0), (g1, m1) = out
-    assert m0["objective"] == m1["objective"]
-    for k in g0:
-        assert rel_err(g1[k], g0[k]) < 1e-4, k
-
-
 @pytest.mark.parametrize("n", [8, 5])
 def test_se_blocks_by_linearity_match_the_default_path_and_the_oracle(n):
     """XEMO_SE_LIN: squeeze(t2) -> gate (W3 folded in) -> expand convolution with the excite in its epilogue

@@ -198,6 +198,12 @@ def test_batch_assembly_matches_reference_rules():
     with pytest.raises(ValueError):
         B.get_batch([spec], [lg], [(0, 1)], loss_type="nope")
     assert B.width_bucket(1234) == 1000 and B.width_bucket(399) == 300 and B.centre_crop(spec, 100).shape == (512, 100)
+    # compute_audio_feats.m:183-186: rstart = round(d / 2) (1-based, 0 -> 1): W = 450 -> columns 25..424 (1-based), i.e.
+    # 0-based 24..423; d = 0, 1, 2, 3 -> 0-based starts 0, 0, 0, 1
+    cols = np.arange(450, dtype=np.float32)[None, :].repeat(2, 0)
+    assert B.centre_crop(cols, 400)[0, 0] == 24 and B.centre_crop(cols, 400)[0, -1] == 423
+    for d, start in ((0, 0), (1, 0), (2, 0), (3, 1), (4, 1), (5, 2)):
+        assert B.centre_crop(cols[:, : 400 + d], 400)[0, 0] == start, d
     with pytest.raises(ValueError):
         B.width_bucket(50)
 
@@ -347,11 +353,23 @@ def test_conv_plans_respect_the_hardware_budgets(n):
             assert groups * T >= R * S * c_tiles and splits >= 1 and 1 <= wgrid <= 148, name
 
 
-def test_unsupported_loss_types_fail_loudly_before_touching_the_device():
-    """emoVoxZoo.m:137-150 also offers 'euclidean' and 'huber'; they are not on the hot path and must not silently
-    train with another loss."""
+def test_loss_types_of_the_zoo():
+    """emoVoxZoo.m:137-157: four loss types; 'euclidean' scales the head filters by 1/10 (:141-144); anything else is
+    rejected before the device is touched."""
+    from mcncrossmodalemotions_b200 import zoo
     from mcncrossmodalemotions_b200.programs import StudentProgram
 
-    for lt in ("euclidean", "huber", "nonsense"):
-        with pytest.raises(NotImplementedError):
-            StudentProgram({}, 4, 100, loss_type=lt)
+    with pytest.raises(ValueError):
+        StudentProgram({}, 4, 100, loss_type="nonsense")
+    with pytest.raises(ValueError):
+        zoo.emoVoxZoo("emovoxceleb-student", scratch=True, lossType="nonsense")
+    base = zoo.emoVoxZoo("emovoxceleb-student", scratch=True, lossType="hot-cross-ent")
+    for lt, block, inputs in (("euclidean", "dagnn.EuclideanLoss", ["prediction", "logitTarget", "instanceWeights"]),
+                              ("huber", "dagnn.HuberLoss", ["prediction", "logitTarget", "instanceWeights"]),
+                              ("softmaxlog", "dagnn.Loss", ["prediction", "maxLabel"])):
+        dag = zoo.emoVoxZoo("emovoxceleb-student", scratch=True, lossType=lt)
+        layer = dag.layers[dag.getLayerIndex("loss")]
+        assert layer.block.type == block and layer.inputs == inputs and layer.outputs == ["objective"]
+        scale = 0.1 if lt == "euclidean" else 1.0
+        np.testing.assert_allclose(dag.params["fc8f"], base.params["fc8f"] * scale, rtol=1e-6)
+        np.testing.assert_array_equal(dag.params["fc7f"], base.params["fc7f"])

@@ -159,6 +159,27 @@ def test_softmaxceloss_gradient_is_q_minus_p_over_T():
         M.vl_nnsoftmaxceloss(x, tl)  # targets that are not distributions are rejected
 
 
+def test_euclidean_and_huber_losses_known_answers_and_gradients():
+    """emoVoxZoo.m:138-147: dagnn.EuclideanLoss / dagnn.HuberLoss('sigma', 1) on {prediction, logitTarget, instanceWeights}."""
+    x = np.array([0.0, 3.0, -2.0, 0.5]).reshape(1, 1, 4, 1)
+    t = np.array([0.0, 1.0, 0.0, 0.0]).reshape(1, 1, 4, 1)
+    assert np.isclose(M.vl_nneuclideanloss(x, t), 0.5 * (4 + 4 + 0.25))
+    # smooth-L1, sigma = 1: |d| - 0.5 beyond 1, d^2 / 2 inside
+    assert np.isclose(M.vl_nnhuberloss(x, t), (2 - 0.5) + (2 - 0.5) + 0.125)
+    assert np.allclose(M.vl_nnhuberloss(x, t, 1.0).reshape(-1), [0, 1, -1, 0.5])
+    # sigma = 2: knee at 1/4, slope 4 d inside, |d| - 1/8 outside
+    assert np.isclose(M.vl_nnhuberloss(x, t, sigma=2.0), (2 - 0.125) * 2 + (0.5 - 0.125))
+    rng = np.random.default_rng(6)
+    x, t = rng.standard_normal((1, 1, 8, 5)) * 2, rng.standard_normal((1, 1, 8, 5))
+    w = rng.uniform(0.5, 2, (1, 1, 1, 5))
+    for f in (M.vl_nneuclideanloss, M.vl_nnhuberloss):
+        num = numgrad(lambda v: np.array(f(v, t, instanceWeights=w)), x.copy(), 1.0)
+        assert np.allclose(f(x, t, 1.0, instanceWeights=w), num, atol=1e-5)
+        # per-sample weights broadcast over the classes; unit weights are the default
+        assert np.isclose(f(x, t, instanceWeights=np.ones(5)), f(x, t))
+        assert np.isclose(f(x, t, instanceWeights=3 * np.ones(5)), 3 * f(x, t))
+
+
 def test_classerror_and_error_stats():
     x = np.zeros((1, 1, 3, 4)); x[0, 0, 2, 0] = 1; x[0, 0, 0, 1] = 1; x[0, 0, 1, 2] = 1  # sample 3: all-equal -> class 1
     c = np.array([3, 1, 1, 1])
