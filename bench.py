@@ -9,7 +9,19 @@
 One step = SENet50-ferplus teacher forward on a batch of 48x48 uint8 faces (preprocessing fused on the
 device) -> max-aggregation of the frame logits -> VGGVox student forward + backward on 512x300
 spectrograms with the T=2 softmax cross-entropy -> (all-reduce of the 16.6 M-parameter gradient over
-NCCL when N > 1) -> SGD-momentum update.  Weak scaling: every rank processes `--per-gpu-batch` pairs.
+NCCL when N > 1) -> SGD-momentum update.
+
+Scaling.  BASELINE.json's headline configuration (C4) is ONE batch of 256 pairs split over the GPUs
+(cnn_train_dag gives lab i the samples batch(i:numlabs:end), emoVoxCeleb/run_distillation.m:75,179-181), so the
+default is STRONG scaling: `--global-batch 256`, 256 / N pairs per GPU.  The weak-scaling measurement (256 pairs
+on every GPU) runs in the same process when N > 1 and is reported under "weak_scaling"; `--scaling weak` makes it
+the headline instead.
+
+Other BASELINE configs: `--config c2` (ResNet50 teacher forward, 256 x 224 x 224 x 3), `--config c3` (student
+forward + backward + update, batch 128 @512x300), `--config c5` (embedding sweeps, batch 64...1024).
+At N = 1 the line also carries "parity_mode": the student step of the same workload in the fp32-equivalent mode
+(split-operand convolutions, parity.StudentProgramF32 -- the configuration whose gradients meet 1e-3), beside the
+fp16-operand fast mode the headline is measured in.
 
 `value`  : pairs/s with the step inputs already resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same metric through DistillationStep.step_host with pinned HOST buffers: H2D of the uint8
@@ -183,49 +195,464 @@ def synth_inputs(batch, rank):
     return torch.from_numpy(faces.reshape(-1)).pin_memory(), torch.from_numpy(spec.reshape(-1)).pin_memory()
 
 
-def cpu_step_seconds(pairs, threads):
-    """One distillation step of the CPU restatement (oracle port) on `pairs` face+audio pairs."""
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_seconds(config, units, threads, teacher="senet50"):
+    """One pass of `config` through the CPU restatement (oracle port, fp32 torch CPU kernels) on `units` samples."""
     import torch
 
     from oracle import nets
 
     torch.set_num_threads(threads)
-    tp, sp = nets.teacher_init("senet50"), nets.student_init()
-    faces = nets.faces48_to_input(nets.synth_faces48(pairs))
-    spec = nets.synth_spectrograms(pairs, WIDTH)
-    t0 = time.perf_counter()
-    logits = nets.teacher_forward(tp, faces, nets.TorchOps)
-    target = np.stack([nets.aggregate_logits(logits[0, 0, :, i][None, :]) for i in range(pairs)], axis=1).reshape(1, 1, 8, pairs)
-    nets.distillation_student_step(sp, {}, spec, target.astype(np.float32), lr=1e-4, ops=nets.TorchOps)
+    if config == "c4":
+        tp, sp = nets.teacher_init(teacher), nets.student_init()
+        faces = nets.faces48_to_input(nets.synth_faces48(units))
+        spec = nets.synth_spectrograms(units, WIDTH)
+        t0 = time.perf_counter()
+        logits = nets.teacher_forward(tp, faces, nets.TorchOps)
+        target = np.stack([nets.aggregate_logits(logits[0, 0, :, i][None, :]) for i in range(units)], axis=1).reshape(1, 1, 8, units)
+        nets.distillation_student_step(sp, {}, spec, target.astype(np.float32), lr=1e-4, ops=nets.TorchOps)
+    elif config == "c2":
+        tp = nets.teacher_init("resnet50")
+        faces = nets.synth_faces(units)
+        t0 = time.perf_counter()
+        nets.teacher_forward(tp, faces, nets.TorchOps)
+    elif config == "c3":
+        sp = nets.student_init()
+        spec, tgt = nets.synth_spectrograms(units, WIDTH), nets.synth_teacher_logits(units)
+        t0 = time.perf_counter()
+        nets.distillation_student_step(sp, {}, spec, tgt, lr=1e-4, ops=nets.TorchOps)
+    else:   # c5: one face through the teacher and one clip through the student in test mode, per unit
+        tp, sp = nets.teacher_init("senet50"), nets.student_randomize_bn(nets.student_init())
+        faces, spec = nets.synth_faces(units), nets.synth_spectrograms(units, WIDTH)
+        t0 = time.perf_counter()
+        nets.teacher_forward(tp, faces, nets.TorchOps)
+        nets.student_forward(sp, spec, "test", nets.TorchOps)
     return time.perf_counter() - t0
 
 
+CONFIGS = {
+    "c4": dict(metric=METRIC, unit=UNIT,
+               workload="full distillation step: %s-ferplus teacher fwd (48x48 uint8 faces -> 224x224x3) + VGGVox student "
+                        "fwd+bwd @512x300 + T=2 softmax CE + SGD-momentum"),
+    "c2": dict(metric="ResNet50-ferplus teacher forward faces/sec", unit="faces/s",
+               workload="ResNet50-ferplus teacher forward (test-mode BN folded), 224x224x3 single faces"),
+    "c3": dict(metric="VGGVox student step clips/sec", unit="clips/s",
+               workload="VGGVox student forward + backward + T=2 softmax CE + SGD-momentum on 512x300 spectrograms"),
+    "c5": dict(metric="embedding extraction samples/sec (SENet50 face logits + VGGVox audio logits)", unit="samples/s",
+               workload="compute_visual_feats / compute_audio_feats: SENet50 forward on 224x224x3 faces and VGGVox test-mode "
+                        "forward on 512x300 spectrograms, one face + one clip per sample"),
+}
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (no MATLAB here -> the oracle port), all host threads."""
+    """--impl reference: the reference's CPU path (no MATLAB here -> the oracle port), all host threads, rank 0 only."""
     if rank != 0:
         return
+    cfg = CONFIGS[args.config]
     threads = os.cpu_count() or 1
-    t_probe = cpu_step_seconds(1, threads)
+    t_probe = cpu_seconds(args.config, 1, threads, args.teacher)
     budget = 150.0 / max(1, args.steps + args.warmup)
-    pairs = int(max(1, min(8, budget / max(t_probe, 1e-3))))
+    units = int(max(1, min(8, budget / max(t_probe, 1e-3))))
     for _ in range(args.warmup):
-        cpu_step_seconds(pairs, threads)
+        cpu_seconds(args.config, units, threads, args.teacher)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step_seconds(pairs, threads)
+        cpu_seconds(args.config, units, threads, args.teacher)
     dt = time.perf_counter() - t0
-    value = pairs * args.steps / dt
-    sample = "%d face+audio pair(s) per step (SENet50 fwd + VGGVox fwd/bwd + T-softmax CE + SGD), fp32, torch CPU kernels" % pairs
+    value = units * args.steps / dt
+    sample = "%d sample(s) per step of: %s; fp32, torch CPU kernels behind the MatConvNet operator semantics" % (
+        units, cfg["workload"] % args.teacher if "%s" in cfg["workload"] else cfg["workload"])
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "full distillation step (SENet50 teacher fwd + VGGVox student fwd/bwd @512x300 + T=2 softmax CE + SGD)",
-                   "pairs_per_step": pairs, "spectrogram": "512x300", "faces": "48x48 uint8 -> 224x224x3"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["workload"] % args.teacher if "%s" in cfg["workload"] else cfg["workload"],
+                   "samples_per_step": units, "spectrogram": "512x300", "faces": "48x48 uint8 -> 224x224x3" if args.config == "c4" else "224x224x3"},
+        "cpu_baseline": {"value": value, "unit": cfg["unit"], "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm helpers
+class Dist:
+    """rank / world plumbing: barrier + max-over-ranks timing as the bench contract asks."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.allreduce = (lambda g: dist.all_reduce(g)) if self.world > 1 else None
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def timed_loop(D, stream, fn, steps, warmup):
+    """`warmup` untimed + `steps` timed calls of fn between barriers; CUDA events on `stream`; max over ranks (ms total)."""
+    torch = D.torch
+    for _ in range(warmup):
+        fn()
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    D.barrier()
+    return D.max_over_ranks(e0.elapsed_time(e1))
+
+
+def measure_step(D, args, B, global_batch, clocks=None, with_e2e=True):
+    """Resident and end-to-end timing of the distillation step at per-GPU batch B.  Returns (step, dict)."""
+    import torch
+
+    from mcncrossmodalemotions_b200 import zoo
+    from mcncrossmodalemotions_b200.distill import DistillationStep
+
+    step = DistillationStep(zoo.teacher_init(args.teacher), zoo.student_init(), B, WIDTH, device=D.local)
+    step.student.set_hyper(lr=1e-4, momentum=0.9, weight_decay=5e-4, batch_size=global_batch)
+    faces_h, spec_h = synth_inputs(B, D.rank)
+    step.prefetch(faces_h, spec_h)
+    step.step_host(D.allreduce)
+    step.sync()
+    run = lambda: step.step_resident(D.allreduce)
+    for _ in range(args.warmup):
+        run()
+    D.barrier()
+    t0 = clocks.mark() if clocks else None
+    c0 = step.ctx.launch_count()
+    ms_res = timed_loop(D, step.stream, run, args.steps, 0)
+    launches = step.ctx.launch_count() - c0
+    out = dict(ms_res=ms_res, launches=launches)
+    if with_e2e:
+        # end to end: pinned host buffers -> H2D -> step -> D2H loss, every step (copies of step i+1 overlap step i)
+        for _ in range(2):
+            step.prefetch(faces_h, spec_h)
+            step.step_host(D.allreduce)
+        D.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(step.stream)
+        step.prefetch(faces_h, spec_h)
+        for i in range(args.steps):
+            step.step_host(D.allreduce)
+            if i + 1 < args.steps:
+                step.prefetch(faces_h, spec_h)
+        e1.record(step.stream)
+        D.barrier()
+        out["ms_e2e"] = D.max_over_ranks(e0.elapsed_time(e1))
+    if clocks:
+        t1 = clocks.mark()
+        # a short timed region (few steps, many GPUs sharing one nvidia-smi) can end before a 200 ms sample lands inside it:
+        # keep the same step running (untimed) until two samples have been taken under this load
+        extra = 0
+        for _ in range(50):
+            need = 1.0 if (clocks.proc and clocks.count_between(t0, t1) < 2) else 0.0
+            if D.max_over_ranks(need) == 0.0:   # collective decision: every rank runs the same number of extra steps
+                break
+            for _ in range(8):
+                run()
+            extra += 8
+            D.barrier()
+            t1 = clocks.mark()
+        clk = clocks.stop(t0, t1)
+        clk["extra_load_steps"] = extra
+        out["clocks"] = clk
+    out["loss"] = float(step.loss_host[0])
+    return step, out
+
+
+def graph_ms(D, ctx, stream, record, iters=5):
+    """Capture `record()` into a CUDA graph and time its replay (ms per launch)."""
+    torch = D.torch
+    record()
+    ctx.capture_begin()
+    record()
+    g = ctx.capture_end()
+    g.launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iters):
+        g.launch()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    g.destroy()
+    return ms
+
+
+def conv_roofline(D, step, B, ms_step):
+    """All tcgen05 convolution launches of one step, timed one by one (instrumented eager pass), plus the fractions
+    north_star names: whole step, teacher forward alone, student step alone (graph replays)."""
+    import torch
+
+    prof = ConvProfiler(step.stream)
+    step.use_graph = False
+    side, step.side, step.student.side_stream = step.side, None, None   # per-op timing needs one stream
+    step.grad_step()  # warm
+    step.sync()
+    step.ctx.profiler = prof
+    with torch.cuda.stream(step.stream):
+        step.grad_step()
+    step.ctx.profiler = None
+    fl, t, n_launch, by = prof.summary()
+    t_ms = graph_ms(D, step.ctx, step.stream, step.teacher._record)
+    s_ms = graph_ms(D, step.ctx, step.stream, lambda: (step.student._record_forward(True), step.student._record_backward(),
+                                                         step.student._record_update()))
+    step.use_graph = True
+    step.side, step.student.side_stream = side, side
+    peaks = measured_peaks()
+    peak = peaks["tflops_sustained"]
+    achieved = fl / t / 1e12
+    frac_of = lambda gflop_per, ms: B * gflop_per / ms / peak   # GFLOP / ms == TFLOP/s
+    arch = step.teacher.arch
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None, "traffic_note": "dram__bytes of the conv launches: profiles/r02_conv_traffic.json (ncu capture, not measured in this run)",
+            "kernel": "conv_fprop_kernel / conv_wgrad_kernel (tcgen05): all %d convolution launches of one step" % n_launch,
+            "launches_per_step": n_launch, "conv_ms_per_step": t * 1e3, "by_op": by,
+            "step_frac": frac_of(GFLOP_TEACHER[arch] + GFLOP_STUDENT_FWD_BWD, ms_step),
+            "teacher_forward": {"ms": t_ms, "tflops": B * GFLOP_TEACHER[arch] / t_ms, "frac": frac_of(GFLOP_TEACHER[arch], t_ms)},
+            "student_step": {"ms": s_ms, "tflops": B * GFLOP_STUDENT_FWD_BWD / s_ms, "frac": frac_of(GFLOP_STUDENT_FWD_BWD, s_ms)},
+            "peak_source": peaks["source"] + ", sustained bf16", "operand_dtype": "fp16 x fp16 -> fp32 (TMEM)"}
+
+
+def cpu_baseline(args, config, units):
+    threads = os.cpu_count() or 1
+    cpu_seconds(config, 1, threads, args.teacher)  # warm
+    dt = cpu_seconds(config, units, threads, args.teacher)
+    cfg = CONFIGS[config]
+    return {"value": units / dt, "unit": cfg["unit"], "cores": threads, "kind": "port",
+            "sample": "1 pass over %d sample(s) of the same workload, fp32 torch CPU kernels, %.1f s" % (units, dt)}
+
+
+def parity_mode_rate(D, args, B=32, steps=2):
+    """The student step of the same workload in the fp32-equivalent mode (split-operand convolutions, fp32 storage)."""
+    import torch
+
+    from mcncrossmodalemotions_b200 import zoo
+    from mcncrossmodalemotions_b200.parity import StudentProgramF32
+
+    rng = np.random.default_rng(5)
+    spec = rng.standard_normal((512, WIDTH, 1, B)).astype(np.float32)
+    tgt = (3 * rng.standard_normal((1, 1, 8, B))).astype(np.float32)
+    prog = StudentProgramF32(zoo.student_init(), B, WIDTH)
+    prog.set_input(spec, tgt)
+    prog.grad_step(); prog.update(); prog.ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        prog.grad_step(); prog.update()
+    prog.ctx.sync()
+    dt = (time.perf_counter() - t0) / steps
+    del prog
+    torch.cuda.empty_cache()
+    return {"value": B / dt, "unit": "clips/s", "dtype": "f32 (fp16 x 3 split operands, fp32 accumulate / storage)", "batch": B,
+            "ms_per_step": dt * 1e3, "what": "student forward + backward + update through the vl_nn* boundary operators "
+            "(parity.StudentProgramF32); the configuration that meets 1e-3 on gradients, tests/test_gpu_parity.py"}
+
+
+# ------------------------------------------------------------------------------------------------ configs
+def run_c4(args, D):
+    world = D.world
+    strong = args.scaling == "strong"
+    if strong:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch %d is not divisible by %d ranks" % (args.global_batch, world))
+        B = args.global_batch // world
+    else:
+        B = args.per_gpu_batch
+    clocks = ClockSampler(D.local)
+    clocks.start()   # nvidia-smi needs a few hundred ms to come up: started ahead of the warm-up, rows are time-stamped
+    step, m = measure_step(D, args, B, B * world, clocks)
+    roof = conv_roofline(D, step, B, m["ms_res"] / args.steps) if D.rank == 0 else None
+    D.barrier()
+    kernels = step.num_kernels()
+    h2d, d2h = step.h2d_bytes, step.d2h_bytes
+    del step
+    D.torch.cuda.empty_cache()
+    other = None
+    if world > 1 and not args.single_line:
+        # the other scaling mode in the same process: weak (256 pairs on every GPU) beside the strong headline, or vice versa
+        B2 = args.per_gpu_batch if strong else args.global_batch // world
+        if B2 != B and B2 >= 1:
+            step2, m2 = measure_step(D, args, B2, B2 * world, None, with_e2e=False)
+            other = {"scaling": "weak" if strong else "strong", "value": B2 * world * args.steps / (m2["ms_res"] * 1e-3), "unit": UNIT,
+                     "ms_per_step": m2["ms_res"] / args.steps, "per_gpu_batch": B2, "global_batch": B2 * world}
+            del step2
+            D.torch.cuda.empty_cache()
+    cpu = parity = None
+    if D.rank == 0 and world == 1:
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline(args, "c4", args.cpu_pairs)
+        if not args.no_parity_mode:
+            parity = parity_mode_rate(D, args)
+    D.barrier()
+    if D.rank == 0:
+        total = B * world * args.steps
+        value = total / (m["ms_res"] * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": m["ms_res"] / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": CONFIGS["c4"]["workload"] % args.teacher, "global_batch": B * world, "per_gpu_batch": B,
+                       "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (%.1f GB of activations per GPU) exceeds the 126 MB L2; no flush needed" % (0.045 * B),
+                       "gflop_per_pair": GFLOP_PAIR, "achieved_tflops_per_gpu": value / world * GFLOP_PAIR / 1e3},
+            "e2e": {"value": total / (m["ms_e2e"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": m["ms_e2e"] / args.steps},
+            "gpu_launches": int(m["launches"]), "kernels_per_step": kernels, "loss": m["loss"],
+            "clocks": m["clocks"], "roofline": roof, "cpu_baseline": cpu,
+        }
+        if other:
+            line["%s_scaling" % other["scaling"]] = other
+        if parity:
+            line["parity_mode"] = parity
+        print(json.dumps(line))
+
+
+def run_single_program(args, D):
+    """c2 / c3 / c5: one program per rank (replicas: no collective except c3's gradient all-reduce)."""
+    import torch
+
+    from mcncrossmodalemotions_b200 import zoo
+    from mcncrossmodalemotions_b200.programs import StudentProgram, TeacherProgram
+
+    cfg = CONFIGS[args.config]
+    peaks = measured_peaks()
+    peak = peaks["tflops_sustained"]
+    clocks = ClockSampler(D.local)
+    clocks.start()
+    rng = np.random.default_rng(100 + D.rank)
+    extra = {}
+    if args.config == "c2":
+        B = args.batch or 256
+        prog = TeacherProgram(zoo.teacher_init("resnet50"), B, device=D.local)
+        host = torch.from_numpy((rng.uniform(0, 255, B * 3 * 224 * 224) - 110.0).astype(np.float32)).pin_memory()
+        out_host = torch.zeros(B, 16).pin_memory()
+        prog.set_input(host); prog.run(); prog.sync()
+        run = prog.run
+
+        def run_e2e():
+            prog.set_input(host)
+            prog.run()
+            with torch.cuda.stream(prog.stream):
+                out_host.copy_(prog.a["logits"], non_blocking=True)
+        gflop, h2d, d2h, stream, ctx = GFLOP_TEACHER["resnet50"], host.numel() * 4, out_host.numel() * 4, prog.stream, prog.ctx
+    elif args.config == "c3":
+        B = args.batch or 128
+        prog = StudentProgram(zoo.student_init(), B, WIDTH, device=D.local)
+        prog.set_hyper(lr=1e-4, batch_size=B * D.world)
+        _, spec_h = synth_inputs(B, D.rank)
+        tgt_h = torch.from_numpy((3 * rng.standard_normal((B, 8))).astype(np.float32)).pin_memory()
+        loss_host = torch.zeros(2).pin_memory()
+        prog.set_input(spec_h, tgt_h)
+
+        def run():
+            prog.grad_step()
+            if D.allreduce is not None:
+                with torch.cuda.stream(prog.stream):
+                    D.allreduce(prog.grad)
+            prog.update()
+
+        def run_e2e():
+            prog.set_input(spec_h, tgt_h)
+            run()
+            with torch.cuda.stream(prog.stream):
+                loss_host.copy_(prog.a["scalars"], non_blocking=True)
+        run(); prog.sync()
+        gflop, h2d, d2h, stream, ctx = GFLOP_STUDENT_FWD_BWD, spec_h.numel() * 4 + tgt_h.numel() * 4, 8, prog.stream, prog.ctx
+    else:   # c5 sweep: per batch size, teacher forward + student test-mode forward
+        sweep = {}
+        for B in (64, 128, 256, 512, 1024):
+            tprog = TeacherProgram(zoo.teacher_init("senet50"), B, device=D.local)
+            tprog.run(); tprog.sync()
+            t_ms = timed_loop(D, tprog.stream, tprog.run, 5, 3) / 5
+            del tprog
+            torch.cuda.empty_cache()
+            sprog = StudentProgram(zoo.student_init(), B, WIDTH, device=D.local)
+            f = lambda: sprog._run("fwd_test", lambda: sprog._record_forward(False))
+            f(); sprog.sync()
+            s_ms = timed_loop(D, sprog.stream, f, 5, 3) / 5
+            del sprog
+            torch.cuda.empty_cache()
+            sweep["batch %d" % B] = {"teacher_ms": t_ms, "teacher_faces_per_s": B * D.world / t_ms * 1e3, "teacher_frac": B * GFLOP_TEACHER["senet50"] / t_ms / peak,
+                                     "student_ms": s_ms, "student_clips_per_s": B * D.world / s_ms * 1e3, "student_frac": B * 5.662228992 / s_ms / peak,
+                                     "samples_per_s": B * D.world / (t_ms + s_ms) * 1e3}
+        extra["sweep"] = sweep
+        B = args.batch or 256
+        tprog = TeacherProgram(zoo.teacher_init("senet50"), B, device=D.local)
+        sprog = StudentProgram(zoo.student_init(), B, WIDTH, device=D.local, stream=tprog.stream, ctx=tprog.ctx)
+        host_f = torch.from_numpy((rng.uniform(0, 255, B * 3 * 224 * 224) - 110.0).astype(np.float32)).pin_memory()
+        _, host_s = synth_inputs(B, D.rank)
+        out_host = torch.zeros(2, B, 16).pin_memory()
+        ftest = lambda: sprog._run("fwd_test", lambda: sprog._record_forward(False))
+        tprog.run(); ftest(); tprog.sync()
+
+        def run():
+            tprog.run()
+            ftest()
+
+        def run_e2e():
+            tprog.set_input(host_f)
+            sprog.set_input(host_s)
+            run()
+            with torch.cuda.stream(tprog.stream):
+                out_host[0].copy_(tprog.a["logits"], non_blocking=True)
+                out_host[1].copy_(sprog.a["pred32"], non_blocking=True)
+        gflop, h2d, d2h, stream, ctx = GFLOP_TEACHER["senet50"] + 5.662228992, (host_f.numel() + host_s.numel()) * 4, out_host.numel() * 4, tprog.stream, tprog.ctx
+        prog = tprog
+    for _ in range(args.warmup):
+        run()
+    D.barrier()
+    t0 = clocks.mark()
+    c0 = ctx.launch_count()
+    ms = timed_loop(D, stream, run, args.steps, 0)
+    launches = ctx.launch_count() - c0
+    ms_e2e = timed_loop(D, stream, run_e2e, args.steps, 2)
+    clk = clocks.stop(t0, clocks.mark())
+    cpu = cpu_baseline(args, args.config, min(args.cpu_pairs, 4)) if (D.rank == 0 and D.world == 1 and not args.no_cpu_baseline) else None
+    D.barrier()
+    if D.rank == 0:
+        total = B * D.world * args.steps
+        value = total / (ms * 1e-3)
+        tfl = B * gflop / (ms / args.steps)
+        line = {"metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": D.world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+                "data": "synthetic",
+                "config": {"workload": cfg["workload"], "name": args.config, "per_gpu_batch": B, "global_batch": B * D.world,
+                           "parallelism": "replicas x%d" % D.world if args.config != "c3" else "dp%d" % D.world,
+                           "l2": "activations of one pass exceed the 126 MB L2; no flush needed"},
+                "e2e": {"value": total / (ms_e2e * 1e-3), "unit": cfg["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clk,
+                "roofline": {"bound": "tensor", "achieved": tfl, "peak": peak, "unit": "TFLOP/s", "frac": tfl / peak, "traffic": None,
+                             "kernel": "whole pass (all kernels) against the tensor peak: the quantity north_star names",
+                             "peak_source": peaks["source"] + ", sustained bf16"},
+                "cpu_baseline": cpu}
+        line.update(extra)
+        print(json.dumps(line))
 
 
 def main():
@@ -234,158 +661,34 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--per-gpu-batch", type=int, default=256)
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--global-batch", type=int, default=256, help="strong scaling: the batch split over the ranks (BASELINE C4)")
+    ap.add_argument("--per-gpu-batch", type=int, default=256, help="weak scaling: pairs per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="c2 / c3 / c5: per-GPU batch (default: the BASELINE size)")
     ap.add_argument("--teacher", default="senet50", choices=["senet50", "resnet50"])
-    ap.add_argument("--cpu-pairs", type=int, default=4, help="pairs in the bounded cpu_baseline sample")
+    ap.add_argument("--cpu-pairs", type=int, default=4, help="samples in the bounded cpu_baseline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-mode", action="store_true")
+    ap.add_argument("--single-line", action="store_true", help="skip the other scaling mode's measurement when N > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
         return
 
     import torch
-    import torch.distributed as dist
-
-    from mcncrossmodalemotions_b200 import zoo
-    from mcncrossmodalemotions_b200.distill import DistillationStep
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B = args.per_gpu_batch
-    step = DistillationStep(zoo.teacher_init(args.teacher), zoo.student_init(), B, WIDTH, device=local)
-    step.student.set_hyper(lr=1e-4, momentum=0.9, weight_decay=5e-4, batch_size=B * world)
-    allreduce = (lambda g: dist.all_reduce(g)) if world > 1 else None
-    faces_h, spec_h = synth_inputs(B, rank)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- inputs resident in HBM, warm-up (captures the graphs)
-    clocks = ClockSampler(local)
-    clocks.start()   # nvidia-smi needs a few hundred ms to come up: started ahead of the warm-up, rows are time-stamped
-    step.prefetch(faces_h, spec_h)
-    step.step_host(allreduce)
-    step.sync()
-    for _ in range(args.warmup):
-        step.step_resident(allreduce)
-    barrier()
-    t_load0 = clocks.mark()
-    c0 = step.ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(step.stream)
-    for _ in range(args.steps):
-        step.step_resident(allreduce)
-    e1.record(step.stream)
-    barrier()
-    launches = step.ctx.launch_count() - c0
-    ms_res = max_over_ranks(e0.elapsed_time(e1))
-    # ---- end to end: pinned host buffers -> H2D -> step -> D2H loss, every step
-    for _ in range(2):
-        step.prefetch(faces_h, spec_h)
-        step.step_host(allreduce)
-    barrier()
-    e0.record(step.stream)
-    step.prefetch(faces_h, spec_h)
-    for i in range(args.steps):
-        step.step_host(allreduce)
-        if i + 1 < args.steps:
-            step.prefetch(faces_h, spec_h)
-    e1.record(step.stream)
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    t_load1 = clocks.mark()
-    # a short timed region (few steps, many GPUs sharing one nvidia-smi) can end before a 200 ms sample lands inside it:
-    # keep the same step running (untimed) until two samples have been taken under this load
-    extra = 0
-    for _ in range(50):
-        need = 1.0 if (clocks.proc and clocks.count_between(t_load0, t_load1) < 2) else 0.0
-        if max_over_ranks(need) == 0.0:   # collective decision: every rank runs the same number of extra steps
-            break
-        for _ in range(8):
-            step.step_resident(allreduce)
-        extra += 8
-        barrier()
-        t_load1 = clocks.mark()
-    clk = clocks.stop(t_load0, t_load1)
-    clk["extra_load_steps"] = extra
-    loss = float(step.loss_host[0])
-
-    # ---- roofline of the tcgen05 convolution launches (instrumented eager pass, rank 0)
-    roof = None
-    if rank == 0:
-        prof = ConvProfiler(step.stream)
-        step.use_graph = False
-        side, step.side, step.student.side_stream = step.side, None, None   # per-op timing needs one stream
-        step.grad_step()  # warm
-        step.sync()
-        step.ctx.profiler = prof
-        with torch.cuda.stream(step.stream):
-            step.grad_step()
-        step.ctx.profiler = None
-        step.use_graph = True
-        step.side, step.student.side_stream = side, side
-        fl, t, n_launch, by = prof.summary()
-        peaks = measured_peaks()
-        achieved = fl / t / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
-        if os.path.exists(tpath):   # dram__bytes_read+write of the same launches from the committed ncu capture
-            with open(tpath) as f:
-                tj = json.load(f)
-            if tj.get("per_gpu_batch") == B:
-                traffic = tj["dram_bytes"]
-        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tflops_sustained"], "traffic": traffic, "traffic_unit": "bytes per step (all conv launches)", "kernel": "conv_fprop_kernel / conv_wgrad_kernel (tcgen05)",
-                "launches_per_step": n_launch, "conv_ms_per_step": t * 1e3, "by_op": by, "peak_source": peaks["source"] + ", sustained bf16",
-                "operand_dtype": "fp16 x fp16 -> fp32 (TMEM)"}
-    barrier()
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        cpu_step_seconds(1, threads)  # warm
-        dt = cpu_step_seconds(args.cpu_pairs, threads)
-        cpu = {"value": args.cpu_pairs / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "1 step of %d pairs (SENet50 fwd + VGGVox fwd/bwd @512x300 + loss + SGD), fp32 torch CPU kernels, %.1f s" % (args.cpu_pairs, dt)}
-    if world > 1:
-        dist.barrier()
-    if rank == 0:
-        total = B * world * args.steps
-        value = total / (ms_res * 1e-3)
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
-            "data": "synthetic",
-            "config": {"workload": "full distillation step: %s-ferplus teacher fwd (48x48 uint8 faces -> 224x224x3) + VGGVox student "
-                                   "fwd+bwd @512x300 + T=2 softmax CE + SGD-momentum" % args.teacher,
-                       "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
-                       "l2": "per-step working set (>10 GB of activations) exceeds the 126 MB L2; no flush needed",
-                       "gflop_per_pair": GFLOP_PAIR, "achieved_tflops_per_gpu": value / world * GFLOP_PAIR / 1e3},
-            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": step.d2h_bytes,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "kernels_per_step": step.num_kernels(), "loss": loss,
-            "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-        }))
-    if world > 1:
-        dist.destroy_process_group()
+    D = Dist()
+    try:
+        if args.config == "c4":
+            run_c4(args, D)
+        else:
+            run_single_program(args, D)
+    finally:
+        D.close()
 
 
 if __name__ == "__main__":

@@ -153,8 +153,7 @@ class StudentProgramF32:
                 cur = dx
         finally:
             self.ctx.set_conv_precision(prev)
-        self.grads = g
-        self.tape = {}
+        self.grads = g      # (the tape stays until the next forward: export_decisions reads it)
 
     # ---- StudentProgram interface
     def forward(self, spec, mode="test"):
@@ -195,6 +194,19 @@ class StudentProgramF32:
         self.ctx.sync()
         s, cs = self.scalars.cpu(), self.class_stats.cpu()
         return dict(objective=float(s[0]), classerror=float(s[1]), correct=cs[: self.K].numpy(), count=cs[self.K :].numpy())
+
+    def export_decisions(self):
+        """The discrete decisions of the last train-mode forward (see StudentProgram.export_decisions): ReLU masks x > 0
+        ('relu<i>', H x W x C x N bool) and the uint8 window-local arg-max of every max pool ('pool<i>')."""
+        out = {}
+        for L in self.layers:
+            n, i = L["name"], L["name"][-1]
+            if L["bn"]:
+                out["relu" + i] = gather(self.tape[L["bn"] + ":relu"]) > 0
+            if L["pool"] and L["pool"][0] == "max":
+                _, idx = vl_nn.vl_nnpool(self.tape[n + ":pool"], L["pool"][1], stride=L["pool"][2], method="max", return_index=True)
+                out["pool" + i] = idx
+        return out
 
     def prediction(self):
         return gather(self.pred).reshape(self.K, self.N).T.copy()

@@ -200,14 +200,20 @@ def vl_nnpool(x, pool, dzdy=None, pad=0, stride=1, method="max", return_index=Fa
     meth = 0 if method == "max" else 1
     if dzdy is None:
         ya, yi = m.out((OH, OW, Cc, N))
-        idx = None
-        if return_index and meth == 0:
-            if m.on_gpu:
-                raise ValueError("return_index is supported for CPU arrays")
-            idx = np.empty((N, Cc, OW, OH), dtype=np.uint8)
-        ctx.vl_nnpool(xa, pool, None, pad, stride, meth, ya, idx.ctypes.data_as(C.c_void_p) if idx is not None else None)
-        y = m.result(yi)
-        return (y, idx.transpose(3, 2, 1, 0)) if idx is not None else y
+        if not (return_index and meth == 0):
+            ctx.vl_nnpool(xa, pool, None, pad, stride, meth, ya, None)
+            return m.result(yi)
+        if m.on_gpu:       # gpuArray in: the uint8 indices are produced on the device and gathered
+            import torch
+
+            idx_t = torch.empty(N * Cc * OW * OH, dtype=torch.uint8, device="cuda")
+            torch.cuda.current_stream().synchronize()
+            ctx.vl_nnpool(xa, pool, None, pad, stride, meth, ya, C.c_void_p(idx_t.data_ptr()))
+            ctx.sync()
+            return m.result(yi), idx_t.cpu().numpy().reshape(N, Cc, OW, OH).transpose(3, 2, 1, 0)
+        idx = np.empty((N, Cc, OW, OH), dtype=np.uint8)
+        ctx.vl_nnpool(xa, pool, None, pad, stride, meth, ya, idx.ctypes.data_as(C.c_void_p))
+        return m.result(yi), idx.transpose(3, 2, 1, 0)
     dya = m.arr(dzdy)
     dxa, dxi = m.out((H, W, Cc, N))
     ctx.vl_nnpool(xa, pool, dya, pad, stride, meth, dxa, None)

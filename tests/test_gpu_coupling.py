@@ -64,7 +64,7 @@ def test_distillation_step_with_13_frames_per_clip(method):
     from oracle import nets
     from mcncrossmodalemotions_b200.distill import DistillationStep
 
-    n, F, width = 2, 13, 100
+    n, F, width = 4, 13, 100     # (train-mode BN needs more than two samples per batch to be well conditioned)
     tp, sp = nets.teacher_init("senet50"), nets.student_init()
     faces = nets.synth_faces48(n * F)
     spec = nets.synth_spectrograms(n, width)
