@@ -248,6 +248,103 @@ def test_dagnn_mat_files_round_trip(tmp_path):
         matfile.load_dagnn(str(tmp_path / "bad.mat"), "student")
 
 
+def _caffe_style_teacher_file(path, tp, order, wrap_in_net=False):
+    """A DagNN file laid out the way the MatConvNet imports of the Caffe ResNet-50 / SE-ResNet-50 graphs are: Caffe-derived
+    parameter names, BatchNorm (mult, bias, moments) after every convolution, projection branch first ('resnet') or after
+    the SE layers ('senet')."""
+    from scipy.io import savemat
+
+    from mcncrossmodalemotions_b200.programs import TEACHER_STAGES
+
+    entries = []
+
+    def conv_bn(tag, fkey, bnkey):
+        entries.append((tag + "_filter", tp[fkey + "f"]))
+        entries.append((tag + "_bn_mult", tp[bnkey + "m"].reshape(-1, 1)))
+        entries.append((tag + "_bn_bias", tp[bnkey + "b"].reshape(-1, 1)))
+        entries.append((tag + "_bn_moments", tp[bnkey + "x"]))
+
+    conv_bn("conv1_7x7_s2", "conv1", "bn1")
+    for si, (nb, mid, cout, _) in enumerate(TEACHER_STAGES):
+        for bi in range(nb):
+            pre, tag = "s%db%d_" % (si + 2, bi + 1), "conv%d_%d" % (si + 2, bi + 1)
+            proj = lambda: conv_bn(tag + "_1x1_proj", pre + "proj", pre + "bnp")
+            if bi == 0 and order == "resnet":
+                proj()
+            conv_bn(tag + "_1x1_reduce", pre + "c1", pre + "bn1")
+            conv_bn(tag + "_3x3", pre + "c2", pre + "bn2")
+            conv_bn(tag + "_1x1_increase", pre + "c3", pre + "bn3")
+            if tp["arch"] == "senet50":
+                for fc, key in (("_1x1_down", "se1"), ("_1x1_up", "se2")):
+                    entries.append((tag + fc + "_filter", tp[pre + key + "f"]))
+                    entries.append((tag + fc + "_bias", tp[pre + key + "b"].reshape(-1, 1)))
+            if bi == 0 and order == "senet":
+                proj()
+    entries.append(("classifier_filter", tp["classifierf"]))
+    entries.append(("classifier_bias", tp["classifierb"].reshape(-1, 1)))
+    p = np.zeros(len(entries), dtype=[("name", object), ("value", object)])
+    for i, (k, v) in enumerate(entries):
+        p[i] = (k, v)
+    net = {"params": p, "meta": {"normalization": {"imageSize": np.array([224.0, 224, 3]), "averageImage": np.array([131.0912, 103.8827, 91.4953])}}}
+    savemat(path, {"net": net} if wrap_in_net else net, do_compression=True)
+
+
+@pytest.mark.parametrize("arch,order,wrap", [("resnet50", "resnet", False), ("senet50", "senet", True), ("senet50", "resnet", False)])
+def test_teacher_mat_import_by_shape_walk(tmp_path, arch, order, wrap):
+    """emoVoxZoo.m:28-31,40-48: the released teachers are DagNN files with upstream parameter names the reference pins
+    nowhere; load_dagnn maps them by shape and position, for both Caffe layer orders, with or without a `net` wrapper."""
+    from mcncrossmodalemotions_b200 import matfile, zoo
+
+    tp = zoo.teacher_init(arch + "-ferplus")
+    path = str(tmp_path / (arch + "-ferplus.mat"))
+    _caffe_style_teacher_file(path, tp, order, wrap)
+    back = matfile.load_dagnn(path, "teacher")
+    assert back["arch"] == arch
+    assert set(back) == set(tp), (set(back) ^ set(tp))
+    for k in tp:
+        if k != "arch":
+            assert back[k].shape == tp[k].shape and np.array_equal(back[k], tp[k]), k
+
+
+def test_teacher_mat_import_rejects_a_foreign_graph(tmp_path):
+    from scipy.io import savemat
+
+    from mcncrossmodalemotions_b200 import matfile
+
+    p = np.zeros(2, dtype=[("name", object), ("value", object)])
+    p[0] = ("conv1_filter", np.zeros((3, 3, 3, 64), np.float32))
+    p[1] = ("conv1_bias", np.zeros((64, 1), np.float32))
+    savemat(str(tmp_path / "vgg.mat"), {"params": p})
+    with pytest.raises(ValueError):
+        matfile.load_dagnn(str(tmp_path / "vgg.mat"), "teacher")
+
+
+def test_cached_logits_formats_round_trip(tmp_path):
+    """imdb.wavLogits (fetch_emovoxceleb_imdb.m:138-148) / faceLogits (compute_visual_feats.m:105-117): 1 x T cells of F_i x 8
+    single arrays among the top-level variables that save(path, '-struct', 'imdb') writes; consumed by
+    getBatchEmoVoxCeleb.m:13 and fed to the coupling operator."""
+    from scipy.io import loadmat
+
+    from mcncrossmodalemotions_b200 import batch, matfile
+
+    rng = np.random.default_rng(3)
+    logits = [rng.standard_normal((f, 8)).astype(np.float32) for f in (13, 1, 40, 17)]
+    path = str(tmp_path / "imdb.mat")
+    matfile.save_logits(path, logits, "wavLogits", extra={"images": {"id": np.arange(1, 5)}})
+    raw = loadmat(path)
+    assert raw["wavLogits"].shape == (1, 4) and raw["wavLogits"].dtype == object and raw["wavLogits"][0, 2].shape == (40, 8)
+    back = matfile.load_logits(path)
+    assert len(back) == 4 and all(np.array_equal(a, b) and a.dtype == np.float32 for a, b in zip(back, logits))
+    a, b = batch.frame_window(len(back[2]), 0.5, 3.5)
+    assert np.array_equal(batch.aggregate(back[2][a:b]), logits[2][a:b].max(axis=0))
+    matfile.save_logits(str(tmp_path / "feats.mat"), logits[:2], "faceLogits")
+    assert [x.shape for x in matfile.load_logits(str(tmp_path / "feats.mat"), "faceLogits")] == [(13, 8), (1, 8)]
+    with pytest.raises(KeyError):
+        matfile.load_logits(path, "faceLogits")
+    with pytest.raises(ValueError):
+        matfile.save_logits(path, logits, "logits")
+
+
 def test_zoo_model_mirrors_the_dagnn_calls_of_the_reference_scripts():
     from mcncrossmodalemotions_b200 import zoo
 
