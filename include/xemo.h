@@ -326,6 +326,83 @@ int xemo_op_cast_f16_f32(xemo_ctx* ctx, const void* src16, size_t n, float scale
 int xemo_op_fill_strided_f32(xemo_ctx* ctx, float* dst, int outer, size_t outer_stride, size_t inner_off, int inner,
                              float value);
 
+/* ------------------------------------------------------------------ (C) graph-level entry points
+ * Whole networks behind the ABI: what dagnn.DagNN.eval (emoVoxCeleb/fetch_emovoxceleb_imdb.m:129,
+ * external/compute_visual_feats.m:90, external/compute_audio_feats.m:126) and cnn_train_dag
+ * (emoVoxCeleb/run_distillation.m:170-182: forward, loss emoVoxZoo.m:137-157, backward, accumulateGradients, gradient
+ * sum over the labs of 'gpus', opts.gpus) do, as single calls.  The library owns the device-resident network, sequences
+ * the kernels, captures the sequence in CUDA graphs and replays them; the host (MATLAB through mex/xemo_dagnn_mex.c,
+ * Python through net.py) moves parameters in, inputs in and logits / metrics out.
+ *
+ * Parameters are named as in the zoo (`conv1f`, `conv1b`, `bn1m`, `bn1b`, `bn1x`, `s2b1_c1f`, ..., `classifierf`) and
+ * travel in MatConvNet layouts: filters FH x FW x FC x K column-major, vectors K x 1, BatchNorm moments C x 2 = [mu sigma]
+ * column-major.  xemo_net_param_name / _dims enumerate them in graph order. */
+typedef struct xemo_net xemo_net;
+typedef struct xemo_comm xemo_comm;
+enum { XEMO_NET_RESNET50 = 0, XEMO_NET_SENET50 = 1, XEMO_NET_VGGVOX = 2 };
+enum { XEMO_INPUT_F32 = 0, XEMO_INPUT_U8 = 1 };
+enum { XEMO_LOSS_SOFTMAXCE = 0, XEMO_LOSS_SOFTMAXLOG = 1, XEMO_LOSS_EUCLIDEAN = 2, XEMO_LOSS_HUBER = 3 };
+enum { XEMO_TENSOR_PARAM = 0, XEMO_TENSOR_GRAD = 1, XEMO_TENSOR_MOMENTUM = 2 };
+
+/* kind XEMO_NET_RESNET50 / _SENET50 (teachers, test-mode BN folded at finalize): `size` is the face size for
+ * XEMO_INPUT_U8 (uint8 grey size x size x N column-major; normalizeFace + bilinear resize to 224 run on the device,
+ * emoVoxCeleb/fetch_emovoxceleb_imdb.m:175-193) and ignored for XEMO_INPUT_F32 (224 x 224 x 3 x N single, normalised).
+ * kind XEMO_NET_VGGVOX (student): `size` is the spectrogram width W (input 512 x W x 1 x N single, row-normalised);
+ * W must reduce to a 1 x 1 output (the width buckets 100 ... 1000 of emoVoxZoo.m:258-259 do). */
+int xemo_net_create(xemo_ctx* ctx, int kind, int batch, int size, int input_mode, int num_outputs, xemo_net** out);
+void xemo_net_destroy(xemo_net* net);
+int xemo_net_num_params(xemo_net* net);
+const char* xemo_net_param_name(xemo_net* net, int index);
+int xemo_net_param_dims(xemo_net* net, const char* name, int64_t dims[4]);
+/* host pointers; every parameter must be set before xemo_net_finalize, which builds the device state.  A finalized
+ * student accepts further set_param calls (checkpoint restore); a teacher's parameters are folded at finalize. */
+int xemo_net_set_param(xemo_net* net, const char* name, const float* data, size_t numel);
+int xemo_net_finalize(xemo_net* net);
+/* student: current value / gradient of the last step (BN `x` entries: the batch moments) / momentum, MatConvNet layout */
+int xemo_net_get_tensor(xemo_net* net, int which, const char* name, float* out, size_t numel);
+int xemo_net_set_momentum(xemo_net* net, const char* name, const float* data, size_t numel);
+/* inputs (host or device memory, stream-ordered copies): faces / spectrograms; student targets logitTarget
+ * (1 x 1 x K x N, i.e. [N][K]; one-hot rows for XEMO_LOSS_SOFTMAXLOG) and instanceWeights (N), either may be NULL */
+int xemo_net_input_bytes(xemo_net* net, size_t* bytes);
+int xemo_net_set_input(xemo_net* net, const void* data, size_t bytes);
+int xemo_net_set_target(xemo_net* net, const float* target, const float* weights);
+/* loss of the training step (emoVoxZoo.m:137-157), its temperature (hot-cross-ent; huber: sigma is 1) and the loss scale
+ * of the fp16 gradient chain */
+int xemo_net_set_loss(xemo_net* net, int loss_type, float temperature, float grad_scale);
+int xemo_net_set_hyper(xemo_net* net, float lr, float momentum, float weight_decay, int batch_size);
+/* named device buffers for zero-copy hosts ("faces", "spec", "target", "logits", "pred32", "grad", ...) */
+void* xemo_net_buffer(xemo_net* net, const char* name);
+size_t xemo_net_grad_elems(xemo_net* net);
+int xemo_net_num_kernels(xemo_net* net);
+
+/* dag.eval: logits_out / pred_out (optional, host or device) receive 1 x 1 x K x N */
+int xemo_teacher_forward(xemo_net* net, float* logits_out);
+int xemo_student_forward(xemo_net* net, int train_mode, float* pred_out);
+/* one cnn_train_dag iteration up to the gradients: forward (train-mode BN) + loss + backward; with a communicator of
+ * more than one rank the flat gradient is summed across ranks inside the captured sequence (fc6..fc8 bucket on a forked
+ * stream while conv5..conv1 are differentiated).  xemo_sgd_step: accumulateGradients (guarded against non-finite values). */
+int xemo_student_train_step(xemo_net* net, xemo_comm* comm);
+int xemo_sgd_step(xemo_net* net, float lr, float momentum, float weight_decay, int batch_size);
+int xemo_allreduce_grads(xemo_net* net, xemo_comm* comm);
+/* teacher -> student coupling on the device; start / end: device int[N_student] half-open row ranges into the teacher's
+ * frame logits, or NULL / NULL for the windows stored by xemo_distill_set_windows (host arrays) */
+int xemo_distill_set_windows(xemo_net* student, const int* start, const int* end);
+int xemo_distill_couple(xemo_net* teacher, xemo_net* student, const int* start, const int* end, int use_mean);
+/* the full distillation step (BASELINE.json's headline configuration) as ONE graph replay */
+int xemo_distill_step(xemo_net* teacher, xemo_net* student, xemo_comm* comm, const int* start, const int* end, int use_mean,
+                      float lr, float momentum, float weight_decay, int batch_size);
+int xemo_net_reset_metrics(xemo_net* net);
+/* out[0] objective, out[1] classerror of the last step; out[2..2+K) correct and out[2+K..2+2K) count per class since the
+ * reset (ErrorStats); out[2+2K] non-finite gradient in the last update, out[3+2K] updates skipped so far */
+int xemo_net_metrics(xemo_net* net, float* out, int n_out);
+
+/* data-parallel communicator: NCCL resolved at run time (dlsym; libnccl.so.2), one rank per context.  Rank 0 creates the
+ * 128-byte unique id and the host distributes it (MATLAB: labBroadcast; Python: torch.distributed / a file). */
+int xemo_comm_unique_id(void* id128);
+int xemo_comm_create(xemo_ctx* ctx, const void* id128, int rank, int world, xemo_comm** out);
+void xemo_comm_destroy(xemo_comm* comm);
+int xemo_comm_allreduce_f32(xemo_comm* comm, float* device_buf, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -124,6 +124,38 @@ SIGNATURES = {
     "xemo_op_cast_f32_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "xemo_op_cast_f16_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p]),
     "xemo_op_fill_strided_f32": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_size_t, c_int, c_float]),
+    # (C) graph-level entry points
+    "xemo_net_create": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, P(c_void_p)]),
+    "xemo_net_destroy": (None, [c_void_p]),
+    "xemo_net_num_params": (c_int, [c_void_p]),
+    "xemo_net_param_name": (C.c_char_p, [c_void_p, c_int]),
+    "xemo_net_param_dims": (c_int, [c_void_p, C.c_char_p, P(c_int64)]),
+    "xemo_net_set_param": (c_int, [c_void_p, C.c_char_p, c_void_p, c_size_t]),
+    "xemo_net_finalize": (c_int, [c_void_p]),
+    "xemo_net_get_tensor": (c_int, [c_void_p, c_int, C.c_char_p, c_void_p, c_size_t]),
+    "xemo_net_set_momentum": (c_int, [c_void_p, C.c_char_p, c_void_p, c_size_t]),
+    "xemo_net_input_bytes": (c_int, [c_void_p, P(c_size_t)]),
+    "xemo_net_set_input": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "xemo_net_set_target": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "xemo_net_set_loss": (c_int, [c_void_p, c_int, c_float, c_float]),
+    "xemo_net_set_hyper": (c_int, [c_void_p, c_float, c_float, c_float, c_int]),
+    "xemo_net_buffer": (c_void_p, [c_void_p, C.c_char_p]),
+    "xemo_net_grad_elems": (c_size_t, [c_void_p]),
+    "xemo_net_num_kernels": (c_int, [c_void_p]),
+    "xemo_teacher_forward": (c_int, [c_void_p, c_void_p]),
+    "xemo_student_forward": (c_int, [c_void_p, c_int, c_void_p]),
+    "xemo_student_train_step": (c_int, [c_void_p, c_void_p]),
+    "xemo_sgd_step": (c_int, [c_void_p, c_float, c_float, c_float, c_int]),
+    "xemo_allreduce_grads": (c_int, [c_void_p, c_void_p]),
+    "xemo_distill_set_windows": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "xemo_distill_couple": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "xemo_distill_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_int]),
+    "xemo_net_reset_metrics": (c_int, [c_void_p]),
+    "xemo_net_metrics": (c_int, [c_void_p, c_void_p, c_int]),
+    "xemo_comm_unique_id": (c_int, [c_void_p]),
+    "xemo_comm_create": (c_int, [c_void_p, c_void_p, c_int, c_int, P(c_void_p)]),
+    "xemo_comm_destroy": (None, [c_void_p]),
+    "xemo_comm_allreduce_f32": (c_int, [c_void_p, c_void_p, c_size_t]),
 }
 
 _lib = None

@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .programs import STUDENT_CONVS, TEACHER_STAGES
+from .arch import STUDENT_CONVS, TEACHER_STAGES
 
 
 def _student_layers(params):

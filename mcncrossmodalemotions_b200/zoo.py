@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .programs import STUDENT_CONVS, TEACHER_STAGES
+from .arch import STUDENT_CONVS, TEACHER_STAGES
 
 TEACHERS = ("resnet50-ferplus", "senet50-ferplus")
 STUDENTS = ("emovoxceleb-student",)

@@ -450,6 +450,31 @@ def test_conv_plans_respect_the_hardware_budgets(n):
             assert groups * T >= R * S * c_tiles and splits >= 1 and 1 <= wgrid <= 148, name
 
 
+def test_layer_tables_agree_with_the_library():
+    """csrc/xemo_net.cu carries its own architecture tables (the library does not depend on the Python package): every
+    parameter name / MatConvNet shape it enumerates for the three networks must be the zoo's, in graph order."""
+    import ctypes as C
+
+    from mcncrossmodalemotions_b200 import _lib, zoo
+
+    lib = _lib.load_library()
+    for kind, params, size in ((0, zoo.teacher_init("resnet50"), 224), (1, zoo.teacher_init("senet50"), 224), (2, zoo.student_init(), 300)):
+        h = C.c_void_p()
+        assert lib.xemo_net_create(None, kind, 4, size, 0, 8, C.byref(h)) == 0
+        names = [lib.xemo_net_param_name(h, i).decode() for i in range(lib.xemo_net_num_params(h))]
+        assert set(names) == {k for k in params if k != "arch"}, set(names) ^ set(params)
+        for name in names:
+            d = (C.c_int64 * 4)()
+            assert lib.xemo_net_param_dims(h, name.encode(), d) == 0
+            shape = tuple(params[name].shape) + (1,) * (4 - params[name].ndim)
+            assert tuple(d) == shape, (name, tuple(d), shape)
+        assert lib.xemo_net_finalize(h) != 0          # description only: no device
+        lib.xemo_net_destroy(h)
+    h = C.c_void_p()
+    assert lib.xemo_net_create(None, 2, 4, 20, 0, 8, C.byref(h)) != 0       # too narrow for the pooling chain
+    assert lib.xemo_net_create(None, 7, 4, 300, 0, 8, C.byref(h)) != 0
+
+
 def test_loss_types_of_the_zoo():
     """emoVoxZoo.m:137-157: four loss types; 'euclidean' scales the head filters by 1/10 (:141-144); anything else is
     rejected before the device is touched."""
