@@ -325,42 +325,101 @@ def timed_loop(D, stream, fn, steps, warmup):
     return D.max_over_ranks(e0.elapsed_time(e1))
 
 
+class StepDriver:
+    """The timed object: the full distillation step behind the graph-level C ABI (net.DistillStep -> xemo_distill_step, one
+    graph replay per step; the gradient exchange is ncclAllReduce issued by the library inside the captured step).  torch
+    is used here for pinned host memory, the copy stream and the CUDA events that time the region -- nothing else."""
+
+    def __init__(self, D, args, B, global_batch):
+        import torch
+
+        from mcncrossmodalemotions_b200 import zoo
+        from mcncrossmodalemotions_b200.net import Comm, DistillStep
+
+        self.torch, self.D, self.B = torch, D, B
+        dev = torch.device("cuda", D.local)
+        self.stream = torch.cuda.Stream(dev)
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.step = DistillStep(zoo.teacher_init(args.teacher), zoo.student_init(), B, WIDTH, device=D.local, stream=self.stream.cuda_stream)
+        self.ctx = self.step.ctx
+        if D.world > 1:
+            self.step.comm = Comm.from_torch(self.ctx)
+        self.step.student.set_hyper(lr=1e-4, momentum=0.9, weight_decay=5e-4, batch_size=global_batch)
+        self.faces_h, self.spec_h = synth_inputs(B, D.rank)
+        with torch.cuda.stream(self.stream):
+            self.stage_faces = torch.empty(self.faces_h.numel(), dtype=torch.uint8, device=dev)
+            self.stage_spec = torch.empty(self.spec_h.numel(), dtype=torch.float32, device=dev)
+        self.loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.h2d_done, self.stage_free = torch.cuda.Event(), torch.cuda.Event()
+        self.stage_free.record(self.stream)
+        self.h2d_bytes = self.faces_h.numel() + self.spec_h.numel() * 4
+        self.d2h_bytes = 8
+        self.scalars = self.step.student.buffer("scalars")
+
+    def prefetch(self):
+        """asynchronous H2D of the next step's inputs (pinned host tensors) on the copy stream"""
+        torch = self.torch
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.stage_free)
+            self.stage_faces.copy_(self.faces_h, non_blocking=True)
+            self.stage_spec.copy_(self.spec_h, non_blocking=True)
+            self.h2d_done.record(self.copy_stream)
+
+    def step_resident(self):
+        self.step.step()
+
+    def step_host(self):
+        """consume the prefetched inputs, run the step, copy objective / classerror back to pinned host memory"""
+        import ctypes as C
+
+        self.stream.wait_event(self.h2d_done)
+        self.step.teacher.set_input(self.stage_faces)
+        self.step.student.set_input(self.stage_spec)
+        self.stage_free.record(self.stream)
+        self.step.step()
+        self.ctx.d2h(C.c_void_p(self.loss_host.data_ptr()), C.c_void_p(self.scalars), 8)
+
+    def sync(self):
+        self.ctx.sync()
+
+    def close(self):
+        if self.step.comm:
+            self.step.comm.close()
+        self.step.student.close()
+        self.step.teacher.close()
+
+
 def measure_step(D, args, B, global_batch, clocks=None, with_e2e=True):
-    """Resident and end-to-end timing of the distillation step at per-GPU batch B.  Returns (step, dict)."""
+    """Resident and end-to-end timing of the distillation step at per-GPU batch B.  Returns (driver, dict)."""
     import torch
 
-    from mcncrossmodalemotions_b200 import zoo
-    from mcncrossmodalemotions_b200.distill import DistillationStep
-
-    step = DistillationStep(zoo.teacher_init(args.teacher), zoo.student_init(), B, WIDTH, device=D.local)
-    step.student.set_hyper(lr=1e-4, momentum=0.9, weight_decay=5e-4, batch_size=global_batch)
-    faces_h, spec_h = synth_inputs(B, D.rank)
-    step.prefetch(faces_h, spec_h)
-    step.step_host(D.allreduce)
-    step.sync()
-    run = lambda: step.step_resident(D.allreduce)
+    drv = StepDriver(D, args, B, global_batch)
+    drv.prefetch()
+    drv.step_host()
+    drv.sync()
+    run = drv.step_resident
     for _ in range(args.warmup):
         run()
     D.barrier()
     t0 = clocks.mark() if clocks else None
-    c0 = step.ctx.launch_count()
-    ms_res = timed_loop(D, step.stream, run, args.steps, 0)
-    launches = step.ctx.launch_count() - c0
+    c0 = drv.ctx.launch_count()
+    ms_res = timed_loop(D, drv.stream, run, args.steps, 0)
+    launches = drv.ctx.launch_count() - c0
     out = dict(ms_res=ms_res, launches=launches)
     if with_e2e:
         # end to end: pinned host buffers -> H2D -> step -> D2H loss, every step (copies of step i+1 overlap step i)
         for _ in range(2):
-            step.prefetch(faces_h, spec_h)
-            step.step_host(D.allreduce)
+            drv.prefetch()
+            drv.step_host()
         D.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(step.stream)
-        step.prefetch(faces_h, spec_h)
+        e0.record(drv.stream)
+        drv.prefetch()
         for i in range(args.steps):
-            step.step_host(D.allreduce)
+            drv.step_host()
             if i + 1 < args.steps:
-                step.prefetch(faces_h, spec_h)
-        e1.record(step.stream)
+                drv.prefetch()
+        e1.record(drv.stream)
         D.barrier()
         out["ms_e2e"] = D.max_over_ranks(e0.elapsed_time(e1))
     if clocks:
@@ -380,8 +439,9 @@ def measure_step(D, args, B, global_batch, clocks=None, with_e2e=True):
         clk = clocks.stop(t0, t1)
         clk["extra_load_steps"] = extra
         out["clocks"] = clk
-    out["loss"] = float(step.loss_host[0])
-    return step, out
+    drv.sync()
+    out["loss"] = float(drv.loss_host[0])
+    return drv, out
 
 
 def graph_ms(D, ctx, stream, record, iters=5):
@@ -404,11 +464,20 @@ def graph_ms(D, ctx, stream, record, iters=5):
     return ms
 
 
-def conv_roofline(D, step, B, ms_step):
-    """All tcgen05 convolution launches of one step, timed one by one (instrumented eager pass), plus the fractions
-    north_star names: whole step, teacher forward alone, student step alone (graph replays)."""
+def conv_roofline(D, args, B, ms_step):
+    """All tcgen05 convolution launches of one step, timed one by one (instrumented eager pass over the Python-side
+    assembly of the same kernel sequence: its per-call hooks are what times each launch), plus the fractions north_star
+    names: whole step, teacher forward alone, student step alone (graph replays)."""
     import torch
 
+    from mcncrossmodalemotions_b200 import zoo
+    from mcncrossmodalemotions_b200.distill import DistillationStep
+
+    step = DistillationStep(zoo.teacher_init(args.teacher), zoo.student_init(), B, WIDTH, device=D.local)
+    faces_h, spec_h = synth_inputs(B, D.rank)
+    step.prefetch(faces_h, spec_h)
+    step.step_host()
+    step.sync()
     prof = ConvProfiler(step.stream)
     step.use_graph = False
     side, step.side, step.student.side_stream = step.side, None, None   # per-op timing needs one stream
@@ -485,22 +554,25 @@ def run_c4(args, D):
         B = args.per_gpu_batch
     clocks = ClockSampler(D.local)
     clocks.start()   # nvidia-smi needs a few hundred ms to come up: started ahead of the warm-up, rows are time-stamped
-    step, m = measure_step(D, args, B, B * world, clocks)
-    roof = conv_roofline(D, step, B, m["ms_res"] / args.steps) if D.rank == 0 else None
-    D.barrier()
-    kernels = step.num_kernels()
-    h2d, d2h = step.h2d_bytes, step.d2h_bytes
-    del step
+    drv, m = measure_step(D, args, B, B * world, clocks)
+    kernels = drv.step.num_kernels()
+    h2d, d2h = drv.h2d_bytes, drv.d2h_bytes
+    drv.close()
+    del drv
     D.torch.cuda.empty_cache()
+    roof = conv_roofline(D, args, B, m["ms_res"] / args.steps) if D.rank == 0 else None
+    D.torch.cuda.empty_cache()
+    D.barrier()
     other = None
     if world > 1 and not args.single_line:
         # the other scaling mode in the same process: weak (256 pairs on every GPU) beside the strong headline, or vice versa
         B2 = args.per_gpu_batch if strong else args.global_batch // world
         if B2 != B and B2 >= 1:
-            step2, m2 = measure_step(D, args, B2, B2 * world, None, with_e2e=False)
+            drv2, m2 = measure_step(D, args, B2, B2 * world, None, with_e2e=False)
+            drv2.close()
             other = {"scaling": "weak" if strong else "strong", "value": B2 * world * args.steps / (m2["ms_res"] * 1e-3), "unit": UNIT,
                      "ms_per_step": m2["ms_res"] / args.steps, "per_gpu_batch": B2, "global_batch": B2 * world}
-            del step2
+            del drv2
             D.torch.cuda.empty_cache()
     cpu = parity = None
     if D.rank == 0 and world == 1:
@@ -533,11 +605,13 @@ def run_c4(args, D):
 
 
 def run_single_program(args, D):
-    """c2 / c3 / c5: one program per rank (replicas: no collective except c3's gradient all-reduce)."""
+    """c2 / c3 / c5: one network per rank behind the graph-level C ABI (replicas: no collective except c3's gradient sum)."""
+    import ctypes as C
+
     import torch
 
-    from mcncrossmodalemotions_b200 import zoo
-    from mcncrossmodalemotions_b200.programs import StudentProgram, TeacherProgram
+    from mcncrossmodalemotions_b200 import _lib, zoo
+    from mcncrossmodalemotions_b200.net import Comm, StudentNet, TeacherNet
 
     cfg = CONFIGS[args.config]
     peaks = measured_peaks()
@@ -546,83 +620,79 @@ def run_single_program(args, D):
     clocks.start()
     rng = np.random.default_rng(100 + D.rank)
     extra = {}
+    stream = torch.cuda.Stream(torch.device("cuda", D.local))
+    ctx = _lib.Context(D.local, stream.cuda_stream)
+    vp = lambda t: C.c_void_p(t.data_ptr())
     if args.config == "c2":
         B = args.batch or 256
-        prog = TeacherProgram(zoo.teacher_init("resnet50"), B, device=D.local)
+        net = TeacherNet(zoo.teacher_init("resnet50"), B, ctx=ctx)
         host = torch.from_numpy((rng.uniform(0, 255, B * 3 * 224 * 224) - 110.0).astype(np.float32)).pin_memory()
         out_host = torch.zeros(B, 16).pin_memory()
-        prog.set_input(host); prog.run(); prog.sync()
-        run = prog.run
+        net.set_input(host); net.run(); net.sync()
+        run = net.run
 
         def run_e2e():
-            prog.set_input(host)
-            prog.run()
-            with torch.cuda.stream(prog.stream):
-                out_host.copy_(prog.a["logits"], non_blocking=True)
-        gflop, h2d, d2h, stream, ctx = GFLOP_TEACHER["resnet50"], host.numel() * 4, out_host.numel() * 4, prog.stream, prog.ctx
+            net.set_input(host)
+            net.run()
+            ctx.d2h(vp(out_host), C.c_void_p(net.buffer("logits")), out_host.numel() * 4)
+        gflop, h2d, d2h = GFLOP_TEACHER["resnet50"], host.numel() * 4, out_host.numel() * 4
     elif args.config == "c3":
         B = args.batch or 128
-        prog = StudentProgram(zoo.student_init(), B, WIDTH, device=D.local)
-        prog.set_hyper(lr=1e-4, batch_size=B * D.world)
+        net = StudentNet(zoo.student_init(), B, WIDTH, ctx=ctx)
+        net.set_hyper(lr=1e-4, batch_size=B * D.world)
+        comm = Comm.from_torch(ctx) if D.world > 1 else None
         _, spec_h = synth_inputs(B, D.rank)
         tgt_h = torch.from_numpy((3 * rng.standard_normal((B, 8))).astype(np.float32)).pin_memory()
         loss_host = torch.zeros(2).pin_memory()
-        prog.set_input(spec_h, tgt_h)
+        net.set_input(spec_h)
+        net._check(net.lib.xemo_net_set_target(net.handle, vp(tgt_h), None))
 
         def run():
-            prog.grad_step()
-            if D.allreduce is not None:
-                with torch.cuda.stream(prog.stream):
-                    D.allreduce(prog.grad)
-            prog.update()
+            net.grad_step(comm)
+            net.update()
 
         def run_e2e():
-            prog.set_input(spec_h, tgt_h)
+            net.set_input(spec_h)
+            net._check(net.lib.xemo_net_set_target(net.handle, vp(tgt_h), None))
             run()
-            with torch.cuda.stream(prog.stream):
-                loss_host.copy_(prog.a["scalars"], non_blocking=True)
-        run(); prog.sync()
-        gflop, h2d, d2h, stream, ctx = GFLOP_STUDENT_FWD_BWD, spec_h.numel() * 4 + tgt_h.numel() * 4, 8, prog.stream, prog.ctx
+            ctx.d2h(vp(loss_host), C.c_void_p(net.buffer("scalars")), 8)
+        run(); net.sync()
+        gflop, h2d, d2h = GFLOP_STUDENT_FWD_BWD, spec_h.numel() * 4 + tgt_h.numel() * 4, 8
     else:   # c5 sweep: per batch size, teacher forward + student test-mode forward
         sweep = {}
+        sfwd = lambda n_: n_._check(n_.lib.xemo_student_forward(n_.handle, 0, None))
         for B in (64, 128, 256, 512, 1024):
-            tprog = TeacherProgram(zoo.teacher_init("senet50"), B, device=D.local)
-            tprog.run(); tprog.sync()
-            t_ms = timed_loop(D, tprog.stream, tprog.run, 5, 3) / 5
-            del tprog
-            torch.cuda.empty_cache()
-            sprog = StudentProgram(zoo.student_init(), B, WIDTH, device=D.local)
-            f = lambda: sprog._run("fwd_test", lambda: sprog._record_forward(False))
-            f(); sprog.sync()
-            s_ms = timed_loop(D, sprog.stream, f, 5, 3) / 5
-            del sprog
-            torch.cuda.empty_cache()
+            tnet = TeacherNet(zoo.teacher_init("senet50"), B, ctx=ctx)
+            tnet.run(); tnet.sync()
+            t_ms = timed_loop(D, stream, tnet.run, 5, 3) / 5
+            tnet.close()
+            snet = StudentNet(zoo.student_init(), B, WIDTH, ctx=ctx)
+            sfwd(snet); snet.sync()
+            s_ms = timed_loop(D, stream, lambda: sfwd(snet), 5, 3) / 5
+            snet.close()
             sweep["batch %d" % B] = {"teacher_ms": t_ms, "teacher_faces_per_s": B * D.world / t_ms * 1e3, "teacher_frac": B * GFLOP_TEACHER["senet50"] / t_ms / peak,
                                      "student_ms": s_ms, "student_clips_per_s": B * D.world / s_ms * 1e3, "student_frac": B * 5.662228992 / s_ms / peak,
                                      "samples_per_s": B * D.world / (t_ms + s_ms) * 1e3}
         extra["sweep"] = sweep
         B = args.batch or 256
-        tprog = TeacherProgram(zoo.teacher_init("senet50"), B, device=D.local)
-        sprog = StudentProgram(zoo.student_init(), B, WIDTH, device=D.local, stream=tprog.stream, ctx=tprog.ctx)
+        tnet = TeacherNet(zoo.teacher_init("senet50"), B, ctx=ctx)
+        snet = StudentNet(zoo.student_init(), B, WIDTH, ctx=ctx)
         host_f = torch.from_numpy((rng.uniform(0, 255, B * 3 * 224 * 224) - 110.0).astype(np.float32)).pin_memory()
         _, host_s = synth_inputs(B, D.rank)
         out_host = torch.zeros(2, B, 16).pin_memory()
-        ftest = lambda: sprog._run("fwd_test", lambda: sprog._record_forward(False))
-        tprog.run(); ftest(); tprog.sync()
+        tnet.run(); sfwd(snet); ctx.sync()
 
         def run():
-            tprog.run()
-            ftest()
+            tnet.run()
+            sfwd(snet)
 
         def run_e2e():
-            tprog.set_input(host_f)
-            sprog.set_input(host_s)
+            tnet.set_input(host_f)
+            snet.set_input(host_s)
             run()
-            with torch.cuda.stream(tprog.stream):
-                out_host[0].copy_(tprog.a["logits"], non_blocking=True)
-                out_host[1].copy_(sprog.a["pred32"], non_blocking=True)
-        gflop, h2d, d2h, stream, ctx = GFLOP_TEACHER["senet50"] + 5.662228992, (host_f.numel() + host_s.numel()) * 4, out_host.numel() * 4, tprog.stream, tprog.ctx
-        prog = tprog
+            ctx.d2h(vp(out_host[0]), C.c_void_p(tnet.buffer("logits")), B * 16 * 4)
+            ctx.d2h(vp(out_host[1]), C.c_void_p(snet.buffer("pred32")), B * 16 * 4)
+        gflop, h2d, d2h = GFLOP_TEACHER["senet50"] + 5.662228992, (host_f.numel() + host_s.numel()) * 4, out_host.numel() * 4
     for _ in range(args.warmup):
         run()
     D.barrier()

@@ -351,6 +351,7 @@ enum { XEMO_TENSOR_PARAM = 0, XEMO_TENSOR_GRAD = 1, XEMO_TENSOR_MOMENTUM = 2 };
  * W must reduce to a 1 x 1 output (the width buckets 100 ... 1000 of emoVoxZoo.m:258-259 do). */
 int xemo_net_create(xemo_ctx* ctx, int kind, int batch, int size, int input_mode, int num_outputs, xemo_net** out);
 void xemo_net_destroy(xemo_net* net);
+int xemo_net_batch(xemo_net* net);
 int xemo_net_num_params(xemo_net* net);
 const char* xemo_net_param_name(xemo_net* net, int index);
 int xemo_net_param_dims(xemo_net* net, const char* name, int64_t dims[4]);

@@ -127,6 +127,7 @@ SIGNATURES = {
     # (C) graph-level entry points
     "xemo_net_create": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, P(c_void_p)]),
     "xemo_net_destroy": (None, [c_void_p]),
+    "xemo_net_batch": (c_int, [c_void_p]),
     "xemo_net_num_params": (c_int, [c_void_p]),
     "xemo_net_param_name": (C.c_char_p, [c_void_p, c_int]),
     "xemo_net_param_dims": (c_int, [c_void_p, C.c_char_p, P(c_int64)]),

@@ -802,6 +802,7 @@ extern "C" void xemo_net_destroy(xemo_net* n) {
   delete n;
 }
 
+extern "C" int xemo_net_batch(xemo_net* n) { return n ? n->N : 0; }
 extern "C" int xemo_net_num_params(xemo_net* n) { return n ? int(n->order.size()) : 0; }
 extern "C" const char* xemo_net_param_name(xemo_net* n, int i) { return (n && i >= 0 && i < int(n->order.size())) ? n->order[i].c_str() : nullptr; }
 extern "C" int xemo_net_param_dims(xemo_net* n, const char* name, int64_t dims[4]) {

@@ -1,12 +1,12 @@
 """Embedding / logit extraction sweeps: external/compute_visual_feats.m (teacher, batch 128 loop :83-98) and
 external/compute_audio_feats.m (student, one clip per eval with the width-bucketed pool6, :116-136, :160-185) --
-here the student clips are grouped by bucket and each bucket is batched."""
+here the student clips are grouped by bucket and each bucket is batched.  Both run through the graph-level C ABI (net.py)."""
 from __future__ import annotations
 
 import numpy as np
 
 from . import batch as B
-from .programs import StudentProgram, TeacherProgram
+from .net import StudentNet, TeacherNet
 
 
 def compute_visual_feats(teacher_params, faces, batch_size=128, device=0, input_mode=None):
@@ -15,9 +15,9 @@ def compute_visual_feats(teacher_params, faces, batch_size=128, device=0, input_
     faces = np.asarray(faces)
     u8 = faces.ndim == 3
     m = faces.shape[-1]
-    prog = TeacherProgram(teacher_params, batch_size, device=device, input_mode="u8" if u8 else "hwcn224",
-                          face_size=faces.shape[0] if u8 else 48)
-    out = np.zeros((m, prog.num_outputs), np.float32)
+    prog = TeacherNet(teacher_params, batch_size, device=device, input_mode="u8" if u8 else "hwcn224",
+                      face_size=faces.shape[0] if u8 else 48)
+    out = np.zeros((m, prog.K), np.float32)
     for s in range(0, m, batch_size):
         chunk = faces[..., s : s + batch_size]
         n = chunk.shape[-1]
@@ -37,7 +37,7 @@ def compute_audio_feats(student_params, spectrograms, batch_size=64, device=0, i
     for i, s in enumerate(spectrograms):
         buckets.setdefault(B.width_bucket(s.shape[1]), []).append(i)
     for width, idxs in sorted(buckets.items()):
-        prog = StudentProgram(student_params, batch_size, width, device=device)
+        prog = StudentNet(student_params, batch_size, width, device=device)
         for s in range(0, len(idxs), batch_size):
             sel = idxs[s : s + batch_size]
             data = np.zeros((512, width, 1, batch_size), np.float32)

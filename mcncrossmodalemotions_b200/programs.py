@@ -852,6 +852,10 @@ class StudentProgram(_Base):
                     out[bn + s] = flat[o : o + L["cout"]].copy()
         return out
 
+    def export_momentum(self):
+        self.sync()
+        return self._export(self.momentum)
+
     def load_momentum(self, momentum):
         """Restore the optimiser state exported by `_export(self.momentum)` (checkpoint resume)."""
         flat = np.zeros(self.nparam, np.float32)

@@ -1,8 +1,9 @@
 """Training driver: the parts of cnn_train_dag the reference relies on (emoVoxCeleb/run_distillation.m:170-182) --
 epochs over a (sub-sampled) training set, per-epoch learning rate, SGD-momentum with weight decay, validation pass,
 running objective / classerror / per-class accuracy (extractStats, run_distillation.m:186-207), checkpoint per epoch
-and 'continue' (resume from the latest) -- on top of StudentProgram, plus `run_distillation`, the option surface of
-the reference driver (run_distillation.m:71-90)."""
+and 'continue' (resume from the latest) -- on top of the graph-level C ABI (net.StudentNet: xemo_student_train_step /
+xemo_sgd_step; the gradient sum across ranks is ncclAllReduce inside the library), plus `run_distillation`, the option
+surface of the reference driver (run_distillation.m:71-90)."""
 from __future__ import annotations
 
 import glob
@@ -14,8 +15,7 @@ import time
 import numpy as np
 
 from . import zoo
-from .dist import GradientAllReducer
-from .programs import StudentProgram
+from .net import Comm, StudentNet
 
 EMOTIONS = ["neutral", "happiness", "surprise", "sadness", "anger", "disgust", "fear", "contempt"]  # FER+ order
 
@@ -53,7 +53,7 @@ def find_last_checkpoint(exp_dir):
 
 def save_checkpoint(exp_dir, epoch, program, stats):
     params = program.export_params()
-    momentum = program._export(program.momentum)
+    momentum = program.export_momentum()
     np.savez(os.path.join(exp_dir, "net-epoch-%d.npz" % epoch), **{"p:" + k: v for k, v in params.items()},
              **{"m:" + k: v for k, v in momentum.items()}, stats=json.dumps(stats))
 
@@ -83,11 +83,11 @@ def cnn_train_dag(params, imdb, get_batch, *, learning_rate, batch_size=64, num_
                 params, mom, info = load_checkpoint(exp_dir, start)
                 log("resuming from epoch %d" % start)
     per_rank = batch_size // world
-    prog = StudentProgram(params, per_rank, width, device=device, loss_type=loss_type)
+    prog = StudentNet(params, per_rank, width, device=device, loss_type=loss_type)
     tkey = "maxLabel" if loss_type == "softmaxlog" else "logitTarget"   # the loss layer's second input (emoVoxZoo.m:137-157)
     if mom is not None:
         prog.load_momentum(mom)
-    allreduce = GradientAllReducer() if world > 1 else None
+    comm = Comm.from_torch(prog.ctx) if world > 1 else None   # one process per GPU, torch.distributed only hands out the NCCL id
     for epoch in range(start, num_epochs):
         rng = np.random.default_rng([seed, epoch])   # per-epoch stream: a resumed run draws the same permutations
         lr = float(learning_rate[min(epoch, len(learning_rate) - 1)])
@@ -103,7 +103,7 @@ def cnn_train_dag(params, imdb, get_batch, *, learning_rate, batch_size=64, num_
         for it in range(steps):
             idx = order[it * batch_size : (it + 1) * batch_size][rank::world]   # labindex:numlabs:end
             inputs = get_batch(imdb, idx)
-            prog.train_step(inputs["data"], inputs[tkey], allreduce, weights=inputs.get("instanceWeights"))
+            prog.train_step(inputs["data"], inputs[tkey], comm, weights=inputs.get("instanceWeights"))
             m = prog.metrics()   # objective / classerror of this batch; class counters accumulate
             obj += m["objective"]; err += m["classerror"]; seen += len(idx)
         m = prog.metrics()
@@ -166,10 +166,18 @@ def run_distillation(imdb, get_batch, root="data/xEmo18", **overrides):
     net = zoo.emoVoxZoo(opts["student"], scratch=opts["fromScratch"], lossType=opts["lossType"], numSeconds=opts["numSeconds"],
                         numOutputs=opts["numPredEmotions"])
     train, val = np.asarray(opts["train"]), np.asarray(opts["val"])
+    world, rank = 1, 0
+    try:    # 'gpus', opts.gpus (run_distillation.m:179): one process per GPU under torch.distributed.run
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(), dist.get_rank()
+    except ImportError:
+        pass
     if opts["miniVal"] and len(val):
         val = np.random.default_rng(0).permutation(val)[: max(1, int(round(opts["miniVal"] * len(val))))]  # seeded val subsample
     store_meta_info(opts, exp_dir)
     return cnn_train_dag(net.params, imdb, get_batch, learning_rate=opts["learningRate"], batch_size=opts["batchSize"],
                          num_epochs=opts["numEpochs"], train=train, val=val, cont=opts["cont"], exp_dir=exp_dir,
-                         width=100 * opts["numSeconds"], epoch_size=int(len(train) * opts["miniEpochRatio"]), device=opts["gpus"][0],
-                         max_steps_per_epoch=extra.get("max_steps_per_epoch"), loss_type=opts["lossType"])
+                         width=100 * opts["numSeconds"], epoch_size=int(len(train) * opts["miniEpochRatio"]),
+                         device=opts["gpus"][rank % len(opts["gpus"])], world=world, rank=rank, max_steps_per_epoch=extra.get("max_steps_per_epoch"), loss_type=opts["lossType"])

@@ -221,9 +221,9 @@ class Model:
         self.device = device
 
     def eval(self, inputs):
-        """dag.eval({'data', x}): runs the fused program, stores `prediction` (1 x 1 x K x N) in vars(end).value when it
+        """dag.eval({'data', x}): runs the network through the graph-level C ABI (net.py), stores `prediction` (1 x 1 x K x N) in vars(end).value when it
         is the last variable (losses removed), and returns it as N x K (`gather(squeeze(dag.vars(end).value))'`)."""
-        from .programs import StudentProgram, TeacherProgram
+        from .net import StudentNet, TeacherNet
 
         if isinstance(inputs, (list, tuple)):   # MATLAB-style {'data', x}
             inputs = dict(zip(inputs[0::2], inputs[1::2]))
@@ -231,7 +231,7 @@ class Model:
         n = x.shape[-1]
         if self.kind == "teacher":
             if self._prog is None or self._prog.N != n:
-                self._prog = TeacherProgram(self.params, n, input_mode="u8" if x.ndim == 3 else "hwcn224",
+                self._prog = TeacherNet(self.params, n, input_mode="u8" if x.ndim == 3 else "hwcn224",
                                             face_size=x.shape[0] if x.ndim == 3 else 48)
             out = self._prog.forward(x)
         else:
@@ -240,7 +240,7 @@ class Model:
                 raise ValueError("pool6.poolSize = %s does not match a %d-column input (expected %s): set it from the width bucket "
                                  "as compute_audio_feats.m:121-125 does" % (self.pool6, width, pool6_window(width)))
             if self._prog is None or self._prog.N != n or self._prog.W != width:
-                self._prog = StudentProgram(self.params, n, width)
+                self._prog = StudentNet(self.params, n, width)
             out = self._prog.forward(x, "test" if self.mode == "test" else "train")
         for v in self.vars:
             if v.name == "prediction":

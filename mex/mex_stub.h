@@ -24,6 +24,7 @@ double mxGetScalar(const mxArray*);
 char* mxArrayToString(const mxArray*);
 void mxFree(void*);
 mxArray* mxCreateNumericArray(mwSize, const mwSize*, mxClassID, mxComplexity);
+mxArray* mxCreateDoubleScalar(double);
 int mxInitGPU(void);
 const mxGPUArray* mxGPUCreateFromMxArray(const mxArray*);
 const void* mxGPUGetDataReadOnly(const mxGPUArray*);

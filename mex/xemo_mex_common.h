@@ -63,6 +63,29 @@ static xemo_array xm_in(const mxArray* a, const mxGPUArray** keep) {
   return r;
 }
 
+/* the same for network inputs, which may also be uint8 (grey faces, teacher/ferplus_baselines.m:181) */
+static xemo_array xm_in_any(const mxArray* a, const mxGPUArray** keep) {
+  xemo_array r;
+  const mwSize* d;
+  mwSize nd;
+  *keep = NULL;
+  memset(&r, 0, sizeof(r));
+  if (!a || mxIsEmpty(a)) return r;
+  nd = mxGetNumberOfDimensions(a);
+  d = mxGetDimensions(a);
+  r.h = (int64_t)d[0];
+  r.w = nd > 1 ? (int64_t)d[1] : 1;
+  r.c = nd > 2 ? (int64_t)d[2] : 1;
+  r.n = nd > 3 ? (int64_t)d[3] : 1;
+  if (mxIsGPUArray(a)) {
+    *keep = mxGPUCreateFromMxArray(a);
+    r.data = (void*)mxGPUGetDataReadOnly(*keep);
+  } else {
+    r.data = mxGetData(a);
+  }
+  return r;
+}
+
 /* allocate an output where the input lives (gpuArray in -> gpuArray out), return its xemo_array view */
 static xemo_array xm_out(mxArray** plhs, int on_gpu, int64_t h, int64_t w, int64_t c, int64_t n) {
   xemo_array r;

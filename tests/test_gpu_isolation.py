@@ -66,4 +66,4 @@ def test_gradients_under_the_device_decisions_are_arithmetic_close(stem):
         # 7e-3 either way: that residue is the train-mode logit error of the fp16 forward, 5e-3, carried by dpred)
         assert l1 < 2.5e-2, (k, l1)
         assert r1 < 6e-2, (k, r1)      # (max-norm: fc7f 3.8e-2 under the stem-by-linearity path)
-        assert l1 < 0.25 * l0 or l0 < 2.5e-2, (k, l0, l1)
+        assert l1 < 0.35 * l0 or l0 < 2.5e-2, (k, l0, l1)

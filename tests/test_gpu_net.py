@@ -101,7 +101,11 @@ def test_student_training_step_through_the_c_abi(nets, loss_type):
     assert set(g) == set(gp) == set(p)
     for k in g:
         assert g[k].shape == gp[k].shape == p[k].shape, k
-        assert rel_err(g[k], gp[k]) < 1e-4 or np.abs(gp[k]).max() < 1e-8, (k, rel_err(g[k], gp[k]))
+        if k.endswith("b") and not k.startswith("bn") and k != "fc8b":
+            # conv biases ahead of a train-mode BN: the true gradient is zero, both runs hold cancellation noise
+            assert np.abs(g[k] - gp[k]).max() <= 1e-3 * np.abs(gp[k[:-1] + "f"]).max(), k
+        else:
+            assert rel_err(g[k], gp[k]) < 1e-4, (k, rel_err(g[k], gp[k]))
         assert rel_err(q[k], qp[k]) < 1e-5, k
     exact = nets.distillation_student_step(_f64(p), {}, spec.astype(np.float64), tgt.astype(np.float64), lr=lr, ops=nets.TorchOps,
                                            loss_type=loss_type, instance_weights=w, update=False)
@@ -166,3 +170,17 @@ def test_c_abi_argument_errors(nets):
     net = StudentNet(p, 2, 100)
     with pytest.raises(_lib.XemoError):
         net._check(net.lib.xemo_net_set_input(net.handle, net.buffer("spec"), 12))     # wrong byte count
+
+
+def test_data_parallel_step_on_two_gpus():
+    """xemo_comm_* + the exchange inside the captured step: sum of local gradients, bit-identical parameters on all ranks
+    (tests/tools/dp_check.py under torch.distributed.run; needs two visible GPUs)."""
+    import os
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", os.path.join(ROOT, "tests", "tools", "dp_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "dp_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
