@@ -345,6 +345,7 @@ class StepDriver:
         if D.world > 1:
             self.step.comm = Comm.from_torch(self.ctx)
         self.step.student.set_hyper(lr=1e-4, momentum=0.9, weight_decay=5e-4, batch_size=global_batch)
+        self.step.student.set_overlap(args.overlap)
         self.faces_h, self.spec_h = synth_inputs(B, D.rank)
         with torch.cuda.stream(self.stream):
             self.stage_faces = torch.empty(self.faces_h.numel(), dtype=torch.uint8, device=dev)
@@ -383,10 +384,11 @@ class StepDriver:
         self.ctx.sync()
 
     def close(self):
-        if self.step.comm:
-            self.step.comm.close()
+        # networks first: their captured graphs hold NCCL nodes, and ncclCommDestroy waits for those graphs to be destroyed
         self.step.student.close()
         self.step.teacher.close()
+        if self.step.comm:
+            self.step.comm.close()
 
 
 def measure_step(D, args, B, global_batch, clocks=None, with_e2e=True):
@@ -704,6 +706,10 @@ def run_single_program(args, D):
     clk = clocks.stop(t0, clocks.mark())
     cpu = cpu_baseline(args, args.config, min(args.cpu_pairs, 4)) if (D.rank == 0 and D.world == 1 and not args.no_cpu_baseline) else None
     D.barrier()
+    if args.config == "c3":
+        net.close()           # (the network's graphs before the communicator they captured)
+        if comm:
+            comm.close()
     if D.rank == 0:
         total = B * D.world * args.steps
         value = total / (ms * 1e-3)
@@ -741,7 +747,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-mode", action="store_true")
     ap.add_argument("--single-line", action="store_true", help="skip the other scaling mode's measurement when N > 1")
+    ap.add_argument("--overlap", type=int, default=-1, choices=[-1, 0, 1],
+                    help="forked branches inside the captured step (teacher beside student forward, filter gradients beside the "
+                         "data-gradient chain): -1 = the library's rule (on for per-GPU batch <= 64), 0 off, 1 on")
+    ap.add_argument("--watchdog", type=int, default=int(os.environ.get("XEMO_BENCH_WATCHDOG", "0")),
+                    help="dump every thread's Python stack and exit after this many seconds (debugging hangs)")
     args = ap.parse_args()
+    if args.watchdog > 0:
+        import faulthandler
+
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))

@@ -318,8 +318,9 @@ int xemo_op_moments_average(xemo_ctx* ctx, float* moments, const float* batch_mo
 int xemo_op_grad_guard(xemo_ctx* ctx, const float* g, size_t n, int* state);
 int xemo_op_sgd_momentum_guarded(xemo_ctx* ctx, float* w, float* m, const float* g, size_t n, const float* hyper,
                                  float lr_mult, float wd_mult, float inv_grad_scale, void* w16, const int* guard);
+/* bm_scale: 1 / ranks when batch_moments holds the sum over data-parallel ranks (1 otherwise) */
 int xemo_op_moments_average_guarded(xemo_ctx* ctx, float* moments, const float* batch_moments, int n, float rate,
-                                    const int* guard);
+                                    float bm_scale, const int* guard);
 int xemo_op_cast_f32_f16(xemo_ctx* ctx, const float* src, size_t n, void* dst16);
 int xemo_op_cast_f16_f32(xemo_ctx* ctx, const void* src16, size_t n, float scale, float* dst);
 /* dst[o*outer_stride + inner_off + i] = value for o < outer, i < inner (masks structurally-zero filter slots) */
@@ -392,6 +393,10 @@ int xemo_distill_couple(xemo_net* teacher, xemo_net* student, const int* start, 
 /* the full distillation step (BASELINE.json's headline configuration) as ONE graph replay */
 int xemo_distill_step(xemo_net* teacher, xemo_net* student, xemo_comm* comm, const int* start, const int* end, int use_mean,
                       float lr, float momentum, float weight_decay, int batch_size);
+/* concurrency inside the captured student / distillation step: 1 = the teacher forward runs beside the student forward and
+ * the filter gradients beside the data-gradient chain (forked streams inside the graph); 0 = one stream; -1 (default) =
+ * on when the per-GPU batch is <= 64, where single kernels leave most SMs idle */
+int xemo_net_set_overlap(xemo_net* student, int mode);
 int xemo_net_reset_metrics(xemo_net* net);
 /* out[0] objective, out[1] classerror of the last step; out[2..2+K) correct and out[2+K..2+2K) count per class since the
  * reset (ErrorStats); out[2+2K] non-finite gradient in the last update, out[3+2K] updates skipped so far */
@@ -401,6 +406,8 @@ int xemo_net_metrics(xemo_net* net, float* out, int n_out);
  * 128-byte unique id and the host distributes it (MATLAB: labBroadcast; Python: torch.distributed / a file). */
 int xemo_comm_unique_id(void* id128);
 int xemo_comm_create(xemo_ctx* ctx, const void* id128, int rank, int world, xemo_comm** out);
+/* Destroy every network whose captured step used the communicator FIRST: the captured graphs hold NCCL nodes, and
+ * ncclCommDestroy waits until those graphs are gone. */
 void xemo_comm_destroy(xemo_comm* comm);
 int xemo_comm_allreduce_f32(xemo_comm* comm, float* device_buf, size_t n);
 

@@ -119,7 +119,7 @@ SIGNATURES = {
     "xemo_op_grad_guard": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "xemo_op_sgd_momentum_guarded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_float, c_float, c_float,
                                              c_void_p, c_void_p]),
-    "xemo_op_moments_average_guarded": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
+    "xemo_op_moments_average_guarded": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p]),
     "xemo_op_moments_average": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float]),
     "xemo_op_cast_f32_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "xemo_op_cast_f16_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p]),
@@ -151,6 +151,7 @@ SIGNATURES = {
     "xemo_distill_set_windows": (c_int, [c_void_p, c_void_p, c_void_p]),
     "xemo_distill_couple": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "xemo_distill_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_int]),
+    "xemo_net_set_overlap": (c_int, [c_void_p, c_int]),
     "xemo_net_reset_metrics": (c_int, [c_void_p]),
     "xemo_net_metrics": (c_int, [c_void_p, c_void_p, c_int]),
     "xemo_comm_unique_id": (c_int, [c_void_p]),
@@ -196,9 +197,19 @@ class Context:
         self.device = device
         self.profiler = None  # optional object with before(name, args) / after(name, args) hooks (bench.py)
         self.num_sms = self.lib.xemo_num_sms(h)
+        self.children = []    # weak references to objects living in this context (networks, communicators): closed first
+
+    def adopt(self, obj):
+        import weakref
+
+        self.children.append(weakref.ref(obj))
 
     def close(self):
         if getattr(self, "handle", None):
+            # networks before communicators (ncclCommDestroy waits for the graphs that captured it), both before the context
+            kids = [r() for r in getattr(self, "children", [])]
+            for k in sorted((k for k in kids if k is not None), key=lambda k: k.__class__.__name__ == "Comm"):
+                k.close()
             self.lib.xemo_destroy(self.handle)
             self.handle = None
 

@@ -1365,10 +1365,12 @@ static __global__ void sgd_momentum_kernel(float* __restrict__ w, float* __restr
 // BN moments moving average (dagnn.BatchNorm moments param: trainMethod 'average', learningRate 0.1):
 //   moments <- (1 - rate) * moments + rate * batch_moments
 static __global__ void moments_average_kernel(float* __restrict__ moments, const float* __restrict__ batch_moments, int n,
-                                       float rate, const int* __restrict__ guard = nullptr) {
+                                       float rate, const int* __restrict__ guard = nullptr, float bm_scale = 1.f) {
   if (guard && guard[0]) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) moments[i] = (1.f - rate) * moments[i] + rate * batch_moments[i];
+  // bm_scale = 1 / ranks when batch_moments holds the SUM over the data-parallel ranks (MatConvNet's parameter server sums
+  // the labs' moment "derivatives", each weighted by its sub-batch size, and divides by the global batch)
+  if (i < n) moments[i] = (1.f - rate) * moments[i] + rate * bm_scale * batch_moments[i];
 }
 
 static __global__ void f32_to_f16_kernel(const float* __restrict__ s, size_t n, __half* __restrict__ d) {

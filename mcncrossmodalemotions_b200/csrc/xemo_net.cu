@@ -18,6 +18,7 @@
 #include <cuda_fp16.h>
 #include <dlfcn.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -156,6 +157,12 @@ struct xemo_net {
   std::map<std::string, void*> buf;                     // named device buffers (activations, folded vectors, filters)
   // teacher
   std::vector<Block> blocks;
+  // SE blocks by linearity (the squeeze is linear in the 3x3 output: s = a3 (W3 mean_hw t2) + b3, so the gate is known before
+  // the expand convolution runs and the excite folds into its epilogue; u is never written or re-read) on the stages whose
+  // feature map is at least this wide -- measured on B200: a gain at 56 x 56 and 28 x 28, a loss at 14 x 14 and 7 x 7
+  // (profiles/r02_ab_experimental_options.json).  XEMO_SE_LIN_MIN_HW overrides (0 disables).
+  int se_lin_min_hw = 28;
+  bool se_lin(int hw) const { return se_lin_min_hw > 0 && hw >= se_lin_min_hw; }
   // student
   std::vector<ConvLayer> layers;
   std::map<std::string, size_t> seg;                    // offset (floats) of each parameter inside the flat buffers
@@ -177,6 +184,15 @@ struct xemo_net {
   xemo_net* g_step_teacher = nullptr;
   const int *g_step_start = nullptr, *g_step_end = nullptr;
   int *win_start = nullptr, *win_end = nullptr;         // coupling windows set by xemo_distill_set_windows
+  // concurrency inside the captured step (xemo_net_set_overlap): kernels of a small per-GPU batch leave most SMs idle, so
+  // independent branches run side by side -- the teacher forward beside the student forward (they meet at the loss) and the
+  // filter gradients beside the data-gradient chain
+  float* bm_flat = nullptr;                             // batch moments of all BN layers, contiguous
+  size_t bm_elems = 0;
+  float bm_scale = 1.f;                                 // 1 / ranks once the batch moments are summed across ranks
+  int overlap = -1;                                     // -1 auto (on for batch <= 64), 0 off, 1 on
+  cudaStream_t side_a = nullptr, side_b = nullptr;
+  bool use_overlap() const { return overlap < 0 ? N <= 64 : overlap != 0; }
   int g_step_mean = 0;
 
   template <typename T>
@@ -319,6 +335,7 @@ void fold_bn(xemo_net* n, const std::string& bn, int C, int reps, const std::str
 int teacher_finalize(xemo_net* n) {
   xemo_ctx* ctx = n->ctx;
   const int N = n->N;
+  if (const char* e = getenv("XEMO_SE_LIN_MIN_HW")) n->se_lin_min_hw = atoi(e);
   // stem: row-im2col filter G[k][r][0][s*4 + c] = F[r, s, c, k] in pixel-pair (block-diagonal) form [128][7][1][64]
   {
     const std::vector<float>& f = n->host["conv1f"];
@@ -373,7 +390,11 @@ int teacher_finalize(xemo_net* n) {
     n->alloc<__half>(b.pre + "t1", px * b.mid);
     n->alloc<__half>(b.pre + "t2", px * b.mid);
     if (b.proj) n->alloc<__half>(b.pre + "sc", px * b.cout);
-    if (n->kind == XEMO_NET_SENET50) {
+    if (n->kind == XEMO_NET_SENET50 && n->se_lin(o)) {
+      n->alloc<float>(b.pre + "m2", size_t(N) * b.mid);
+      n->alloc<float>(b.pre + "gs", size_t(N) * b.cout);
+      n->alloc<float>(b.pre + "gh", size_t(N) * b.cout);
+    } else if (n->kind == XEMO_NET_SENET50) {
       n->alloc<__half>(b.pre + "u", px * b.cout);
       n->alloc<float>(b.pre + "s", size_t(N) * b.cout);
       n->alloc<float>(b.pre + "g", size_t(N) * b.cout);
@@ -415,7 +436,12 @@ int teacher_record(xemo_net* n) {
       NET_OP(conv(n, cur, N, hw, hw, b.cin, H(p + "proj:w"), b.cout, 1, 1, b.stride, b.stride, kPad0, F(p + "proj:a"), F(p + "proj:b"), nullptr, 0, H(p + "sc")));
       sc = H(p + "sc");
     }
-    if (se) {
+    if (se && n->se_lin(o)) {
+      NET_OP(xemo_op_se_squeeze(ctx, H(p + "t2"), N, o * o, b.mid, F(p + "m2")));
+      NET_OP(xemo_op_se_gate_lin(ctx, F(p + "m2"), N, b.cout, b.mid, b.cout / 16, H(p + "c3:w"), F(p + "c3:a"), F(p + "c3:b"), F(p + "se1:w"), F(p + "se1:b"),
+                                 F(p + "se2:w"), F(p + "se2:b"), F(p + "gs"), F(p + "gh")));
+      NET_OP(xemo_op_conv_fwd_nc(ctx, H(p + "t2"), N, o, o, b.mid, H(p + "c3:w"), b.cout, 1, 1, 1, 1, 0, 0, 0, 0, F(p + "gs"), F(p + "gh"), sc, 1, H(p + "y")));
+    } else if (se) {
       NET_OP(conv(n, H(p + "t2"), N, o, o, b.mid, H(p + "c3:w"), b.cout, 1, 1, 1, 1, kPad0, F(p + "c3:a"), F(p + "c3:b"), nullptr, 0, H(p + "u")));
       NET_OP(xemo_op_se_squeeze(ctx, H(p + "u"), N, o * o, b.cout, F(p + "s")));
       NET_OP(xemo_op_se_gate(ctx, F(p + "s"), N, b.cout, b.cout / 16, F(p + "se1:w"), F(p + "se1:b"), F(p + "se2:w"), F(p + "se2:b"), F(p + "g")));
@@ -510,8 +536,17 @@ int student_finalize(xemo_net* n) {
       memcpy(&flat[n->seg[L.bn + "m"]], n->host[L.bn + "m"].data(), size_t(L.cout) * 4);
       memcpy(&flat[n->seg[L.bn + "b"]], n->host[L.bn + "b"].data(), size_t(L.cout) * 4);
       upload_f32(n, L.bn + ":moments", n->host[L.bn + "x"]);   // [mu | sigma]
-      n->alloc<float>(L.bn + ":batch_moments", size_t(2) * L.cout);
     }
+  }
+  // the batch moments of all layers in one buffer: under data parallelism they are summed across the ranks with one small
+  // all-reduce (the parameter server of cnn_train_dag sums the labs' moments like any other derivative)
+  n->bm_elems = 0;
+  for (const ConvLayer& L : n->layers) if (L.has_bn) n->bm_elems += size_t(2) * L.cout;
+  n->bm_flat = n->alloc<float>("batch_moments", n->bm_elems);
+  {
+    size_t o = 0;
+    for (const ConvLayer& L : n->layers)
+      if (L.has_bn) { n->buf[L.bn + ":batch_moments"] = n->bm_flat + o; o += size_t(2) * L.cout; }
   }
   n->master = upload_f32(n, "master", flat);
   n->momentum = n->alloc<float>("momentum", off);
@@ -560,6 +595,8 @@ int student_finalize(xemo_net* n) {
     }
     if (s != "conv1") n->alloc<__half>(s + ":packed", xemo_dgrad_pack_elems(L.cp, L.kp, L.fh, L.fw, L.sh, L.sw));
   }
+  XEMO_CUDA(ctx, cudaStreamCreateWithFlags(&n->side_a, cudaStreamNonBlocking));
+  XEMO_CUDA(ctx, cudaStreamCreateWithFlags(&n->side_b, cudaStreamNonBlocking));
   n->alloc<float>("pred32", size_t(N) * n->layers.back().kp);
   n->alloc<float>("scalars", 2);
   n->alloc<float>("class_stats", size_t(2) * n->K);
@@ -661,9 +698,12 @@ int student_record_forward_test(xemo_net* n) {
   return XEMO_OK;
 }
 
-// loss (when `loss`) and the backward sweep over layers [lo, hi) in reverse order
+// loss (when `loss`) and the backward sweep over layers [lo, hi) in reverse order.  With overlap the filter gradients of a
+// layer run on a forked stream (nothing downstream needs them before the exchange / update) while the primary stream
+// continues with the data gradient; the fork is joined before returning.
 int student_record_backward(xemo_net* n, int lo, int hi, bool loss) {
   xemo_ctx* ctx = n->ctx;
+  const bool fork = n->use_overlap() && n->side_b;
   const int N = n->N;
   const float gs = n->grad_scale, inv = 1.f / gs;
   auto H = [&](const std::string& k) { return n->get<__half>(k); };
@@ -710,6 +750,10 @@ int student_record_backward(xemo_net* n, int lo, int hi, bool loss) {
     const __half* dy = H(s + ":draw");
     const __half* x = i == 0 ? H("s2d") : H(n->layers[i - 1].name + ":out");
     float* gf = n->grad + n->seg[s + "f"];
+    if (fork) {
+      NET_OP(xemo_stream_wait(ctx, n->side_b, nullptr));
+      NET_OP(xemo_set_stream(ctx, n->side_b));
+    }
     if (stem) {
       NET_OP(xemo_op_conv_wgrad(ctx, x, N, n->s2d_hp, n->s2d_ow, 16, dy, L.kp, L.kp, 4, 1, 1, 1, 0, 0, 0, 0, gf, inv));
       NET_OP(xemo_op_stem_wgrad_finalize(ctx, n->get<double>("stem:ws"), n->w16 + n->seg[s + "f"], n->master + n->seg[s + "b"], n->get<double>(s + ":ws"), rows,
@@ -719,12 +763,14 @@ int student_record_backward(xemo_net* n, int lo, int hi, bool loss) {
       NET_OP(xemo_op_conv_wgrad(ctx, x, N, L.h, L.w, L.cp, dy, L.kp, L.kp, L.fh, L.fw, L.sh, L.sw, L.pad[0], L.pad[1], L.pad[2], L.pad[3], gf, inv));
     }
     if (!fused_bias) NET_OP(xemo_op_colsum(ctx, dy, rows, L.kp, L.kp, inv, n->grad + n->seg[s + "b"]));
+    if (fork) NET_OP(xemo_set_stream(ctx, nullptr));
     if (i > 0) {
       NET_OP(xemo_op_pack_dgrad_filters(ctx, n->w16 + n->seg[s + "f"], L.kp, L.fh, L.fw, L.cp, L.sh, L.sw, L.pad[0], L.pad[2], H(s + ":packed")));
       NET_OP(xemo_op_conv_dgrad(ctx, dy, N, L.h, L.w, L.cp, H(s + ":packed"), L.kp, L.fh, L.fw, L.sh, L.sw, L.pad[0], L.pad[1], L.pad[2], L.pad[3],
                                 H(n->layers[i - 1].name + ":dout")));
     }
   }
+  if (fork) NET_OP(xemo_stream_wait(ctx, nullptr, n->side_b));   // join
   return XEMO_OK;
 }
 
@@ -736,7 +782,8 @@ int student_record_update(xemo_net* n) {
   NET_OP(xemo_op_sgd_momentum_guarded(ctx, n->master, n->momentum, n->grad, n->nparam, n->hyper, 1.f, 1.f, 1.f, n->w16, n->guard));
   for (const ConvLayer& L : n->layers)
     if (L.has_bn)
-      NET_OP(xemo_op_moments_average_guarded(ctx, n->get<float>(L.bn + ":moments"), n->get<float>(L.bn + ":batch_moments"), 2 * L.cout, 0.1f, n->guard));
+      NET_OP(xemo_op_moments_average_guarded(ctx, n->get<float>(L.bn + ":moments"), n->get<float>(L.bn + ":batch_moments"), 2 * L.cout, 0.1f, n->bm_scale,
+                                             n->guard));
   return XEMO_OK;
 }
 
@@ -799,6 +846,8 @@ extern "C" void xemo_net_destroy(xemo_net* n) {
   if (n->ctx) cudaStreamSynchronize(n->ctx->primary);
   for (xemo_graph* g : {n->g_fwd, n->g_train, n->g_update, n->g_step}) xemo_graph_destroy(g);
   for (void* p : n->owned) cudaFree(p);
+  if (n->side_a) cudaStreamDestroy(n->side_a);
+  if (n->side_b) cudaStreamDestroy(n->side_b);
   delete n;
 }
 
@@ -1004,6 +1053,7 @@ extern "C" int xemo_student_forward(xemo_net* n, int train_mode, float* pred_out
 // differentiated, the head bucket after them on the same stream (one communicator: its operations stay ordered)
 static int record_backward_with_exchange(xemo_net* n, xemo_comm* comm) {
   xemo_ctx* ctx = n->ctx;
+  n->bm_scale = (comm && comm->world > 1) ? 1.f / float(comm->world) : 1.f;
   if (!comm || comm->world == 1) return student_record_backward(n, 0, int(n->layers.size()), true);
   NET_OP(student_record_backward(n, n->split_layer, int(n->layers.size()), true));
   NET_OP(xemo_stream_wait(ctx, comm->side, nullptr));          // fork
@@ -1015,6 +1065,7 @@ static int record_backward_with_exchange(xemo_net* n, xemo_comm* comm) {
   NET_OP(xemo_stream_wait(ctx, comm->side, nullptr));          // the head bucket needs conv5..conv1's gradients
   NET_OP(xemo_set_stream(ctx, comm->side));
   rc = xemo_comm_allreduce_f32(comm, n->grad, n->split_offset);
+  if (!rc) rc = xemo_comm_allreduce_f32(comm, n->bm_flat, n->bm_elems);   // BN batch moments: sum over ranks, averaged in the update
   NET_OP(xemo_set_stream(ctx, nullptr));
   if (rc) return rc;
   return xemo_stream_wait(ctx, nullptr, comm->side);           // join
@@ -1030,7 +1081,8 @@ extern "C" int xemo_student_train_step(xemo_net* n, xemo_comm* comm) {
   if (n->ctx->capturing) return record();
   if (!n->g_train || n->g_train_comm != comm) {
     xemo_graph_destroy(n->g_train);
-    n->g_train = nullptr;
+    xemo_graph_destroy(n->g_update);      // (the moments-average scale 1 / ranks is baked into the captured update)
+    n->g_train = n->g_update = nullptr;
     NET_OP(capture(n, &n->g_train, record));
     n->g_train_comm = comm;
     // the warm-up pass already ran the step once on these inputs (and accumulated its class counters): undo that part
@@ -1103,10 +1155,23 @@ extern "C" int xemo_distill_step(xemo_net* teacher, xemo_net* student, xemo_comm
   if (!start && !end) { start = student->win_start; end = student->win_end; }
   XEMO_REQUIRE(n->ctx, start && end, "distill_step: no frame windows (pass device arrays or call xemo_distill_set_windows)");
   NET_OP(xemo_net_set_hyper(student, lr, momentum, weight_decay, batch_size));
-  auto record = [&] {
-    NET_OP(teacher_record(teacher));
-    NET_OP(xemo_distill_couple(teacher, student, start, end, use_mean));
+  // teacher forward + coupling, then (or, with overlap, beside) the student's train-mode forward: they meet at the loss
+  auto forward_both = [&] {
+    const bool fork = student->use_overlap() && student->side_a;
+    if (fork) {
+      NET_OP(xemo_stream_wait(n->ctx, student->side_a, nullptr));
+      NET_OP(xemo_set_stream(n->ctx, student->side_a));
+    }
+    int rc = teacher_record(teacher);
+    if (!rc) rc = xemo_distill_couple(teacher, student, start, end, use_mean);
+    if (fork) NET_OP(xemo_set_stream(n->ctx, nullptr));
+    if (rc) return rc;
     NET_OP(student_record_forward_train(student));
+    if (fork) NET_OP(xemo_stream_wait(n->ctx, nullptr, student->side_a));
+    return int(XEMO_OK);
+  };
+  auto record = [&] {
+    NET_OP(forward_both());
     NET_OP(record_backward_with_exchange(student, comm));
     return student_record_update(student);
   };
@@ -1115,15 +1180,23 @@ extern "C" int xemo_distill_step(xemo_net* teacher, xemo_net* student, xemo_comm
     xemo_graph_destroy(n->g_step);
     n->g_step = nullptr;
     // eager pass without the update (kernel attributes), then the capture; the eager pass's class counters are undone
-    NET_OP(teacher_record(teacher));
-    NET_OP(xemo_distill_couple(teacher, student, start, end, use_mean));
-    NET_OP(student_record_forward_train(student));
+    NET_OP(forward_both());
     NET_OP(record_backward_with_exchange(student, comm));
     NET_OP(xemo_memset(n->ctx, n->buf["class_stats"], 0, size_t(2) * n->K * 4));
     NET_OP(capture(n, &n->g_step, record, false));
     n->g_step_comm = comm; n->g_step_teacher = teacher; n->g_step_start = start; n->g_step_end = end; n->g_step_mean = use_mean;
   }
   return xemo_graph_launch(n->ctx, n->g_step);
+}
+
+extern "C" int xemo_net_set_overlap(xemo_net* n, int mode) {
+  if (!n || n->kind != XEMO_NET_VGGVOX) return XEMO_ERR_INVALID;
+  if (mode != n->overlap) {     // baked into the captured sequences
+    xemo_graph_destroy(n->g_train); xemo_graph_destroy(n->g_step);
+    n->g_train = n->g_step = nullptr;
+  }
+  n->overlap = mode;
+  return XEMO_OK;
 }
 
 extern "C" int xemo_net_num_kernels(xemo_net* n) {

@@ -851,15 +851,15 @@ extern "C" int xemo_op_sgd_momentum(xemo_ctx* ctx, float* w, float* m, const flo
 }
 
 extern "C" int xemo_op_moments_average_guarded(xemo_ctx* ctx, float* moments, const float* batch_moments, int n, float rate,
-                                               const int* guard) {
+                                               float bm_scale, const int* guard) {
   XEMO_REQUIRE(ctx, moments && batch_moments, "moments_average: null pointer");
-  moments_average_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(moments, batch_moments, n, rate, guard);
+  moments_average_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(moments, batch_moments, n, rate, guard, bm_scale);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }
 
 extern "C" int xemo_op_moments_average(xemo_ctx* ctx, float* moments, const float* batch_moments, int n, float rate) {
-  return xemo_op_moments_average_guarded(ctx, moments, batch_moments, n, rate, nullptr);
+  return xemo_op_moments_average_guarded(ctx, moments, batch_moments, n, rate, 1.f, nullptr);
 }
 
 extern "C" int xemo_op_cast_f32_f16(xemo_ctx* ctx, const float* src, size_t n, void* dst16) {

@@ -70,6 +70,13 @@ class Comm:
         if rc:
             raise _lib.XemoError(rc, ctx.lib.xemo_last_error(ctx.handle).decode())
         self.handle = h
+        ctx.adopt(self)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     @classmethod
     def from_torch(cls, ctx):
@@ -87,9 +94,10 @@ class Comm:
         return cls(ctx, dist.get_rank(), dist.get_world_size(), bcast)
 
     def close(self):
-        if getattr(self, "handle", None):
+        """(close the networks whose captured steps used this communicator first)"""
+        if getattr(self, "handle", None) and getattr(self.ctx, "handle", None):
             self.ctx.lib.xemo_comm_destroy(self.handle)
-            self.handle = None
+        self.handle = None
 
 
 class Net:
@@ -100,6 +108,7 @@ class Net:
         h = VP()
         self._check(self.lib.xemo_net_create(self.ctx.handle, KINDS[kind], self.N, int(size), int(input_mode), self.K, C.byref(h)))
         self.handle = h
+        self.ctx.adopt(self)
         self.names = [self.lib.xemo_net_param_name(h, i).decode() for i in range(self.lib.xemo_net_num_params(h))]
         self.dims = {}
         for name in self.names:
@@ -146,9 +155,9 @@ class Net:
         self.ctx.sync()
 
     def close(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and getattr(self.ctx, "handle", None):
             self.lib.xemo_net_destroy(self.handle)
-            self.handle = None
+        self.handle = None
 
     def __del__(self):
         try:
@@ -186,6 +195,10 @@ class StudentNet(Net):
         self.W, self.loss_type = width, loss_type
         self._check(self.lib.xemo_net_set_loss(self.handle, LOSSES[loss_type], float(temperature), float(grad_scale)))
         self.hyper = dict(lr=1e-4, momentum=0.9, weight_decay=5e-4, batch_size=self.N)
+
+    def set_overlap(self, mode):
+        """-1 auto (on for batch <= 64), 0 one stream, 1 forked branches inside the captured step"""
+        self._check(self.lib.xemo_net_set_overlap(self.handle, int(mode)))
 
     def set_hyper(self, **kw):
         self.hyper.update({k: v for k, v in kw.items() if v is not None})
@@ -296,3 +309,9 @@ class DistillStep:
 
     def sync(self):
         self.ctx.sync()
+
+    def close(self):
+        self.student.close()        # (networks before the communicator their captured step used)
+        self.teacher.close()
+        if self.comm:
+            self.comm.close()

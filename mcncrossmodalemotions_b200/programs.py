@@ -150,10 +150,13 @@ class TeacherProgram(_Base):
         self.face_size = face_size
         self.mean3 = self.upload(np.asarray(average_image, np.float32))
         self.graph = None
-        # EXPERIMENTAL, off by default, not yet run on a GPU: SE blocks by linearity -- squeeze of the
-        # C/4-channel 3x3 output, gate, and the excite folded into the expand convolution's epilogue; the expand output u is
-        # never materialised (2.5 C instead of 5.25 C bytes per pixel of SE traffic).  XEMO_SE_LIN=1 enables.
-        self.se_lin = os.environ.get("XEMO_SE_LIN", "0") == "1"
+        # SE blocks by linearity -- squeeze of the C/4-channel 3x3 output, gate, and the excite folded into the expand
+        # convolution's epilogue; the expand output u is never materialised (2.5 C instead of 5.25 C bytes per pixel of SE
+        # traffic) -- on the stages whose feature map is at least se_lin_min_hw wide: measured on B200, a gain at 56 x 56 and
+        # 28 x 28, a loss at 14 x 14 and 7 x 7 (profiles/r02_ab_experimental_options.json).  XEMO_SE_LIN_MIN_HW overrides
+        # (0 disables; 7 = every stage).  The same rule as csrc/xemo_net.cu.
+        self.se_lin_min_hw = int(os.environ.get("XEMO_SE_LIN_MIN_HW", "28"))
+        self.se_lin = lambda hw: self.se_lin_min_hw > 0 and hw >= self.se_lin_min_hw
         self._load(params)
         self._alloc()
 
@@ -214,12 +217,12 @@ class TeacherProgram(_Base):
             A[pre + "t2"] = self.f16(N, ohw, ohw, mid)
             if proj:
                 A[pre + "sc"] = self.f16(N, ohw, ohw, cout)
-            if self.arch == "senet50":
+            if self.arch == "senet50" and self.se_lin(ohw):
+                A[pre + "m2"], A[pre + "gs"], A[pre + "gh"] = self.f32(N, mid), self.f32(N, cout), self.f32(N, cout)
+            elif self.arch == "senet50":
                 A[pre + "u"] = self.f16(N, ohw, ohw, cout)
                 A[pre + "s"] = self.f32(N, cout)
                 A[pre + "g"] = self.f32(N, cout)
-                if self.se_lin:
-                    A[pre + "m2"], A[pre + "gs"], A[pre + "gh"] = self.f32(N, mid), self.f32(N, cout), self.f32(N, cout)
             A[pre + "y"] = self.f16(N, ohw, ohw, cout)
             hw = ohw
         A["pool5"] = self.f16(N, 2048)
@@ -254,7 +257,7 @@ class TeacherProgram(_Base):
             else:
                 sc = cur
             a, b = W[pre + "bn3"]
-            if se and self.se_lin:
+            if se and self.se_lin(ohw):
                 ctx.op_se_squeeze(_p(A[pre + "t2"]), N, ohw * ohw, mid, _p(A[pre + "m2"]))
                 ctx.op_se_gate_lin(_p(A[pre + "m2"]), N, cout, mid, cout // 16, _p(W[pre + "c3"]), _p(a), _p(b), _p(W[pre + "se1"]),
                                    _p(W[pre + "se1b"]), _p(W[pre + "se2"]), _p(W[pre + "se2b"]), _p(A[pre + "gs"]), _p(A[pre + "gh"]))
@@ -718,7 +721,7 @@ class StudentProgram(_Base):
         ctx.op_sgd_momentum_guarded(_p(self.master), _p(self.momentum), _p(self.grad), self.nparam, _p(self.hyper), 1.0, 1.0, 1.0,
                                     _p(self.w16), guard)
         for bn, m in self.moments.items():
-            ctx.op_moments_average_guarded(_p(m), _p(self.batch_moments[bn]), m.numel(), 0.1, guard)
+            ctx.op_moments_average_guarded(_p(m), _p(self.batch_moments[bn]), m.numel(), 0.1, 1.0, guard)
 
     # ---- graph plumbing
     def _run(self, key, record):

@@ -97,6 +97,8 @@ def cnn_train_dag(params, imdb, get_batch, *, learning_rate, batch_size=64, num_
             order = order[: int(epoch_size)]   # 'epochSize': a random subset of the training set per epoch
         prog.reset_metrics()
         t0, seen, obj, err = time.time(), 0, 0.0, 0.0
+        # (a trailing partial batch is dropped: train-mode BN statistics and the captured graphs are tied to the batch size;
+        # upstream cnn_train_dag would run it as a smaller batch)
         steps = len(order) // batch_size
         if max_steps_per_epoch:
             steps = min(steps, max_steps_per_epoch)
@@ -122,18 +124,23 @@ def cnn_train_dag(params, imdb, get_batch, *, learning_rate, batch_size=64, num_
 
 
 def evaluate(prog, imdb, get_batch, indices, batch, tkey="logitTarget"):
-    """Validation pass: forward in test mode, class error against the arg-max teacher label."""
+    """Validation pass: forward in test mode, class error against the arg-max teacher label.  The last, partial batch is
+    processed too (padded with repeats of its last sample; the padding rows are discarded) -- test-mode BN makes every
+    sample independent of its batch."""
     wrong = total = 0
-    for it in range(len(indices) // batch):
-        idx = indices[it * batch : (it + 1) * batch]
+    for it in range((len(indices) + batch - 1) // batch):
+        idx = np.asarray(indices[it * batch : (it + 1) * batch])
+        n = len(idx)
+        if n < batch:
+            idx = np.concatenate([idx, np.repeat(idx[-1:], batch - n)])
         inputs = get_batch(imdb, idx)
-        pred = prog.forward(inputs["data"], "test")
+        pred = prog.forward(inputs["data"], "test")[:n]
         if tkey == "maxLabel":
-            label = np.asarray(inputs["maxLabel"]).reshape(-1).astype(np.int64) - 1
+            label = np.asarray(inputs["maxLabel"]).reshape(-1).astype(np.int64)[:n] - 1
         else:
-            label = inputs["logitTarget"].reshape(pred.shape[1], -1).argmax(axis=0)
+            label = inputs["logitTarget"].reshape(pred.shape[1], -1).argmax(axis=0)[:n]
         wrong += int((pred.argmax(axis=1) != label).sum())
-        total += len(idx)
+        total += n
     return {"classerror": wrong / max(total, 1), "num": total}
 
 

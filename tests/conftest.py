@@ -11,8 +11,6 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
-    config.addinivalue_line("markers", "gpu_experimental: needs a B200; covers default-OFF options that have not been measured yet "
-                                       "(not part of `-m gpu`; run with -m gpu_experimental)")
 
 
 def rel_err(a, b):

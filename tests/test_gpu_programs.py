@@ -61,6 +61,26 @@ def test_teacher_48x48_plumbing_config(nets):
     assert rel_err(TeacherProgram(p, n).forward(x), ref) < TOL
 
 
+@pytest.mark.parametrize("n", [8, 5])
+def test_se_blocks_by_linearity_on_every_stage_selection(nets, n, monkeypatch):
+    """SE blocks by linearity: squeeze(t2) -> gate (W3 folded in) -> expand convolution with the excite in its epilogue
+    (conv_fprop_kernel<64, true>).  Default: the 56 x 56 and 28 x 28 stages; also none and all of them (n = 5 makes the
+    7 x 7 stage's 128-row tiles straddle up to four images).  Every selection holds 1e-3 against the oracle."""
+    from mcncrossmodalemotions_b200.programs import TeacherProgram
+
+    p = nets.teacher_init("senet50")
+    x = nets.synth_faces(n)
+    ref = nets.teacher_forward(_f64(p), x.astype(np.float64), nets.TorchOps).reshape(8, n).T
+    out = {}
+    for min_hw in ("0", "28", "7"):
+        monkeypatch.setenv("XEMO_SE_LIN_MIN_HW", min_hw)
+        prog = TeacherProgram(p, n, use_graph=False)
+        assert prog.se_lin(56) == (min_hw != "0") and prog.se_lin(7) == (min_hw == "7")
+        out[min_hw] = prog.forward(x)
+        assert rel_err(out[min_hw], ref) < TOL, (min_hw, rel_err(out[min_hw], ref))
+    assert not np.array_equal(out["0"], out["28"]) and not np.array_equal(out["28"], out["7"])     # the paths do differ
+
+
 @pytest.mark.parametrize("width,n", [(300, 8), (100, 5), (400, 3)])
 def test_student_test_mode_forward(nets, width, n):
     from mcncrossmodalemotions_b200.programs import StudentProgram

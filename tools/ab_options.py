@@ -64,8 +64,8 @@ if __name__ == "__main__":
     which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["se_lin"]
     out = {"batch": n}
     if "se_lin" in which:
-        for v in ("0", "1"):
-            out["teacher senet50 XEMO_SE_LIN=" + v] = with_env({"XEMO_SE_LIN": v}, lambda: teacher_ms(n))
+        for v in ("0", "28", "14", "7"):
+            out["teacher senet50 XEMO_SE_LIN_MIN_HW=" + v] = with_env({"XEMO_SE_LIN_MIN_HW": v}, lambda: teacher_ms(n))
     if "costmodel" in which:
         v = os.environ.get("XEMO_CONV_COSTMODEL", "1")   # read once per process by the library: one value per run
         out["teacher senet50 XEMO_CONV_COSTMODEL=" + v] = teacher_ms(n)
