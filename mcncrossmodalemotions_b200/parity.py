@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import vl_nn
+from .arch import TEACHER_STAGES
 from .programs import BN_EPS, LOSS_TYPES, STUDENT_CONVS, STUDENT_POOLS, _out
 from .vl_nn import GpuArray, gather, gpuArray
 
@@ -227,3 +228,58 @@ class StudentProgramF32:
         out = self._export(self.grads)
         out.update({k: v.copy() for k, v in self.batch_moments.items()})
         return out
+
+
+class TeacherProgramF32:
+    """ResNet50 / SENet50 -ferplus forward (dag.mode = 'test', emoVoxCeleb/fetch_emovoxceleb_imdb.m:107,129) in
+    fp32-equivalent arithmetic: the dagnn layer sequence on gpuArrays through the boundary operators, convolutions in the
+    split-operand mode.  The fast program's worst logit over a 256-face batch sits at 1.06e-3 of the range (fp16 rounding of
+    the residual stream at each of the 16 bottlenecks); this mode is the one that holds 1e-3 on every logit."""
+
+    def __init__(self, params):
+        self.ctx = vl_nn.default_context()
+        self.arch = params["arch"]
+        self.p = {}
+        for k, v in params.items():
+            if isinstance(v, np.ndarray):
+                self.p[k] = v if k.endswith("x") else gpuArray(v.reshape(-1, 1) if v.ndim == 1 else v)
+
+    def _cbr(self, name, bn, t, stride=1, pad=0, relu=True):
+        t = vl_nn.vl_nnconv(t, self.p[name + "f"], None, pad=pad, stride=stride)
+        t, _ = vl_nn.vl_nnbnorm(t, self.p[bn + "m"], self.p[bn + "b"], epsilon=BN_EPS, moments=self.p[bn + "x"])
+        return vl_nn.vl_nnrelu(t) if relu else t
+
+    def forward(self, faces):
+        """faces: 224 x 224 x 3 x N normalised singles -> N x K logits."""
+        p, se = self.p, self.arch == "senet50"
+        prev = self.ctx.lib.xemo_get_conv_precision(self.ctx.handle)
+        self.ctx.set_conv_precision(1)
+        try:
+            cur = self._cbr("conv1", "bn1", gpuArray(faces), stride=2, pad=3)
+            cur = vl_nn.vl_nnpool(cur, (3, 3), pad=(0, 1, 0, 1), stride=2, method="max")
+            for si, (blocks, mid, cout, stride) in enumerate(TEACHER_STAGES):
+                for bi in range(blocks):
+                    pre = "s%db%d_" % (si + 2, bi + 1)
+                    s = stride if bi == 0 else 1
+                    u = self._cbr(pre + "c1", pre + "bn1", cur, stride=s)
+                    u = self._cbr(pre + "c2", pre + "bn2", u, pad=1)
+                    u = self._cbr(pre + "c3", pre + "bn3", u, relu=False)
+                    sc = self._cbr(pre + "proj", pre + "bnp", cur, stride=s, relu=False) if bi == 0 else cur
+                    if se:
+                        z = vl_nn.vl_nnglobalpool(u)
+                        z = vl_nn.vl_nnrelu(vl_nn.vl_nnconv(z, p[pre + "se1f"], p[pre + "se1b"]))
+                        a = vl_nn.vl_nnsigmoid(vl_nn.vl_nnconv(z, p[pre + "se2f"], p[pre + "se2b"]))
+                        cur = vl_nn.vl_nnrelu(vl_nn.vl_nnaxpy(a, u, sc))
+                    else:
+                        cur = vl_nn.vl_nnrelu(vl_nn.vl_nnaxpy(GpuArray((1, 1, cout, faces.shape[3]), self._ones(cout * faces.shape[3])), u, sc))
+            cur = vl_nn.vl_nnpool(cur, (7, 7), stride=1, method="avg")
+            out = vl_nn.vl_nnconv(cur, p["classifierf"], p["classifierb"])
+        finally:
+            self.ctx.set_conv_precision(prev)
+        k = out.shape[2]
+        return gather(out).reshape(k, -1).T.copy()
+
+    def _ones(self, n):
+        t = torch.ones(n, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        return t
