@@ -74,6 +74,13 @@ int xemo_num_sms(xemo_ctx* ctx);
  *                   as the three leading terms hi*hi + lo*hi + hi*lo on tcgen05 (one convolution over a 3x longer
  *                   reduction), fp32 accumulation -- fp32-equivalent results (~2^-22 per product) at 3x the MMA work. */
 enum { XEMO_CONV_F16 = 0, XEMO_CONV_F32X3 = 1 };
+/* Determinism option of the training step (also XEMO_DETERMINISTIC=1 at xemo_create): the filter-gradient kernel does
+ * not split its pixel reduction (every dF element has one producer instead of several `red.global.add` contributors),
+ * the bias column sums use one slab, the loss sums its warps in a fixed order.  The BatchNorm reductions add fp32 block
+ * partials with fp64 atomics (exact for these magnitudes, hence order-free).  Two runs of a step then produce bit-identical
+ * gradients; costs idle SMs on layers with few filter-gradient tiles. */
+int xemo_set_deterministic(xemo_ctx* ctx, int on);
+int xemo_get_deterministic(xemo_ctx* ctx);
 int xemo_set_conv_precision(xemo_ctx* ctx, int mode);
 int xemo_get_conv_precision(xemo_ctx* ctx);
 /* number of kernels this context has launched (graph replays count their kernel nodes) */

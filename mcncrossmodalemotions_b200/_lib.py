@@ -113,6 +113,8 @@ SIGNATURES = {
                                   c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "xemo_op_loss": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_int, c_float,
                              c_float, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "xemo_set_deterministic": (c_int, [c_void_p, c_int]),
+    "xemo_get_deterministic": (c_int, [c_void_p]),
     "xemo_set_conv_precision": (c_int, [c_void_p, c_int]),
     "xemo_get_conv_precision": (c_int, [c_void_p]),
     "xemo_op_sgd_momentum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_float, c_float, c_float, c_void_p]),
@@ -232,7 +234,7 @@ class Context:
 
     def __getattr__(self, name):
         if name.startswith(("op_", "vl_")) or name in ("sync", "h2d", "d2h", "memset", "capture_begin", "graph_launch", "set_stream", "stream_wait",
-                                                     "set_conv_precision"):
+                                                     "set_conv_precision", "set_deterministic"):
             return lambda *a: self.call(name, *a)
         raise AttributeError(name)
 

@@ -225,8 +225,11 @@ inline int pick_chunk(int n) { return (n % 64 == 0) ? 64 : (n % 32 == 0) ? 32 : 
 
 // x: NHWC fp16 [N][H][W][Cin] (Cin % 16 == 0); dy: [P][ldy] fp16 (ldy % 16 == 0, Kout <= ldy);
 // dF: [Kout][R][S][Cin] fp32, accumulated into.
+// deterministic: no split of the pixel reduction -- every dF element is produced by exactly one work item, so its value
+// does not depend on the order in which `red.global.add` operations land (at the price of idle SMs on layers with few
+// output tiles)
 inline bool conv_wgrad_plan(WgradPlan* plan, const ConvGeom& g, const __half* x, const __half* dy, int ldy, float* dF,
-                            float scale, int num_sms, bool encode_maps = true) {
+                            float scale, int num_sms, bool encode_maps = true, bool deterministic = false) {
   if (g.Cin % 16 || ldy % 16 || g.Kout > ldy) {
     fprintf(stderr, "[xemo] wgrad: Cin=%d / ldy=%d must be multiples of 16 and Kout=%d <= ldy\n", g.Cin, ldy, g.Kout);
     return false;
@@ -293,7 +296,7 @@ inline bool conv_wgrad_plan(WgradPlan* plan, const ConvGeom& g, const __half* x,
   int splits = (2 * num_sms) / base_items;
   const int max_splits = (pix_blocks + 7) / 8;
   if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  if (splits < 1 || deterministic) splits = 1;
   p.pix_blocks_per_split = (pix_blocks + splits - 1) / splits;
   p.splits = (pix_blocks + p.pix_blocks_per_split - 1) / p.pix_blocks_per_split;
   const int stage_bytes = wgrad_stage_bytes(T, block_c, p.pix, mt);

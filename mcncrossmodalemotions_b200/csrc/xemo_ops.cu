@@ -29,6 +29,11 @@ extern "C" int xemo_create(int device, void* cuda_stream, xemo_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) return XEMO_ERR_CUDA;
   if (!tma_api().ok) return XEMO_ERR_NO_DEVICE;
   xemo_ctx* ctx = new xemo_ctx();
+  if (const char* e = getenv("XEMO_DETERMINISTIC")) ctx->deterministic = e[0] == '1';
+  if (cudaMalloc(&ctx->scratch, kScratchFloats * sizeof(float)) != cudaSuccess) {
+    delete ctx;
+    return XEMO_ERR_NOMEM;
+  }
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   if (cuda_stream) {
@@ -49,6 +54,7 @@ extern "C" int xemo_create(int device, void* cuda_stream, xemo_ctx** out) {
 extern "C" void xemo_destroy(xemo_ctx* ctx) {
   if (!ctx) return;
   if (ctx->own_stream) cudaStreamDestroy(ctx->primary);
+  if (ctx->scratch) cudaFree(ctx->scratch);
   delete ctx;
 }
 
@@ -65,6 +71,12 @@ extern "C" int xemo_set_conv_precision(xemo_ctx* ctx, int mode) {
   return XEMO_OK;
 }
 extern "C" int xemo_get_conv_precision(xemo_ctx* ctx) { return ctx ? ctx->conv_precision : -1; }
+extern "C" int xemo_set_deterministic(xemo_ctx* ctx, int on) {
+  if (!ctx) return XEMO_ERR_INVALID;
+  ctx->deterministic = on ? 1 : 0;
+  return XEMO_OK;
+}
+extern "C" int xemo_get_deterministic(xemo_ctx* ctx) { return ctx ? ctx->deterministic : -1; }
 extern "C" uint64_t xemo_launch_count(xemo_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int xemo_h2d(xemo_ctx* ctx, void* dst, const void* src, size_t bytes) {
@@ -409,7 +421,7 @@ extern "C" int xemo_op_conv_wgrad(xemo_ctx* ctx, const void* x16, int N, int H, 
   ConvGeom g{N, H, W, Cin, Kout, R, S, sh, sw, pt, pb, pl, pr};
   WgradPlan plan;
   if (!conv_wgrad_plan(&plan, g, static_cast<const __half*>(x16), static_cast<const __half*>(dy16), ldy, dF, scale,
-                       ctx->num_sms))
+                       ctx->num_sms, true, ctx->deterministic != 0))
     return fail(ctx, XEMO_ERR_INVALID, "conv_wgrad: unsupported geometry Cin=%d Kout=%d ldy=%d R=%d S=%d", Cin, Kout, ldy, R, S);
   cudaError_t err = conv_wgrad_run(plan, ctx->stream);
   if (err != cudaSuccess) return fail(ctx, XEMO_ERR_CUDA, "conv_wgrad launch failed: %s", cudaGetErrorString(err));
@@ -423,7 +435,7 @@ extern "C" int xemo_op_colsum(xemo_ctx* ctx, const void* dy16, size_t P, int ld,
   int row_blocks = int((P + 511) / 512);
   const int cap = ctx->num_sms * 4;
   if (row_blocks > cap) row_blocks = cap;
-  if (row_blocks < 1) row_blocks = 1;
+  if (row_blocks < 1 || ctx->deterministic) row_blocks = 1;   // (one slab: no fp32 atomics between slabs)
   dim3 grid((C + 31) / 32, row_blocks), block(32, 8);
   colsum_kernel<__half><<<grid, block, 0, ctx->stream>>>(static_cast<const __half*>(dy16), P, ld, C, scale, out);
   XEMO_LAUNCHED(ctx, 1);
@@ -673,13 +685,22 @@ extern "C" int xemo_op_se_squeeze(xemo_ctx* ctx, const void* u16, int N, int HW,
 extern "C" int xemo_op_se_gate(xemo_ctx* ctx, const float* s, int N, int C, int Cr, const float* w1, const float* b1,
                                const float* w2, const float* b2, float* gate) {
   XEMO_REQUIRE(ctx, s && w1 && w2 && gate && kSeSpb * (C + Cr) * 4 <= 48 * 1024 && C % 128 == 0, "se_gate: C must be a multiple of 128 and (C + Cr) <= 6144");
+  // two wide launches (hidden units, then gates) when the hidden units fit the context workspace and C splits into
+  // 256-channel blocks; XEMO_SE_GATE_SPLIT=0 restores the one-launch kernel (A/B measurements)
+  static const bool split_enabled = [] { const char* e = getenv("XEMO_SE_GATE_SPLIT"); return !(e && e[0] == '0'); }();
+  if (split_enabled && size_t(N) * Cr <= kScratchFloats && C % 256 == 0 && kSeFcSpb * Cr * 4 <= 48 * 1024) {
+    const dim3 g1((N + kSeFcSpb - 1) / kSeFcSpb, (Cr + 7) / 8), g2((N + kSeFcSpb - 1) / kSeFcSpb, C / 256);
+    se_fc1_kernel<<<g1, 256, 0, ctx->stream>>>(s, N, C, Cr, w1, b1, ctx->scratch);
+    se_fc2_kernel<<<g2, 256, size_t(kSeFcSpb) * Cr * 4, ctx->stream>>>(ctx->scratch, N, C, Cr, w2, b2, gate);
+    XEMO_LAUNCHED(ctx, 2);
+    return XEMO_OK;
+  }
   const int threads = C <= 512 ? 512 : 1024;  // latency-bound: many warps keep enough weight loads in flight
   se_gate_kernel<<<(N + kSeSpb - 1) / kSeSpb, threads, size_t(kSeSpb) * (C + Cr) * 4, ctx->stream>>>(s, N, C, Cr, w1, b1, w2, b2, gate);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }
 
-// EXPERIMENTAL (default-off): SE block by linearity -- see se_gate_lin_kernel / conv_fprop_kernel<64, true>
 extern "C" int xemo_op_se_gate_lin(xemo_ctx* ctx, const float* m2, int N, int C, int Cm, int Cr, const void* w3_16, const float* a3,
                                    const float* b3, const float* w1, const float* b1, const float* w2t, const float* b2,
                                    float* nc_scale, float* nc_shift) {
@@ -806,9 +827,11 @@ extern "C" int xemo_op_loss(xemo_ctx* ctx, const void* x, int x_f32, int ldx, co
                             float* scalars, float* class_stats, int* max_label) {
   XEMO_REQUIRE(ctx, x && t && scalars && C >= 1 && C <= kLossMaxC && C <= ldx && C <= ldt && (!dx || C <= lddx), "loss: bad arguments");
   XEMO_REQUIRE(ctx, loss_type >= 0 && loss_type <= 2 && T > 0.f, "loss: loss_type must be 0 (softmax CE), 1 (euclidean) or 2 (huber), T / sigma > 0");
-  const int grid = (N + 127) / 128;
+  // (deterministic: one block of up to 1024 samples, whose warps' partial sums are added in a fixed order)
+  const int threads = ctx->deterministic ? 1024 : 128;
+  const int grid = (N + threads - 1) / threads;
 #define XEMO_LOSS(TX, TDX)                                                                                                     \
-  loss_fused_kernel<TX, TDX><<<grid, 128, 0, ctx->stream>>>(static_cast<const TX*>(x), ldx, t, ldt, w, N, C, loss_type, T,     \
+  loss_fused_kernel<TX, TDX><<<grid, threads, 0, ctx->stream>>>(static_cast<const TX*>(x), ldx, t, ldt, w, N, C, loss_type, T,     \
                                                            logit_targets, dzdy, grad_scale, static_cast<TDX*>(dx), lddx, scalars, \
                                                            class_stats, max_label)
   if (x_f32 && dx_f32) XEMO_LOSS(float, float);

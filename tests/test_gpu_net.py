@@ -190,3 +190,30 @@ def test_data_parallel_step_on_two_gpus():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29517", os.path.join(ROOT, "tests", "tools", "dp_check.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "dp_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_deterministic_option_gives_bit_identical_training_steps(nets):
+    """xemo_set_deterministic: two independent runs of two training steps end with bit-identical gradients and parameters
+    (the default mode's filter gradients differ in their last bits: several split-K contributors per element)."""
+    from mcncrossmodalemotions_b200 import _lib
+    from mcncrossmodalemotions_b200.net import StudentNet
+
+    n, width = 8, 100
+    p = nets.student_randomize_bn(nets.student_init())
+    spec, tgt = nets.synth_spectrograms(n, width), nets.synth_teacher_logits(n)
+    runs = []
+    for _ in range(2):
+        ctx = _lib.Context(0)
+        ctx.set_deterministic(1)
+        assert ctx.lib.xemo_get_deterministic(ctx.handle) == 1
+        net = StudentNet(p, n, width, ctx=ctx)
+        net.set_hyper(lr=1e-3, batch_size=n)
+        for _ in range(2):
+            net.train_step(spec, tgt)
+        runs.append((net.export_grads(), net.export_params(), net.metrics()["objective"]))
+        net.close()
+    (g0, q0, o0), (g1, q1, o1) = runs
+    assert o0 == o1
+    for k in g0:
+        assert np.array_equal(g0[k], g1[k]), k
+        assert np.array_equal(q0[k], q1[k]), k
