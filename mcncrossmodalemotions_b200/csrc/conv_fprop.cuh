@@ -69,7 +69,7 @@ struct ConvFpropParams {
   // ONCE per CTA (k_iters slots) instead of once per tile -- for the K = 64..576 layers at 56 x 56 and the stems the
   // per-tile filter re-fetch is 40-65 % of the L2->smem traffic and of the TMA row requests
   int b_resident;
-  // per-(image, channel) epilogue vectors (kNC instantiation only; EXPERIMENTAL, see conv_fprop_kernel): the SE block's
+  // per-(image, channel) epilogue vectors (kNC instantiation only, see conv_fprop_kernel): the SE block's
   // excite fused into its expand convolution,  y = relu(gate[n,c] * (a[c]*acc + b[c]) + shortcut)
   //   = relu(nc_scale[n,c]*acc + nc_shift[n,c] + residual),  nc_scale = gate*a, nc_shift = gate*b  ([N][Kout] fp32)
   const float* nc_scale;
@@ -103,7 +103,7 @@ __device__ __forceinline__ uint32_t swz_off(int row, int chunk, int pitch, uint3
 
 __device__ __forceinline__ void epi_bar_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 
-// kNC = true (EXPERIMENTAL, default-off path): scale / shift are per (image, channel) instead of per channel.  A separate
+// kNC = true (SE blocks by linearity): scale / shift are per (image, channel) instead of per channel.  A separate
 // instantiation so that the code of the default kernels is untouched.
 template <int BK, bool kNC = false>
 __global__ void __launch_bounds__(kConvThreads, 1)

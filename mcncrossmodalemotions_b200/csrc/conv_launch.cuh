@@ -35,7 +35,7 @@ struct ConvEpilogue {
   int strided_out = 0;
   long long out_sn = 0, out_sh = 0, out_sw = 0;
   int allow_tma_epilogue = 1;  // 0 forces the direct-store epilogue
-  // EXPERIMENTAL per-(image, channel) scale / shift ([N][Kout] fp32; replaces scale / shift), fp16 TMA-store outputs only
+  // per-(image, channel) scale / shift ([N][Kout] fp32; replaces scale / shift), fp16 TMA-store outputs only
   const float* nc_scale = nullptr;
   const float* nc_shift = nullptr;
 };
@@ -177,7 +177,7 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
 
 inline cudaError_t conv_fprop_run(const ConvPlan& plan, cudaStream_t stream) {
   cudaError_t err = cudaSuccess;
-  if (plan.p.nc_scale) {   // EXPERIMENTAL per-(image, channel) epilogue: BK = 64 only (checked by the plan)
+  if (plan.p.nc_scale) {   // per-(image, channel) epilogue: BK = 64 only (checked by the plan)
     static bool attr = false;
     if (!attr) { err = cudaFuncSetAttribute(conv_fprop_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget); attr = true; }
     if (err != cudaSuccess) return err;

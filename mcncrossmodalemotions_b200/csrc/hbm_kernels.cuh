@@ -1114,63 +1114,7 @@ static __global__ void se_gate_kernel(const float* __restrict__ s, int N, int C,
   }
 }
 
-// The same gate as two wide launches (the one-block-per-sample-pair kernel above streams both weight matrices through
-// every block: 16 blocks x 2 MB at 32 faces -- latency-bound, 21-43 us per call):
-//   se_fc1_kernel  grid (ceil(N/4), ceil(Cr/8)), 256 threads: warp w computes hidden unit j = 8 blockIdx.y + w for 4 samples
-//   se_fc2_kernel  grid (ceil(N/4), C/256),      256 threads: thread c computes gate[n][c] for 4 samples
-constexpr int kSeFcSpb = 4;
-static __global__ void se_fc1_kernel(const float* __restrict__ s, int N, int C, int Cr, const float* __restrict__ w1,
-                                     const float* __restrict__ b1, float* __restrict__ hid /* [N][Cr] */) {
-  const int n0 = blockIdx.x * kSeFcSpb;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.y * 8 + warp;
-  if (j >= Cr) return;
-  float t[kSeFcSpb];
-#pragma unroll
-  for (int q = 0; q < kSeFcSpb; ++q) t[q] = 0.f;
-  const float* wr = w1 + size_t(j) * C;
-  for (int c = lane * 4; c < C; c += 128) {   // C is a multiple of 128
-    const float4 w = *reinterpret_cast<const float4*>(wr + c);
-#pragma unroll
-    for (int q = 0; q < kSeFcSpb; ++q) {
-      if (n0 + q < N) {
-        const float4 v = *reinterpret_cast<const float4*>(s + size_t(n0 + q) * C + c);
-        t[q] = fmaf(w.x, v.x, fmaf(w.y, v.y, fmaf(w.z, v.z, fmaf(w.w, v.w, t[q]))));
-      }
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < kSeFcSpb; ++q) {
-    const float r = warp_sum(t[q]);
-    if (lane == 0 && n0 + q < N) hid[size_t(n0 + q) * Cr + j] = fmaxf(r + (b1 ? b1[j] : 0.f), 0.f);
-  }
-}
-static __global__ void se_fc2_kernel(const float* __restrict__ hid, int N, int C, int Cr, const float* __restrict__ w2t,
-                                     const float* __restrict__ b2, float* __restrict__ gate) {
-  extern __shared__ float sh[];   // [kSeFcSpb][Cr]
-  const int n0 = blockIdx.x * kSeFcSpb;
-  for (int i = threadIdx.x; i < kSeFcSpb * Cr; i += blockDim.x) {
-    const int q = i / Cr, j = i - q * Cr;
-    sh[i] = (n0 + q < N) ? hid[size_t(n0 + q) * Cr + j] : 0.f;
-  }
-  __syncthreads();
-  const int c = blockIdx.y * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float t[kSeFcSpb];
-#pragma unroll
-  for (int q = 0; q < kSeFcSpb; ++q) t[q] = b2 ? b2[c] : 0.f;
-#pragma unroll 8
-  for (int j = 0; j < Cr; ++j) {
-    const float w = w2t[size_t(j) * C + c];
-#pragma unroll
-    for (int q = 0; q < kSeFcSpb; ++q) t[q] = fmaf(w, sh[q * Cr + j], t[q]);
-  }
-#pragma unroll
-  for (int q = 0; q < kSeFcSpb; ++q)
-    if (n0 + q < N) gate[size_t(n0 + q) * C + c] = 1.f / (1.f + __expf(-t[q]));
-}
-
-// EXPERIMENTAL (default-off SE-by-linearity path).  The SE squeeze is linear in the bottleneck's
+// SE blocks by linearity (default on the 56 x 56 / 28 x 28 stages).  The SE squeeze is linear in the bottleneck's
 // 3x3 output t2:  s[n,c] = mean_hw(a3[c] * (W3 t2)[n,.,c] + b3[c]) = a3[c] * (W3[c,:] . mean_hw t2[n,:]) + b3[c],
 // so the expand convolution's output u never has to exist before the gate is known.  This kernel takes
 // m2 = mean_hw(t2) ([N][Cm], se_squeeze_kernel on the C/4-channel tensor), forms s, runs the two gate FCs and emits the

@@ -20,7 +20,6 @@ struct xemo_ctx {
   uint64_t launches = 0;        // kernels launched (eager) + kernel nodes replayed
   bool capturing = false;
   uint64_t capture_mark = 0;    // value of `launches` when the capture began
-  float* scratch = nullptr;     // kScratchFloats floats of per-context workspace (SE gate hidden units), allocated at create
   int deterministic = 0;        // xemo_set_deterministic: no order-dependent floating-point reductions in the training step
   int conv_precision = 0;       // xemo_set_conv_precision: 0 = fp16 operands, 1 = split fp16 x 3 (fp32-equivalent)
 };
@@ -32,8 +31,6 @@ struct xemo_graph {
 };
 
 namespace xemo {
-
-constexpr size_t kScratchFloats = 256 * 1024;
 
 inline int fail(xemo_ctx* ctx, int code, const char* fmt, ...) {
   char buf[512];

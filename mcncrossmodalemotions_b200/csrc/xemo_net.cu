@@ -94,7 +94,11 @@ extern "C" int xemo_comm_create(xemo_ctx* ctx, const void* id128, int rank, int 
     delete c;
     return fail(ctx, XEMO_ERR_CUDA, "ncclCommInitRank failed: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
   }
-  XEMO_CUDA(ctx, cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  // highest priority: the all-reduce kernels must get SMs as soon as CTAs of the (persistent, all-SM) convolution kernels
+  // retire, or the exchange trails the backward pass instead of hiding behind it; captured nodes inherit the priority
+  int prio_lo = 0, prio_hi = 0;
+  XEMO_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  XEMO_CUDA(ctx, cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi));
   XEMO_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   XEMO_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   *out = c;
@@ -188,11 +192,13 @@ struct xemo_net {
   // independent branches run side by side -- the teacher forward beside the student forward (they meet at the loss) and the
   // filter gradients beside the data-gradient chain
   float* bm_flat = nullptr;                             // batch moments of all BN layers, contiguous
+  float* mom_flat = nullptr;                            // the moments parameters at the same offsets
   size_t bm_elems = 0;
   float bm_scale = 1.f;                                 // 1 / ranks once the batch moments are summed across ranks
   int overlap = -1;                                     // -1 auto (on for batch <= 64), 0 off, 1 on
   cudaStream_t side_a = nullptr, side_b = nullptr;
   bool use_overlap() const { return overlap < 0 ? N <= 64 : overlap != 0; }
+  bool packs_ahead = false;                             // the dgrad filter packs were recorded beside the forward pass
   int g_step_mean = 0;
 
   template <typename T>
@@ -535,7 +541,6 @@ int student_finalize(xemo_net* n) {
     if (L.has_bn) {
       memcpy(&flat[n->seg[L.bn + "m"]], n->host[L.bn + "m"].data(), size_t(L.cout) * 4);
       memcpy(&flat[n->seg[L.bn + "b"]], n->host[L.bn + "b"].data(), size_t(L.cout) * 4);
-      upload_f32(n, L.bn + ":moments", n->host[L.bn + "x"]);   // [mu | sigma]
     }
   }
   // the batch moments of all layers in one buffer: under data parallelism they are summed across the ranks with one small
@@ -544,9 +549,19 @@ int student_finalize(xemo_net* n) {
   for (const ConvLayer& L : n->layers) if (L.has_bn) n->bm_elems += size_t(2) * L.cout;
   n->bm_flat = n->alloc<float>("batch_moments", n->bm_elems);
   {
+    // ... and the moments parameters ([mu | sigma] per layer) at the same offsets of a second buffer: one moving-average launch
+    std::vector<float> mom(n->bm_elems);
     size_t o = 0;
     for (const ConvLayer& L : n->layers)
-      if (L.has_bn) { n->buf[L.bn + ":batch_moments"] = n->bm_flat + o; o += size_t(2) * L.cout; }
+      if (L.has_bn) { memcpy(&mom[o], n->host[L.bn + "x"].data(), size_t(2) * L.cout * 4); o += size_t(2) * L.cout; }
+    n->mom_flat = upload_f32(n, "moments", mom);
+    o = 0;
+    for (const ConvLayer& L : n->layers)
+      if (L.has_bn) {
+        n->buf[L.bn + ":batch_moments"] = n->bm_flat + o;
+        n->buf[L.bn + ":moments"] = n->mom_flat + o;
+        o += size_t(2) * L.cout;
+      }
   }
   n->master = upload_f32(n, "master", flat);
   n->momentum = n->alloc<float>("momentum", off);
@@ -619,11 +634,22 @@ int student_stem_conv(xemo_net* n, const __half* wt, const float* scale, const f
               scale ? n->get<float>("stem:scale2") : nullptr, n->get<float>("stem:shift2"), nullptr, relu, dst);
 }
 
+int student_record_packs(xemo_net* n);
+
 int student_record_forward_train(xemo_net* n) {
   xemo_ctx* ctx = n->ctx;
   const int N = n->N;
   auto H = [&](const std::string& k) { return n->get<__half>(k); };
   auto F = [&](const std::string& k) { return n->get<float>(k); };
+  // with overlap: the data-gradient filter packs (weights only) run on a forked stream beside the forward pass
+  n->packs_ahead = n->use_overlap() && n->side_b && ctx->stream == ctx->primary;
+  if (n->packs_ahead) {
+    NET_OP(xemo_stream_wait(ctx, n->side_b, nullptr));
+    NET_OP(xemo_set_stream(ctx, n->side_b));
+    const int rc = student_record_packs(n);
+    NET_OP(xemo_set_stream(ctx, nullptr));
+    if (rc) return rc;
+  }
   NET_OP(xemo_op_spec_s2d(ctx, F("spec"), 512, n->W, N, 1, 1, n->s2d_hp, n->s2d_ow, H("s2d")));
   NET_OP(xemo_op_stem_autocorr(ctx, H("s2d"), N, n->s2d_hp, n->s2d_ow, n->layers[0].oh, n->get<double>("stem:ws")));
   const __half* cur = H("s2d");
@@ -656,6 +682,7 @@ int student_record_forward_train(xemo_net* n) {
       NET_OP(xemo_op_affine_act(ctx, cur, rows, L.cout, F(s + ":a"), F(s + ":b"), 1, H(s + ":out")));
     cur = H(s + ":out");
   }
+  if (n->packs_ahead) NET_OP(xemo_stream_wait(ctx, nullptr, n->side_b));   // join before the backward pass
   return XEMO_OK;
 }
 
@@ -694,6 +721,16 @@ int student_record_forward_test(xemo_net* n) {
       dst = H(s + ":out");
     }
     cur = dst;
+  }
+  return XEMO_OK;
+}
+
+// the parity-decomposed (flipped / transposed) filter copies of the data-gradient convolutions: they depend on the weights only
+int student_record_packs(xemo_net* n) {
+  for (size_t i = 1; i < n->layers.size(); ++i) {
+    const ConvLayer& L = n->layers[i];
+    NET_OP(xemo_op_pack_dgrad_filters(n->ctx, n->w16 + n->seg[L.name + "f"], L.kp, L.fh, L.fw, L.cp, L.sh, L.sw, L.pad[0], L.pad[2],
+                                      n->get<__half>(L.name + ":packed")));
   }
   return XEMO_OK;
 }
@@ -765,7 +802,8 @@ int student_record_backward(xemo_net* n, int lo, int hi, bool loss) {
     if (!fused_bias) NET_OP(xemo_op_colsum(ctx, dy, rows, L.kp, L.kp, inv, n->grad + n->seg[s + "b"]));
     if (fork) NET_OP(xemo_set_stream(ctx, nullptr));
     if (i > 0) {
-      NET_OP(xemo_op_pack_dgrad_filters(ctx, n->w16 + n->seg[s + "f"], L.kp, L.fh, L.fw, L.cp, L.sh, L.sw, L.pad[0], L.pad[2], H(s + ":packed")));
+      if (!n->packs_ahead)
+        NET_OP(xemo_op_pack_dgrad_filters(ctx, n->w16 + n->seg[s + "f"], L.kp, L.fh, L.fw, L.cp, L.sh, L.sw, L.pad[0], L.pad[2], H(s + ":packed")));
       NET_OP(xemo_op_conv_dgrad(ctx, dy, N, L.h, L.w, L.cp, H(s + ":packed"), L.kp, L.fh, L.fw, L.sh, L.sw, L.pad[0], L.pad[1], L.pad[2], L.pad[3],
                                 H(n->layers[i - 1].name + ":dout")));
     }
@@ -780,11 +818,7 @@ int student_record_update(xemo_net* n) {
   xemo_ctx* ctx = n->ctx;
   NET_OP(xemo_op_grad_guard(ctx, n->grad, n->nparam, n->guard));
   NET_OP(xemo_op_sgd_momentum_guarded(ctx, n->master, n->momentum, n->grad, n->nparam, n->hyper, 1.f, 1.f, 1.f, n->w16, n->guard));
-  for (const ConvLayer& L : n->layers)
-    if (L.has_bn)
-      NET_OP(xemo_op_moments_average_guarded(ctx, n->get<float>(L.bn + ":moments"), n->get<float>(L.bn + ":batch_moments"), 2 * L.cout, 0.1f, n->bm_scale,
-                                             n->guard));
-  return XEMO_OK;
+  return xemo_op_moments_average_guarded(ctx, n->mom_flat, n->bm_flat, int(n->bm_elems), 0.1f, n->bm_scale, n->guard);
 }
 
 // run `record` eagerly once (kernel attributes must be set outside a capture), then capture it

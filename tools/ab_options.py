@@ -66,9 +66,6 @@ if __name__ == "__main__":
     if "se_lin" in which:
         for v in ("0", "28", "14", "7"):
             out["teacher senet50 XEMO_SE_LIN_MIN_HW=" + v] = with_env({"XEMO_SE_LIN_MIN_HW": v}, lambda: teacher_ms(n))
-    if "se_gate" in which:      # (read once per process by the library: run once per value)
-        v = os.environ.get("XEMO_SE_GATE_SPLIT", "1")
-        out["teacher senet50 XEMO_SE_GATE_SPLIT=" + v] = teacher_ms(n)
     if "costmodel" in which:
         v = os.environ.get("XEMO_CONV_COSTMODEL", "1")   # read once per process by the library: one value per run
         out["teacher senet50 XEMO_CONV_COSTMODEL=" + v] = teacher_ms(n)
