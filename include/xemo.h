@@ -195,6 +195,12 @@ int xemo_debug_conv_plan(int N, int H, int W, int Cin, int Kout, int R, int S, i
                          int num_sms, int* out);
 int xemo_debug_wgrad_plan(int N, int H, int W, int Cin, int ldy, int Kout, int R, int S, int sh, int sw, int pt, int pb, int pl,
                           int pr, int num_sms, int* out);
+/* CTA pairs (tcgen05.mma.cta_group::2, clusters of two CTAs that split the filter tile) in the forward / data-gradient
+ * convolution: -1 = follow XEMO_CONV_2CTA / the planner's rule (default), 0 = never, 1 = the rule, 2 = whenever legal.
+ * xemo_debug_conv_plan reports the choice as out[12] when asked for 13 ints through xemo_debug_conv_plan2. */
+int xemo_debug_set_conv_pair_mode(int mode);
+int xemo_debug_conv_plan2(int N, int H, int W, int Cin, int Kout, int R, int S, int sh, int sw, int pt, int pb, int pl, int pr,
+                          int num_sms, int* out13);
 /* bias gradient: out[c] = scale * sum_p dy[p][c] */
 int xemo_op_colsum(xemo_ctx* ctx, const void* dy16, size_t P, int ld, int C, float scale, float* out);
 

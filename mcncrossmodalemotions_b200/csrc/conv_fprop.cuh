@@ -75,6 +75,10 @@ struct ConvFpropParams {
   const float* nc_scale;
   const float* nc_shift;
   int nc_hw;                // pixels per image (OH*OW): image of a GEMM row = row / nc_hw
+  // CTA pairs (kCtas = 2 instantiation): tiles are taken by clusters of two CTAs, which own two vertically adjacent M tiles
+  // of one N tile and execute them as ONE M = 256 tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and
+  // half of the filter tile, so the filter traffic per output row halves
+  int num_pair_tiles;       // ceil(num_m_tiles / 2) * num_n_tiles
 };
 
 constexpr int kNcSlots = 4;   // images one 128-row tile can touch (7 x 7 maps: 128 / 49 -> up to 4)
@@ -105,7 +109,7 @@ __device__ __forceinline__ void epi_bar_sync(int group) { asm volatile("bar.sync
 
 // kNC = true (SE blocks by linearity): scale / shift are per (image, channel) instead of per channel.  A separate
 // instantiation so that the code of the default kernels is untouched.
-template <int BK, bool kNC = false>
+template <int BK, bool kNC = false, int kCtas = 1>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -115,10 +119,21 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   constexpr int kABytes = kConvBlockM * BK * 2;
-  const int b_bytes = p.block_n * BK * 2;
+  const int b_rows = p.block_n / kCtas;      // filter rows this CTA stages (a CTA pair splits the N tile)
+  const int b_bytes = b_rows * BK * 2;
   const int b_res = p.b_resident;
-  const int stage_bytes = conv_stage_bytes(BK, p.block_n, b_res);
-  const int b_slot = conv_b_slot_bytes(BK, p.block_n);
+  const int stage_bytes = conv_stage_bytes(BK, b_rows, b_res);
+  const int b_slot = conv_b_slot_bytes(BK, b_rows);
+  const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
+  // persistent loop: 1 CTA -> tile = m_tile * num_n_tiles + n_tile; CTA pair -> the cluster takes pair tile t, this CTA the
+  // M tile 2 * (t / num_n_tiles) + rank (possibly one past the last: it then computes and stores nothing but zeros, clipped)
+  const int tile0 = kCtas == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int tile_step = kCtas == 2 ? int(gridDim.x >> 1) : int(gridDim.x);
+  auto tile_mn = [&](int t, int& m_tile, int& n_tile) {
+    const int q = t / p.num_n_tiles;
+    n_tile = t - q * p.num_n_tiles;
+    m_tile = kCtas == 2 ? 2 * q + int(cta_rank) : q;
+  };
   const int num_stages = p.num_stages;
   const int k_iters = p.R * p.S * p.kc_blocks;
 
@@ -154,22 +169,22 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4 * kEpiGroups);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], 4 * kEpiGroups * kCtas);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     for (int a = 0; a < 4; ++a) mbar_init(&res_bar[a], 1);
     mbar_init(b_res_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, kConvTmemCols);
-    tmem_relinquish();
+    if (kCtas == 2) { tmem_alloc_pair(tmem_ptr_smem, kConvTmemCols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_ptr_smem, kConvTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();   // (pair: the peer's barriers must exist before anything signals them)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = kCtas == 2 ? p.num_pair_tiles : p.num_m_tiles * p.num_n_tiles;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -177,13 +192,13 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const int ohw = p.OH * p.OW;
-      if (b_res && int(blockIdx.x) < num_tiles) {  // the whole filter, once (num_n_tiles == 1)
+      if (b_res && tile0 < num_tiles) {  // the whole filter, once (num_n_tiles == 1)
         mbar_arrive_expect_tx(b_res_bar, uint32_t(k_iters) * uint32_t(b_bytes));
         for (int it = 0; it < k_iters; ++it) tma_load_2d(&tmB, b_res_bar, b_res_buf + size_t(it) * b_slot, it * BK, 0);
       }
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        int m_tile, n_tile;
+        tile_mn(tile, m_tile, n_tile);
         const int m0 = m_tile * kConvBlockM;
         const int n_img = m0 / ohw;
         const int rem = m0 - n_img * ohw;
@@ -191,7 +206,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int ow = rem - oh * p.OW;
         const int w_base = ow * p.stride_w - p.pad_l;
         const int h_base = oh * p.stride_h - p.pad_t;
-        const int n0 = n_tile * p.block_n;
+        const int n0 = n_tile * p.block_n + int(cta_rank) * b_rows;
         for (int r = 0; r < p.R; ++r) {
           for (int s = 0; s < p.S; ++s) {
             const int kbase = (r * p.S + s) * p.Cin;
@@ -199,10 +214,17 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = smem + size_t(stage) * stage_bytes;
               uint8_t* sb = sa + kABytes;
-              mbar_arrive_expect_tx(&full_bar[stage], uint32_t(kABytes + (b_res ? 0 : b_bytes)));
-              tma_load_im2col_4d(&tmA, &full_bar[stage], sa, kc * BK, w_base, h_base, n_img, uint16_t(s),
-                                 uint16_t(r));
-              if (!b_res) tma_load_2d(&tmB, &full_bar[stage], sb, kbase + kc * BK, n0);
+              if constexpr (kCtas == 2) {
+                // both CTAs' bytes are counted on the leader's barrier; only the leader arrives on it
+                if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], uint32_t(2 * (kABytes + b_bytes)));
+                tma_load_im2col_4d_pair(&tmA, &full_bar[stage], sa, kc * BK, w_base, h_base, n_img, uint16_t(s), uint16_t(r));
+                tma_load_2d_pair(&tmB, &full_bar[stage], sb, kbase + kc * BK, n0);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], uint32_t(kABytes + (b_res ? 0 : b_bytes)));
+                tma_load_im2col_4d(&tmA, &full_bar[stage], sa, kc * BK, w_base, h_base, n_img, uint16_t(s),
+                                   uint16_t(r));
+                if (!b_res) tma_load_2d(&tmB, &full_bar[stage], sb, kbase + kc * BK, n0);
+              }
               if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -210,20 +232,20 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_f16(kConvBlockM, p.block_n, 0, 0);
+    // ------------------------------------------------------------ MMA issuer (CTA pair: the leader only)
+    if (cta_rank == 0 && elect_one()) {
+      const uint32_t idesc = make_idesc_f16(kConvBlockM * kCtas, p.block_n, 0, 0);
       constexpr uint32_t kSbo = 8 * BK * 2;  // 8 rows of BK fp16
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      if (b_res && int(blockIdx.x) < num_tiles) mbar_wait(b_res_bar, 0);
+      if (b_res && tile0 < num_tiles) mbar_wait(b_res_bar, 0);
       const uint64_t desc0 = make_smem_desc(smem_u32(smem), 16, kSbo, ConvSwizzle<BK>::mode);
       const uint32_t desc_hi = uint32_t(desc0 >> 32), desc_lo0 = uint32_t(desc0);
       const uint32_t stage_inc = uint32_t(stage_bytes) >> 4, bslot_inc = uint32_t(b_slot) >> 4;
       const uint32_t bres_off = (smem_u32(b_res_buf) - smem_u32(smem)) >> 4;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc) * 256u;
@@ -237,13 +259,18 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
-            umma_f16_ss(d_tmem, (uint64_t(desc_hi) << 32) | (a_lo + 2u * k), (uint64_t(desc_hi) << 32) | (b_lo + 2u * k), idesc,
-                        (it > 0 || k > 0) ? 1u : 0u);
+            if constexpr (kCtas == 2)
+              umma_f16_ss_pair(d_tmem, (uint64_t(desc_hi) << 32) | (a_lo + 2u * k), (uint64_t(desc_hi) << 32) | (b_lo + 2u * k), idesc,
+                               (it > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_f16_ss(d_tmem, (uint64_t(desc_hi) << 32) | (a_lo + 2u * k), (uint64_t(desc_hi) << 32) | (b_lo + 2u * k), idesc,
+                          (it > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+          // smem slot free once these MMAs retire (pair: the slot of BOTH CTAs -- the commit arrives on both empty barriers)
+          if constexpr (kCtas == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if constexpr (kCtas == 2) umma_commit_pair(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -286,10 +313,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint8_t* rbuf = rbuf0 + buf * kEpiStageBytes;
       const long long titer = G / chunks_per_tile;
       const int q = int(G - titer * chunks_per_tile);
-      const long long tile = (long long)blockIdx.x + titer * gridDim.x;
+      const long long tile = (long long)tile0 + titer * tile_step;
       if (tile >= num_tiles) return;
-      const int nm = int(tile / p.num_n_tiles);
-      const int nn = int(tile - (long long)nm * p.num_n_tiles);
+      int nm, nn;
+      tile_mn(int(tile), nm, nn);
       mbar_arrive_expect_tx(rbar, chunk_bytes);
       tma_load_2d(&tmRes, rbar, rbuf, nn * p.block_n + q * cw, nm * kConvBlockM);
     };
@@ -297,9 +324,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int bq = 0; bq < epi_bufs; ++bq) prefetch_residual(group + 2 * bq, bq);
 
     long long G0 = 0;  // global chunk index of chunk 0 of the current tile
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, G0 += chunks_per_tile) {
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, G0 += chunks_per_tile) {
+      int m_tile, n_tile;
+      tile_mn(tile, m_tile, n_tile);
       const int m0 = m_tile * kConvBlockM;
       const int row = m0 + row_in_tile;
       const int n0 = n_tile * p.block_n;
@@ -503,7 +530,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {   // the accumulator buffer is free: tell the MMA issuer (pair: the one in the leader CTA)
+        if (kCtas == 2 && cta_rank != 0) mbar_arrive_remote(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -511,10 +540,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();   // (pair: nobody leaves while the other CTA may still touch it)
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kConvTmemCols);
+    if (kCtas == 2) tmem_dealloc_pair(tmem_base, kConvTmemCols); else tmem_dealloc(tmem_base, kConvTmemCols);
   }
 }
 

@@ -46,8 +46,21 @@ struct ConvPlan {
   int bk = 0;
   int grid = 0;
   int smem = 0;
+  int ctas = 1;     // 2: CTA pairs (cluster of two, tcgen05.mma.cta_group::2, M = 256)
   double flops = 0;
 };
+
+// CTA pairs pay when the tile's operand traffic is dominated by the filter: long reductions and wide N tiles.  Measured on
+// B200 with the bring-up harness (profiles/r02_selftest_2cta.log): 3x3 c128 28x28 +12 %, 3x3 c256 14x14 +7 %, 3x3 c512 7x7
+// +18 %, student conv2 +18 %, conv3 +13 %, a 4096^2 x 16384 GEMM +11 % (1469 TFLOP/s); a short reduction with a wide output
+// (1x1 c512 -> k2048, 8 k-iterations) loses 20 %.
+// XEMO_CONV_2CTA: 0 = never, 1 (default) = the rule in conv_fprop_plan, 2 = whenever legal (bring-up / A-B measurements);
+// xemo_debug_set_conv_pair_mode overrides the environment at run time (tests).
+inline int& conv_pair_mode_override() { static int v = -1; return v; }
+inline int conv_pair_mode() {
+  static const int mode = [] { const char* e = getenv("XEMO_CONV_2CTA"); return e ? (e[0] - '0') : 1; }();
+  return conv_pair_mode_override() >= 0 ? conv_pair_mode_override() : mode;
+}
 
 constexpr int kSmemBudget = 227 * 1024;
 
@@ -133,7 +146,13 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   static const bool bres_enabled = [] { const char* e = getenv("XEMO_CONV_BRES"); return !(e && e[0] == '0'); }();
   const int bres_bytes = k_iters * conv_b_slot_bytes(bk, p.block_n);
   p.b_resident = (bres_enabled && p.num_n_tiles == 1 && bres_bytes <= 112 * 1024 && tiles >= num_sms) ? 1 : 0;
-  const int stage_bytes = conv_stage_bytes(bk, p.block_n, p.b_resident);
+  // CTA pairs: legal when the N tile splits into two halves of whole 16-row groups, the filter is not resident and the
+  // per-(image, channel) epilogue is off (its image slots assume in-range M tiles)
+  const bool pair_legal = !p.b_resident && !e.nc_scale && p.block_n % 32 == 0 && p.num_m_tiles >= 2 && num_sms % 2 == 0;
+  const bool pair_wanted = conv_pair_mode() == 2 || (conv_pair_mode() == 1 && k_iters >= 16 && p.block_n >= 128 && tiles >= num_sms);
+  plan->ctas = (pair_legal && pair_wanted) ? 2 : 1;
+  p.num_pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+  const int stage_bytes = conv_stage_bytes(bk, p.block_n / plan->ctas, p.b_resident);
   const int fixed_bytes = p.b_resident ? bres_bytes : 0;
   int stages = 0, epi_bytes = 0;
   for (int bufs = 2; bufs >= 1; --bufs) {
@@ -148,6 +167,7 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   plan->bk = bk;
   plan->smem = stages * stage_bytes + fixed_bytes + epi_bytes + 1024 + kEpiGroups * 2 * 256 * 4 + nc_bytes + (2 * stages + 9) * 8 + 16;
   plan->grid = tiles < num_sms ? tiles : num_sms;
+  if (plan->ctas == 2) plan->grid = 2 * (p.num_pair_tiles < num_sms / 2 ? p.num_pair_tiles : num_sms / 2);
   plan->flops = 2.0 * double(p.M) * g.Kout * g.R * g.S * g.Cin;
   if (!encode_maps) return true;
 
@@ -160,7 +180,7 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
                                  uint32_t(bk), uint32_t(kConvBlockM), swz))
     return false;
   if (!make_tmap_2d_f16(&plan->tmB, w, uint64_t(g.Kout), uint64_t(g.R) * g.S * g.Cin, uint64_t(g.R) * g.S * g.Cin,
-                        uint32_t(bk), uint32_t(p.block_n), swz))
+                        uint32_t(bk), uint32_t(p.block_n / plan->ctas), swz))
     return false;
   memset(&plan->tmOut, 0, sizeof(CUtensorMap));
   memset(&plan->tmRes, 0, sizeof(CUtensorMap));
@@ -175,8 +195,36 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   return true;
 }
 
+template <int BK>
+inline cudaError_t conv_fprop_run_pair(const ConvPlan& plan, cudaStream_t stream) {
+  static bool attr = false;
+  cudaError_t err = cudaSuccess;
+  if (!attr) { err = cudaFuncSetAttribute(conv_fprop_kernel<BK, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget); attr = true; }
+  if (err != cudaSuccess) return err;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(plan.grid);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_fprop_kernel<BK, false, 2>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
+}
+
 inline cudaError_t conv_fprop_run(const ConvPlan& plan, cudaStream_t stream) {
   cudaError_t err = cudaSuccess;
+  if (plan.ctas == 2) {
+    switch (plan.bk) {
+      case 64: return conv_fprop_run_pair<64>(plan, stream);
+      case 32: return conv_fprop_run_pair<32>(plan, stream);
+      case 16: return conv_fprop_run_pair<16>(plan, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   if (plan.p.nc_scale) {   // per-(image, channel) epilogue: BK = 64 only (checked by the plan)
     static bool attr = false;
     if (!attr) { err = cudaFuncSetAttribute(conv_fprop_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget); attr = true; }

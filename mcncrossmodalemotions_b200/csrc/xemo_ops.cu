@@ -303,6 +303,27 @@ extern "C" int xemo_debug_conv_plan(int N, int H, int W, int Cin, int Kout, int 
   return XEMO_OK;
 }
 
+extern "C" int xemo_debug_conv_plan2(int N, int H, int W, int Cin, int Kout, int R, int S, int sh, int sw, int pt, int pb, int pl,
+                                     int pr, int num_sms, int* out13) {
+  if (!out13) return XEMO_ERR_INVALID;
+  const int rc = xemo_debug_conv_plan(N, H, W, Cin, Kout, R, S, sh, sw, pt, pb, pl, pr, num_sms, out13);
+  if (rc) return rc;
+  ConvGeom g{N, H, W, Cin, Kout, R, S, sh, sw, pt, pb, pl, pr};
+  ConvEpilogue e;
+  e.out = reinterpret_cast<__half*>(uintptr_t(16));
+  e.ldc = Kout;
+  ConvPlan plan;
+  if (!conv_fprop_plan(&plan, g, nullptr, nullptr, e, num_sms, 0, false)) return XEMO_ERR_INVALID;
+  out13[12] = plan.ctas;
+  out13[9] = plan.grid;
+  return XEMO_OK;
+}
+
+extern "C" int xemo_debug_set_conv_pair_mode(int mode) {
+  conv_pair_mode_override() = mode;
+  return XEMO_OK;
+}
+
 extern "C" int xemo_debug_wgrad_plan(int N, int H, int W, int Cin, int ldy, int Kout, int R, int S, int sh, int sw, int pt, int pb,
                                      int pl, int pr, int num_sms, int* out) {
   if (!out) return XEMO_ERR_INVALID;

@@ -189,3 +189,40 @@ def test_error_behaviour(vl):
         vl.vl_nnconv(x, np.zeros((5, 5, 8, 8), np.float32))  # filter larger than the input
     with pytest.raises(ValueError):
         vl.vl_nnpool(x, 2, method="median")
+
+
+@pytest.mark.parametrize("geom", [
+    # H, W, C, N, FH, FW, K, pad, stride  -- several M tiles each, so that clusters of two CTAs have pairs to take
+    (30, 17, 128, 3, 3, 3, 256, (1, 1, 1, 1), (1, 1)),       # conv3-like; odd number of M tiles (12): no, 1530 rows -> 12
+    (29, 21, 96, 2, 5, 5, 128, (1, 1, 1, 1), (2, 2)),        # strided: the data gradient runs 4 parity classes through pairs
+    (14, 14, 256, 5, 1, 1, 512, (0, 0, 0, 0), (1, 1)),       # 980 rows -> 8 M tiles, 1x1
+    (9, 8, 64, 11, 9, 1, 160, (0, 0, 0, 0), (1, 1)),         # fc6-like, K = 160 -> N tile 160 (80 rows per CTA)
+    (23, 23, 64, 1, 3, 3, 64, (1, 1, 1, 1), (1, 1)),         # 529 rows -> 5 M tiles: the last cluster's peer has no tile
+])
+def test_vl_nnconv_with_cta_pairs_is_bit_identical_to_single_ctas(geom):
+    """conv_fprop_kernel<BK, false, 2> (tcgen05.mma.cta_group::2: a cluster of two CTAs executes two M tiles as one M = 256
+    MMA, each staging half of the filter tile) against the single-CTA kernel -- same K order, same accumulators: the outputs
+    must be bit-identical, forward and data gradient -- and against the fp64 oracle."""
+    from oracle import mcn_ops as M
+    from mcncrossmodalemotions_b200 import _lib, vl_nn
+
+    H, W, C, N, FH, FW, K, pad, stride = geom
+    rng = np.random.default_rng(17)
+    x = rng.standard_normal((H, W, C, N)).astype(np.float32)
+    f = (rng.standard_normal((FH, FW, C, K)) / np.sqrt(FH * FW * C)).astype(np.float32)
+    b = rng.standard_normal(K).astype(np.float32)
+    y64 = M.vl_nnconv(x.astype(np.float64), f.astype(np.float64), b.astype(np.float64), pad=pad, stride=stride)
+    dy = rng.standard_normal(y64.shape).astype(np.float32)
+    dx64, _, _ = M.vl_nnconv(x.astype(np.float64), f.astype(np.float64), b.astype(np.float64), dy.astype(np.float64), pad=pad, stride=stride)
+    lib = _lib.load_library()
+    out = {}
+    try:
+        for mode in (0, 2):
+            assert lib.xemo_debug_set_conv_pair_mode(mode) == 0
+            y = vl_nn.vl_nnconv(x, f, b, pad=pad, stride=stride)
+            dx, df, db = vl_nn.vl_nnconv(x, f, b, dy, pad=pad, stride=stride)
+            out[mode] = (y, dx)
+    finally:
+        lib.xemo_debug_set_conv_pair_mode(-1)
+    assert np.array_equal(out[0][0], out[2][0]) and np.array_equal(out[0][1], out[2][1])
+    assert rel_err(out[2][0], y64) < 1e-3 and rel_err(out[2][1], dx64) < 1e-3

@@ -475,6 +475,41 @@ def test_layer_tables_agree_with_the_library():
     assert lib.xemo_net_create(None, 7, 4, 300, 0, 8, C.byref(h)) != 0
 
 
+def test_cta_pair_rule_of_the_convolution_planner():
+    """CTA pairs (tcgen05.mma.cta_group::2) are chosen for long reductions with wide N tiles and enough tiles to fill the
+    machine; never with a resident filter; grids come in whole clusters."""
+    import ctypes as C
+
+    from mcncrossmodalemotions_b200 import _lib
+
+    lib = _lib.load_library()
+    out = (C.c_int * 13)()
+
+    def plan(*g):
+        assert lib.xemo_debug_conv_plan2(*g, 148, out) == 0, g
+        return list(out)
+
+    assert lib.xemo_debug_set_conv_pair_mode(1) == 0
+    try:
+        conv2 = plan(256, 126, 73, 128, 256, 5, 5, 2, 2, 1, 1, 1, 1)               # student conv2: 50 k-iterations, N tile 256
+        assert conv2[12] == 2 and conv2[9] == 148 and conv2[6] == 0
+        res4 = plan(256, 14, 14, 256, 256, 3, 3, 1, 1, 1, 1, 1, 1)                   # teacher 3x3 c256
+        assert res4[12] == 2
+        wide = plan(256, 7, 7, 512, 2048, 1, 1, 1, 1, 0, 0, 0, 0)                    # 8 k-iterations, output-bound: single CTAs
+        assert wide[12] == 1
+        stem = plan(256, 56, 56, 64, 64, 3, 3, 1, 1, 1, 1, 1, 1)                     # resident filter: single CTAs
+        assert stem[6] == 1 and stem[12] == 1
+        small = plan(16, 14, 14, 256, 256, 3, 3, 1, 1, 1, 1, 1, 1)                   # 25 M tiles x 4 N tiles < 148: single CTAs
+        assert small[12] == 1 and small[1] == 64
+        assert lib.xemo_debug_set_conv_pair_mode(2) == 0
+        forced = plan(16, 14, 14, 256, 256, 3, 3, 1, 1, 1, 1, 1, 1)                  # 13 pairs of M tiles (the last one half empty) x 4
+        assert forced[12] == 2 and forced[9] == 2 * 13 * 4 and forced[4] > small[4]  # (half the filter per CTA: deeper pipeline)
+        assert lib.xemo_debug_set_conv_pair_mode(0) == 0
+        assert plan(256, 126, 73, 128, 256, 5, 5, 2, 2, 1, 1, 1, 1)[12] == 1
+    finally:
+        lib.xemo_debug_set_conv_pair_mode(-1)
+
+
 def test_loss_types_of_the_zoo():
     """emoVoxZoo.m:137-157: four loss types; 'euclidean' scales the head filters by 1/10 (:141-144); anything else is
     rejected before the device is touched."""
