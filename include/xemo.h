@@ -184,6 +184,12 @@ int xemo_op_pack_dgrad_filters(xemo_ctx* ctx, const void* w16_krsc, int Kout, in
                                int pt, int pl, void* packed16);
 int xemo_op_conv_dgrad(xemo_ctx* ctx, const void* dy16, int N, int H, int W, int Cin, const void* packed16, int Kout,
                        int R, int S, int sh, int sw, int pt, int pb, int pl, int pr, void* dx16);
+/* the same for a FULL-HEIGHT filter (R == H, S == 1, stride 1, no padding: one output row -- the student's fc6): the data
+ * gradient as a plain GEMM over (n, w) rows, without the R - 1 zero taps per pixel of the general form.  `packed16` has the
+ * size xemo_dgrad_pack_elems gives; Cin <= 256. */
+int xemo_op_pack_dgrad_filters_fullheight(xemo_ctx* ctx, const void* w16_krsc, int Kout, int R, int Cin, void* packed16);
+int xemo_op_conv_dgrad_fullheight(xemo_ctx* ctx, const void* dy16, int N, int H, int W, int Cin, const void* packed16, int Kout,
+                                  void* dx16);
 /* filter gradient, accumulated (+=) into dF[Kout][R][S][Cin] fp32, scaled by `scale` */
 int xemo_op_conv_wgrad(xemo_ctx* ctx, const void* x16, int N, int H, int W, int Cin, const void* dy16, int ldy,
                        int Kout, int R, int S, int sh, int sw, int pt, int pb, int pl, int pr, float* dF, float scale);

@@ -74,6 +74,8 @@ SIGNATURES = {
     "xemo_op_pack_dgrad_filters": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "xemo_op_conv_dgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_int, c_int, c_int, c_void_p]),
+    "xemo_op_pack_dgrad_filters_fullheight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "xemo_op_conv_dgrad_fullheight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "xemo_op_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_int, c_int, c_int, c_int, c_void_p, c_float]),
     "xemo_debug_conv_plan": (c_int, [c_int] * 14 + [P(c_int)]),

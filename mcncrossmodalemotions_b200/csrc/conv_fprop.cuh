@@ -60,6 +60,7 @@ struct ConvFpropParams {
   // strided-output mode (dgrad of strided convs): row address = n*out_sn + oh*out_sh + ow*out_sw
   int strided_out;
   long long out_sn, out_sh, out_sw;
+  long long out_stile;      // strided-output mode: element offset of N tile t is t * out_stile (block_n: plain columns)
   // TMA epilogue
   int use_tma_store;        // fp16 `out` written through tmOut
   int use_tma_residual;     // residual read through tmRes
@@ -367,7 +368,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int rem = row - n_img * ohw;
         const int oh = rem / p.OW;
         const int ow = rem - oh * p.OW;
-        row_off = size_t(n_img) * p.out_sn + size_t(oh) * p.out_sh + size_t(ow) * p.out_sw + n0;
+        row_off = size_t(n_img) * p.out_sn + size_t(oh) * p.out_sh + size_t(ow) * p.out_sw + size_t(n_tile) * p.out_stile;
       } else {
         row_off = size_t(row) * p.ldc + n0;
       }

@@ -34,6 +34,7 @@ struct ConvEpilogue {
   // strided-output mode: row address = n*out_sn + oh*out_sh + ow*out_sw (elements)
   int strided_out = 0;
   long long out_sn = 0, out_sh = 0, out_sw = 0;
+  long long out_stile = 0;     // 0 -> block_n (N tiles are plain column ranges); else the element offset between N tiles
   int allow_tma_epilogue = 1;  // 0 forces the direct-store epilogue
   // per-(image, channel) scale / shift ([N][Kout] fp32; replaces scale / shift), fp16 TMA-store outputs only
   const float* nc_scale = nullptr;
@@ -128,6 +129,7 @@ inline bool conv_fprop_plan(ConvPlan* plan, const ConvGeom& g, const __half* x, 
   p.out = e.out; p.out_f32 = e.out_f32;
   p.ldc = e.ldc ? e.ldc : g.Kout;
   p.strided_out = e.strided_out; p.out_sn = e.out_sn; p.out_sh = e.out_sh; p.out_sw = e.out_sw;
+  p.out_stile = e.out_stile ? e.out_stile : p.block_n;
   p.use_tma_store = (e.allow_tma_epilogue && e.out && !e.strided_out && (p.ldc % 8 == 0)) ? 1 : 0;
   p.use_tma_residual = (p.use_tma_store && e.residual) ? 1 : 0;
   p.epi_cw = (p.block_n % 64 == 0) ? 64 : (p.block_n % 32 == 0) ? 32 : 16;

@@ -59,6 +59,19 @@ static __global__ void dgrad_pack_kernel(const __half* __restrict__ w, DgradPack
   }
 }
 
+// Data gradient of a FULL-HEIGHT filter (R == H, one output row, S == 1, no padding: the student's fc6, a 9 x 1 filter over
+// a 9 x W map): dx[(n, w), (h, c)] = sum_k dy[(n, w), k] * F[k][h][0][c] is a plain GEMM.  Its filter operand, one row per
+// output column (h, c) with k contiguous:  G[h * Cin + c][k] = F[k][h][0][c].
+static __global__ void dgrad_pack_fullheight_kernel(const __half* __restrict__ w, int Kout, int R, int Cin, __half* __restrict__ dst) {
+  const size_t total = size_t(R) * Cin * Kout;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int k = int(i % Kout);
+    const int c = int((i / Kout) % Cin);
+    const int h = int(i / (size_t(Kout) * Cin));
+    dst[i] = w[(size_t(k) * R + h) * Cin + c];
+  }
+}
+
 // dF [Kp][R][S][Cp] fp32 (device layout) -> FH x FW x FC x K column-major fp32 (MatConvNet)
 static __global__ void krsc_f32_to_filters_kernel(const float* __restrict__ src, int FH, int FW, int FC, int K, int Cp,
                                            float* __restrict__ dst, const float* __restrict__ mul = nullptr) {

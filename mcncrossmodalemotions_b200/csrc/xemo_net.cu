@@ -135,6 +135,7 @@ struct ConvLayer {   // student
   std::string name, bn;
   int fh, fw, cin, cout, kp, cp, sh, sw, pad[4], h, w, oh, ow;
   bool has_bn;
+  bool full_height = false;  // a filter as tall as its input, one column wide, unpadded, stride 1 (fc6): dgrad as a GEMM
   int pool_method = -1;  // -1 none, 0 max, 1 avg
   int pwh = 0, pww = 0, psh = 1, psw = 1, ph = 0, pw = 0, poh = 0, pow_ = 0;
 };
@@ -485,6 +486,10 @@ int student_describe(xemo_net* n) {
     L.h = h; L.w = w;
     L.oh = out_dim(h, d.pad, d.pad, d.fh, d.sh); L.ow = out_dim(w, d.pad, d.pad, d.fw, d.sw);
     if (L.oh <= 0 || L.ow <= 0) return fail(n->ctx, XEMO_ERR_INVALID, "net: a %d-column spectrogram is too narrow for %s", n->W, d.name);
+    {
+      const char* e = getenv("XEMO_DGRAD_FULLHEIGHT");
+      L.full_height = d.fh == h && d.fw == 1 && d.fh > 1 && d.sh == 1 && d.sw == 1 && d.pad == 0 && L.cp <= 256 && !(e && e[0] == '0');
+    }
     h = L.oh; w = L.ow;
     if (L.name == "conv1" || L.name == "conv2") { L.pool_method = 0; L.pwh = 3; L.pww = 3; L.psh = 2; L.psw = 2; }
     if (L.name == "conv5") { L.pool_method = 0; L.pwh = 5; L.pww = 3; L.psh = 3; L.psw = 2; }
@@ -729,8 +734,11 @@ int student_record_forward_test(xemo_net* n) {
 int student_record_packs(xemo_net* n) {
   for (size_t i = 1; i < n->layers.size(); ++i) {
     const ConvLayer& L = n->layers[i];
-    NET_OP(xemo_op_pack_dgrad_filters(n->ctx, n->w16 + n->seg[L.name + "f"], L.kp, L.fh, L.fw, L.cp, L.sh, L.sw, L.pad[0], L.pad[2],
-                                      n->get<__half>(L.name + ":packed")));
+    if (L.full_height)
+      NET_OP(xemo_op_pack_dgrad_filters_fullheight(n->ctx, n->w16 + n->seg[L.name + "f"], L.kp, L.fh, L.cp, n->get<__half>(L.name + ":packed")));
+    else
+      NET_OP(xemo_op_pack_dgrad_filters(n->ctx, n->w16 + n->seg[L.name + "f"], L.kp, L.fh, L.fw, L.cp, L.sh, L.sw, L.pad[0], L.pad[2],
+                                        n->get<__half>(L.name + ":packed")));
   }
   return XEMO_OK;
 }
@@ -802,10 +810,14 @@ int student_record_backward(xemo_net* n, int lo, int hi, bool loss) {
     if (!fused_bias) NET_OP(xemo_op_colsum(ctx, dy, rows, L.kp, L.kp, inv, n->grad + n->seg[s + "b"]));
     if (fork) NET_OP(xemo_set_stream(ctx, nullptr));
     if (i > 0) {
-      if (!n->packs_ahead)
-        NET_OP(xemo_op_pack_dgrad_filters(ctx, n->w16 + n->seg[s + "f"], L.kp, L.fh, L.fw, L.cp, L.sh, L.sw, L.pad[0], L.pad[2], H(s + ":packed")));
-      NET_OP(xemo_op_conv_dgrad(ctx, dy, N, L.h, L.w, L.cp, H(s + ":packed"), L.kp, L.fh, L.fw, L.sh, L.sw, L.pad[0], L.pad[1], L.pad[2], L.pad[3],
-                                H(n->layers[i - 1].name + ":dout")));
+      if (!n->packs_ahead) {
+        if (L.full_height) NET_OP(xemo_op_pack_dgrad_filters_fullheight(ctx, n->w16 + n->seg[s + "f"], L.kp, L.fh, L.cp, H(s + ":packed")));
+        else NET_OP(xemo_op_pack_dgrad_filters(ctx, n->w16 + n->seg[s + "f"], L.kp, L.fh, L.fw, L.cp, L.sh, L.sw, L.pad[0], L.pad[2], H(s + ":packed")));
+      }
+      // fc6 (a 9 x 1 filter over a 9 x W map, one output row): the data gradient as a plain GEMM over (n, w) rows
+      if (L.full_height) NET_OP(xemo_op_conv_dgrad_fullheight(ctx, dy, N, L.h, L.w, L.cp, H(s + ":packed"), L.kp, H(n->layers[i - 1].name + ":dout")));
+      else NET_OP(xemo_op_conv_dgrad(ctx, dy, N, L.h, L.w, L.cp, H(s + ":packed"), L.kp, L.fh, L.fw, L.sh, L.sw, L.pad[0], L.pad[1], L.pad[2], L.pad[3],
+                                     H(n->layers[i - 1].name + ":dout")));
     }
   }
   if (fork) NET_OP(xemo_stream_wait(ctx, nullptr, n->side_b));   // join

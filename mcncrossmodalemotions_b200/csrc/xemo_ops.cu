@@ -431,6 +431,39 @@ extern "C" int xemo_op_conv_dgrad(xemo_ctx* ctx, const void* dy16, int N, int H,
   return xemo_conv_dgrad_impl(ctx, dy16, N, H, W, Cin, packed16, Kout, R, S, sh, sw, pt, pb, pl, pr, dx16, nullptr);
 }
 
+// Full-height filters (the student's fc6: 9 x 1 over a 9 x W map): the parity-decomposed form above walks R taps of which
+// R - 1 fall outside the one-row dY for every output pixel (196 TFLOP/s of algorithmic work); as a GEMM over (n, w) rows
+// with the R * Cin columns scattered to the R rows of dX by N tile it runs without the zero taps.
+extern "C" int xemo_op_pack_dgrad_filters_fullheight(xemo_ctx* ctx, const void* w16_krsc, int Kout, int R, int Cin, void* packed16) {
+  XEMO_REQUIRE(ctx, w16_krsc && packed16, "pack_dgrad_filters_fullheight: null pointer");
+  dgrad_pack_fullheight_kernel<<<grid_for(size_t(R) * Cin * Kout, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+      static_cast<const __half*>(w16_krsc), Kout, R, Cin, static_cast<__half*>(packed16));
+  XEMO_LAUNCHED(ctx, 1);
+  return XEMO_OK;
+}
+
+extern "C" int xemo_op_conv_dgrad_fullheight(xemo_ctx* ctx, const void* dy16, int N, int H, int W, int Cin, const void* packed16, int Kout,
+                                             void* dx16) {
+  XEMO_REQUIRE(ctx, dy16 && packed16 && dx16, "conv_dgrad_fullheight: null pointer");
+  XEMO_REQUIRE(ctx, Cin % 16 == 0 && Cin <= 256 && Kout % 16 == 0, "conv_dgrad_fullheight: Cin=%d must be a multiple of 16 up to 256, Kout=%d a multiple of 16", Cin, Kout);
+  ConvGeom g{N, 1, W, Kout, H * Cin, 1, 1, 1, 1, 0, 0, 0, 0};     // dY as a 1 x W map with Kout channels; H * Cin output columns
+  ConvEpilogue e;
+  e.out = static_cast<__half*>(dx16);
+  e.strided_out = 1;
+  e.out_sn = (long long)H * W * Cin;    // image
+  e.out_sh = 0;
+  e.out_sw = Cin;                       // pixel (n, w) of row 0; N tile h lands on row h
+  e.out_stile = (long long)W * Cin;
+  e.ldc = Cin;
+  ConvPlan plan;
+  if (!conv_fprop_plan(&plan, g, static_cast<const __half*>(dy16), static_cast<const __half*>(packed16), e, ctx->num_sms, Cin))
+    return fail(ctx, XEMO_ERR_INVALID, "conv_dgrad_fullheight: unsupported geometry N=%d H=%d W=%d Cin=%d Kout=%d", N, H, W, Cin, Kout);
+  cudaError_t err = conv_fprop_run(plan, ctx->stream);
+  if (err != cudaSuccess) return fail(ctx, XEMO_ERR_CUDA, "conv_fprop launch failed: %s", cudaGetErrorString(err));
+  ctx->launches += 1;
+  return XEMO_OK;
+}
+
 extern "C" int xemo_op_conv_wgrad(xemo_ctx* ctx, const void* x16, int N, int H, int W, int Cin, const void* dy16, int ldy,
                                   int Kout, int R, int S, int sh, int sw, int pt, int pb, int pl, int pr, float* dF,
                                   float scale) {

@@ -696,7 +696,14 @@ class StudentProgram(_Base):
                 ctx.op_colsum(_p(dy), rows, L["kp"], L["kp"], inv, _p(self.view(self.grad, n + "b")))
             if side:
                 ctx.set_stream(None)
-            if i > 0:
+            if i > 0 and self._full_height(L):
+                # fc6: a 9 x 1 filter over a 9 x W map -> one output row: the data gradient is a plain GEMM over (n, w) rows
+                # (the general form walks 9 taps of which 8 fall outside dY for every pixel)
+                cp = L["cp"]
+                ctx.op_pack_dgrad_filters_fullheight(_p(self.view(self.w16, n + "f")), L["kp"], L["fh"], cp, _p(A[n + ":packed"]))
+                ctx.op_conv_dgrad_fullheight(_p(dy), N, L["h"], L["w"], cp, _p(A[n + ":packed"]), L["kp"],
+                                             _p(A[self.layers[i - 1]["name"] + ":dout"]))
+            elif i > 0:
                 cp = L["cp"]
                 ctx.op_pack_dgrad_filters(_p(self.view(self.w16, n + "f")), L["kp"], L["fh"], L["fw"], cp, L["stride"][0],
                                           L["stride"][1], L["pad"][0], L["pad"][2], _p(A[n + ":packed"]))
@@ -705,6 +712,12 @@ class StudentProgram(_Base):
 
         if self.side_stream is not None:
             ctx.stream_wait(None, VP(self.side_stream.cuda_stream))  # join before the update / all-reduce
+
+    @staticmethod
+    def _full_height(L):
+        """a filter as tall as its input, one column wide, unpadded, stride 1: one output row (the same rule as xemo_net.cu)"""
+        return (L["fh"] == L["h"] and L["fw"] == 1 and L["fh"] > 1 and L["stride"] == (1, 1) and L["pad"] == (0, 0, 0, 0)
+                and L["cp"] <= 256 and os.environ.get("XEMO_DGRAD_FULLHEIGHT", "1") != "0")
 
     def _input_of(self, i):
         return self.a[self.layers[i - 1]["name"] + ":out"]

@@ -238,3 +238,37 @@ def test_maxpool_forward_records_raw_winner(env):
     assert np.array_equal(got[live], ref[live])
     assert np.all((a * got.astype(np.float32) + b)[~live] <= 0)
 
+
+
+@pytest.mark.parametrize("n,width,cin,kout", [(5, 8, 256, 512), (3, 11, 64, 160)])
+def test_full_height_data_gradient_matches_the_general_form_and_the_oracle(env, n, width, cin, kout):
+    """fc6-type layers (a 9 x 1 filter over a 9 x W map, one output row): xemo_op_conv_dgrad_fullheight (a GEMM over (n, w)
+    rows whose N tiles land on the 9 rows of dX) against the parity-decomposed general form and the oracle's vl_nnconv DX."""
+    torch, ctx, stream = env
+    from oracle import mcn_ops as M
+
+    R = 9
+    rng = np.random.default_rng(n + width)
+    f = (rng.standard_normal((R, 1, cin, kout)) / np.sqrt(R * cin)).astype(np.float16).astype(np.float32)
+    dy = rng.standard_normal((1, width, kout, n)).astype(np.float16).astype(np.float32)
+    x = np.zeros((R, width, cin, n), np.float32)
+    dx_ref, _, _ = M.vl_nnconv(x.astype(np.float64), f.astype(np.float64), None, dy.astype(np.float64))
+    with torch.cuda.stream(stream):
+        w16 = torch.from_numpy(np.ascontiguousarray(np.transpose(f, (3, 0, 1, 2)))).cuda().half()      # [K][R][1][C]
+        dyd = torch.from_numpy(nhwc(dy)).cuda().half()                                               # [N][1][W][K]
+        packed = torch.zeros(int(ctx.lib.xemo_dgrad_pack_elems(cin, kout, R, 1, 1, 1)), dtype=torch.float16, device="cuda")
+        out = {}
+        for which in ("general", "fullheight"):
+            dxd = torch.full((n, R, width, cin), float("nan"), dtype=torch.float16, device="cuda")
+            if which == "general":
+                ctx.op_pack_dgrad_filters(_p(w16), kout, R, 1, cin, 1, 1, 0, 0, _p(packed))
+                ctx.op_conv_dgrad(_p(dyd), n, R, width, cin, _p(packed), kout, R, 1, 1, 1, 0, 0, 0, 0, _p(dxd))
+            else:
+                ctx.op_pack_dgrad_filters_fullheight(_p(w16), kout, R, cin, _p(packed))
+                ctx.op_conv_dgrad_fullheight(_p(dyd), n, R, width, cin, _p(packed), kout, _p(dxd))
+            ctx.sync()
+            out[which] = hwcn(dxd.float().cpu().numpy())
+    scale = np.abs(dx_ref).max()
+    assert np.isfinite(out["fullheight"]).all()
+    assert np.abs(out["fullheight"] - dx_ref).max() / scale < 1e-3
+    assert np.abs(out["fullheight"] - out["general"]).max() / scale < 1e-3
