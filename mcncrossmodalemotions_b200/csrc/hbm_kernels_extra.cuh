@@ -62,13 +62,18 @@ static __global__ void dgrad_pack_kernel(const __half* __restrict__ w, DgradPack
 // Data gradient of a FULL-HEIGHT filter (R == H, one output row, S == 1, no padding: the student's fc6, a 9 x 1 filter over
 // a 9 x W map): dx[(n, w), (h, c)] = sum_k dy[(n, w), k] * F[k][h][0][c] is a plain GEMM.  Its filter operand, one row per
 // output column (h, c) with k contiguous:  G[h * Cin + c][k] = F[k][h][0][c].
+// (for every h a [Kout][Cin] -> [Cin][Kout] transpose through a 32 x 33 shared-memory tile: coalesced on both sides)
 static __global__ void dgrad_pack_fullheight_kernel(const __half* __restrict__ w, int Kout, int R, int Cin, __half* __restrict__ dst) {
-  const size_t total = size_t(R) * Cin * Kout;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int k = int(i % Kout);
-    const int c = int((i / Kout) % Cin);
-    const int h = int(i / (size_t(Kout) * Cin));
-    dst[i] = w[(size_t(k) * R + h) * Cin + c];
+  __shared__ __half tile[32][33];
+  const int h = blockIdx.z, k0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int k = k0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (k < Kout && c < Cin) ? w[(size_t(k) * R + h) * Cin + c] : __float2half(0.f);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, k = k0 + threadIdx.x;
+    if (c < Cin && k < Kout) dst[(size_t(h) * Cin + c) * Kout + k] = tile[threadIdx.x][j];
   }
 }
 

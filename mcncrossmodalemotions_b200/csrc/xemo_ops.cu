@@ -436,7 +436,8 @@ extern "C" int xemo_op_conv_dgrad(xemo_ctx* ctx, const void* dy16, int N, int H,
 // with the R * Cin columns scattered to the R rows of dX by N tile it runs without the zero taps.
 extern "C" int xemo_op_pack_dgrad_filters_fullheight(xemo_ctx* ctx, const void* w16_krsc, int Kout, int R, int Cin, void* packed16) {
   XEMO_REQUIRE(ctx, w16_krsc && packed16, "pack_dgrad_filters_fullheight: null pointer");
-  dgrad_pack_fullheight_kernel<<<grid_for(size_t(R) * Cin * Kout, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+  XEMO_REQUIRE(ctx, R >= 1 && R <= 65535, "pack_dgrad_filters_fullheight: filter height out of range");
+  dgrad_pack_fullheight_kernel<<<dim3((Cin + 31) / 32, (Kout + 31) / 32, R), dim3(32, 8), 0, ctx->stream>>>(
       static_cast<const __half*>(w16_krsc), Kout, R, Cin, static_cast<__half*>(packed16));
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
