@@ -537,6 +537,7 @@ def parity_mode_rate(D, args, B=32, steps=2):
         prog.grad_step(); prog.update()
     prog.ctx.sync()
     dt = (time.perf_counter() - t0) / steps
+    prog.ctx.trim()
     del prog
     torch.cuda.empty_cache()
     return {"value": B / dt, "unit": "clips/s", "dtype": "f32 (fp16 x 3 split operands, fp32 accumulate / storage)", "batch": B,

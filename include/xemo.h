@@ -66,6 +66,9 @@ int xemo_create(int device, void* cuda_stream, xemo_ctx** out);
 void xemo_destroy(xemo_ctx* ctx);
 const char* xemo_last_error(xemo_ctx* ctx);
 int xemo_sync(xemo_ctx* ctx);
+/* The boundary operators (section B) take their scratch from a stream-ordered pool owned by the context and keep it
+ * between calls; xemo_trim synchronises and hands the unused part back to the driver. */
+int xemo_trim(xemo_ctx* ctx);
 int xemo_num_sms(xemo_ctx* ctx);
 /* Operand precision of xemo_vl_nnconv (the reference computes in `single` end to end: cnn_train_dag at
  * emoVoxCeleb/run_distillation.m:170-182 on gpuArray(single) batches, getBatchEmoVoxCeleb.m:197).

@@ -37,6 +37,7 @@ SIGNATURES = {
     "xemo_destroy": (None, [c_void_p]),
     "xemo_last_error": (C.c_char_p, [c_void_p]),
     "xemo_sync": (c_int, [c_void_p]),
+    "xemo_trim": (c_int, [c_void_p]),
     "xemo_num_sms": (c_int, [c_void_p]),
     "xemo_launch_count": (c_uint64, [c_void_p]),
     "xemo_h2d": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
@@ -237,7 +238,7 @@ class Context:
             raise XemoError(rc, self.lib.xemo_last_error(self.handle).decode())
 
     def __getattr__(self, name):
-        if name.startswith(("op_", "vl_")) or name in ("sync", "h2d", "d2h", "memset", "capture_begin", "graph_launch", "set_stream", "stream_wait",
+        if name.startswith(("op_", "vl_")) or name in ("sync", "trim", "h2d", "d2h", "memset", "capture_begin", "graph_launch", "set_stream", "stream_wait",
                                                      "set_conv_precision", "set_deterministic"):
             return lambda *a: self.call(name, *a)
         raise AttributeError(name)

@@ -22,6 +22,7 @@ struct xemo_ctx {
   uint64_t capture_mark = 0;    // value of `launches` when the capture began
   int deterministic = 0;        // xemo_set_deterministic: no order-dependent floating-point reductions in the training step
   int conv_precision = 0;       // xemo_set_conv_precision: 0 = fp16 operands, 1 = split fp16 x 3 (fp32-equivalent)
+  cudaMemPool_t pool = nullptr; // scratch of the boundary operators (xemo_vl.cu): stream-ordered, kept until xemo_destroy
 };
 
 struct xemo_graph {

@@ -4,6 +4,7 @@
 
 #include "conv_launch.cuh"
 #include "hbm_kernels_extra.cuh"
+#include "se_gate.cuh"
 #include "stem_kernels.cuh"
 
 using namespace xemo;
@@ -50,11 +51,21 @@ extern "C" int xemo_create(int device, void* cuda_stream, xemo_ctx** out) {
 
 extern "C" void xemo_destroy(xemo_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->pool) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemPoolDestroy(ctx->pool);
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->primary);
   delete ctx;
 }
 
 extern "C" const char* xemo_last_error(xemo_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int xemo_trim(xemo_ctx* ctx) {
+  XEMO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->pool) XEMO_CUDA(ctx, cudaMemPoolTrimTo(ctx->pool, 0));
+  return XEMO_OK;
+}
 
 extern "C" int xemo_sync(xemo_ctx* ctx) {
   XEMO_CUDA(ctx, cudaStreamSynchronize(ctx->primary));
@@ -730,8 +741,12 @@ extern "C" int xemo_op_se_squeeze(xemo_ctx* ctx, const void* u16, int N, int HW,
   while (lx < 32 && lx * 2 <= C8) lx *= 2;   // min(32, largest power of two <= C/8)
   // pixel-stride lanes: 1024 / lx for the large maps; the 7 x 7 maps (49 pixels) would leave half of a 32-lane stride
   // idle and pay a 1024-thread barrier for two loads per thread (1.4 TB/s in the launch list): 8 lanes there
-  const int ly = HW < 128 ? 8 : 1024 / lx;
-  dim3 grid((C8 + lx - 1) / lx, N), block(lx, ly);
+  // ... 512 threads once there is a block per SM (measured, teacher forward at 256 faces: 4.91 ms with
+  // 1024-thread blocks, 4.80 with 512, 4.90 with 256; at 32 faces 1.25 / 1.30 / 1.32 ms: few blocks want all the threads)
+  const int gx = (C8 + lx - 1) / lx;
+  const int threads = gx * N >= ctx->num_sms ? 512 : 1024;
+  const int ly = HW < 128 ? 8 : (threads / lx > 0 ? threads / lx : 1);
+  dim3 grid(gx, N), block(lx, ly);
   se_squeeze_kernel<__half><<<grid, block, 0, ctx->stream>>>(static_cast<const __half*>(u16), HW, C, s);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
@@ -743,6 +758,13 @@ extern "C" int xemo_op_se_gate(xemo_ctx* ctx, const float* s, int N, int C, int 
   // (a two-launch form -- hidden units over a (samples, units) grid, then gates over a (samples, channels) grid -- was
   // measured in round 2: 5.23 vs 5.12 ms teacher forward at 256 faces, 1.43 vs 1.34 ms at 32: every thread still walks a
   // dependent chain of L2 loads; removed)
+  static const bool cluster_form = !(getenv("XEMO_SE_GATE_CLUSTER") && getenv("XEMO_SE_GATE_CLUSTER")[0] == '0');
+  if (cluster_form) {
+    SeGateParams p{s, N, C, 0, Cr, nullptr, nullptr, nullptr, w1, b1, w2, b2, gate, nullptr};
+    XEMO_CUDA(ctx, se_gate_cluster_launch<false>(p, ctx->num_sms, ctx->stream));
+    ctx->launches += 1;
+    return XEMO_OK;
+  }
   const int threads = C <= 512 ? 512 : 1024;  // latency-bound: many warps keep enough weight loads in flight
   se_gate_kernel<<<(N + kSeSpb - 1) / kSeSpb, threads, size_t(kSeSpb) * (C + Cr) * 4, ctx->stream>>>(s, N, C, Cr, w1, b1, w2, b2, gate);
   XEMO_LAUNCHED(ctx, 1);
@@ -755,6 +777,13 @@ extern "C" int xemo_op_se_gate_lin(xemo_ctx* ctx, const float* m2, int N, int C,
   XEMO_REQUIRE(ctx, m2 && w3_16 && a3 && b3 && w1 && w2t && nc_scale && nc_shift && C % 128 == 0 && Cm % 64 == 0 &&
                         size_t(kSeSpb) * (Cm + C + Cr) * 4 <= 48 * 1024,
                "se_gate_lin: C must be a multiple of 128, Cm of 64, and (Cm + C + Cr) <= 6144");
+  static const bool cluster_form = !(getenv("XEMO_SE_GATE_CLUSTER") && getenv("XEMO_SE_GATE_CLUSTER")[0] == '0');
+  if (cluster_form && (Cm == 64 || Cm == 128 || Cm == 256 || Cm == 512)) {
+    SeGateParams p{m2, N, C, Cm, Cr, static_cast<const __half*>(w3_16), a3, b3, w1, b1, w2t, b2, nc_scale, nc_shift};
+    XEMO_CUDA(ctx, se_gate_cluster_launch<true>(p, ctx->num_sms, ctx->stream));
+    ctx->launches += 1;
+    return XEMO_OK;
+  }
   const int threads = C <= 512 ? 512 : 1024;
   se_gate_lin_kernel<<<(N + kSeSpb - 1) / kSeSpb, threads, size_t(kSeSpb) * (Cm + C + Cr) * 4, ctx->stream>>>(
       m2, N, C, Cm, Cr, static_cast<const __half*>(w3_16), a3, b3, w1, b1, w2t, b2, nc_scale, nc_shift);

@@ -48,7 +48,18 @@ struct Arena {
   void* alloc(size_t bytes, bool zero = false) {
     void* p = nullptr;
     if (bytes == 0) bytes = 16;
-    if (cudaMallocAsync(&p, bytes, ctx->stream) != cudaSuccess) { failed = true; return nullptr; }
+    if (!ctx->pool) {
+      // the context's own pool with an unbounded release threshold: the device's default pool hands freed blocks back
+      // to the driver at every synchronisation, and a chain of boundary calls then re-maps gigabytes of scratch per step
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = ctx->device;
+      if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess) { ctx->pool = nullptr; failed = true; return nullptr; }
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    if (cudaMallocFromPoolAsync(&p, bytes, ctx->pool, ctx->stream) != cudaSuccess) { failed = true; return nullptr; }
     bufs.push_back(p);
     if (zero) cudaMemsetAsync(p, 0, bytes, ctx->stream);
     return p;

@@ -272,3 +272,46 @@ def test_full_height_data_gradient_matches_the_general_form_and_the_oracle(env, 
     assert np.isfinite(out["fullheight"]).all()
     assert np.abs(out["fullheight"] - dx_ref).max() / scale < 1e-3
     assert np.abs(out["fullheight"] - out["general"]).max() / scale < 1e-3
+
+
+@pytest.mark.parametrize("n", [1, 3, 32, 64, 100, 256])                   # cluster sizes 8, 8, 8, 4, 2, 1
+@pytest.mark.parametrize("dims", [(256, 64), (512, 128), (1024, 256), (2048, 512)])   # (C, Cm) of SENet50's four stages
+def test_se_gate_kernels_match_fp64_at_every_cluster_size(env, n, dims):
+    """mcnExtraLayers SE gate (GlobalPooling -> Conv -> ReLU -> Conv -> Sigmoid): the plain form from s and the form
+    by linearity from mean_hw(t2), against numpy fp64.  The cluster of CTAs that shares a group of two samples
+    changes with N; an odd N leaves the last group half empty."""
+    torch, ctx, stream = env
+    Cc, Cm = dims
+    Cr = Cc // 16
+    rng = np.random.default_rng(n * 7 + Cc)
+    s = rng.standard_normal((n, Cc)).astype(np.float32)
+    w1 = (rng.standard_normal((Cr, Cc)) / np.sqrt(Cc)).astype(np.float32)
+    b1 = (0.1 * rng.standard_normal(Cr)).astype(np.float32)
+    w2t = (rng.standard_normal((Cr, Cc)) / np.sqrt(Cr)).astype(np.float32)
+    b2 = (0.1 * rng.standard_normal(Cc)).astype(np.float32)
+
+    def gate_of(sv):
+        hid = np.maximum(sv.astype(np.float64) @ w1.astype(np.float64).T + b1, 0)
+        return 1 / (1 + np.exp(-(hid @ w2t.astype(np.float64) + b2)))
+
+    with torch.cuda.stream(stream):
+        d = {k: torch.from_numpy(v).cuda() for k, v in dict(s=s, w1=w1, b1=b1, w2t=w2t, b2=b2).items()}
+        g = torch.full((n, Cc), -1.0, device="cuda")
+        ctx.op_se_gate(_p(d["s"]), n, Cc, Cr, _p(d["w1"]), _p(d["b1"]), _p(d["w2t"]), _p(d["b2"]), _p(g))
+        ctx.sync()
+        assert np.abs(g.cpu().numpy() - gate_of(s)).max() < 2e-6
+
+        m2 = rng.standard_normal((n, Cm)).astype(np.float32)
+        w3 = (rng.standard_normal((Cc, Cm)) / np.sqrt(Cm)).astype(np.float16)
+        a3 = rng.uniform(0.5, 1.5, Cc).astype(np.float32)
+        b3 = (0.2 * rng.standard_normal(Cc)).astype(np.float32)
+        dl = {k: torch.from_numpy(v).cuda() for k, v in dict(m2=m2, w3=w3, a3=a3, b3=b3).items()}
+        sc = torch.full((n, Cc), -1.0, device="cuda")
+        sh = torch.full((n, Cc), -1.0, device="cuda")
+        ctx.op_se_gate_lin(_p(dl["m2"]), n, Cc, Cm, Cr, _p(dl["w3"]), _p(dl["a3"]), _p(dl["b3"]), _p(d["w1"]), _p(d["b1"]), _p(d["w2t"]),
+                           _p(d["b2"]), _p(sc), _p(sh))
+        ctx.sync()
+        s_lin = a3 * (m2.astype(np.float64) @ w3.astype(np.float64).T) + b3
+        gl = gate_of(s_lin)
+        assert np.abs(sc.cpu().numpy() - gl * a3).max() < 5e-6
+        assert np.abs(sh.cpu().numpy() - gl * b3).max() < 5e-6

@@ -179,6 +179,20 @@ def test_gpuarray_inputs_stay_on_device(vl, M):
     assert np.array_equal(vl.gather(r), np.maximum(vl.gather(y), 0))
 
 
+def test_scratch_pool_is_kept_between_calls_and_can_be_trimmed(vl, M):
+    """The boundary operators draw their scratch from the context's own stream-ordered pool (kept between calls);
+    xemo_trim hands it back and the next call simply grows it again."""
+    rng = np.random.default_rng(10)
+    x = rng.standard_normal((20, 20, 32, 2)).astype(np.float32)
+    f = (rng.standard_normal((3, 3, 32, 32)) / 17).astype(np.float32)
+    ctx = vl.default_context()
+    y0 = vl.vl_nnconv(x, f, None, pad=1)
+    ctx.trim()
+    y1 = vl.vl_nnconv(x, f, None, pad=1)
+    assert np.array_equal(y0, y1)
+    ctx.trim()
+
+
 def test_error_behaviour(vl):
     from mcncrossmodalemotions_b200._lib import XemoError
 
