@@ -4,10 +4,13 @@
 // how many SMs pull weights at once.
 //
 //   * every phase issues its weight loads in batches of >= 8 independent 16-byte loads per thread before the FMAs;
-//   * a thread-block CLUSTER of K CTAs (1, 2, 4, 8; chosen so that groups * K fills the SMs) shares one group of
+//   * a thread-block CLUSTER of K CTAs (1, 2, 4; chosen so that groups * K stays within the SMs) shares one group of
 //     samples: CTA r computes 1/K of each phase's outputs from 1/K of the weights and writes them into the shared
 //     memory of ALL K CTAs (st.shared::cluster through mapa), with a cluster barrier between phases.  At 256 faces
-//     K = 1 (128 groups); at the 32 faces per GPU of the 8-GPU strong-scaling point K = 8 turns 16 busy SMs into 128.
+//     K = 1 (128 groups); at the 32 faces per GPU of the 8-GPU strong-scaling point K = 4 turns 16 busy SMs into 64.
+//     Measured (teacher forward graph, ms, K capped at 1 / 2 / 4 / 8): 32 faces 1.207 / 1.152 / 1.124 / 1.245,
+//     64 faces 1.728 / 1.673 / 1.645 / --, 128 faces 2.765 / 2.711 / -- / --; the round-1 kernels: 1.349 at 32 faces.
+//     Clusters of 8 CTAs x 1024 threads lose more to placement and barriers than they gain: K <= 4.
 //
 //   kLin = false : s [N][C] (se_squeeze of u)               -> gate [N][C]
 //   kLin = true  : m2 [N][Cm] (se_squeeze of the 3x3 output) -> s = a3 * (W3 m2) + b3 -> gate -> nc_scale = gate * a3,
@@ -15,6 +18,8 @@
 //                  (SE by linearity)
 // w3: [C][Cm] fp16 (the KRSC 1x1 expand filter); w1: [Cr][C] fp32; w2t: [Cr][C] fp32 (second FC transposed).
 #pragma once
+#include <stdlib.h>
+
 #include "hbm_kernels.cuh"
 #include "xemo_ptx.cuh"
 
@@ -235,18 +240,20 @@ static __global__ void __launch_bounds__(kSeGateThreads, 1) se_gate_cluster_kern
   }
 }
 
-// cluster size for `groups` sample groups: the largest power of two <= 8 that keeps groups * K within the SMs and
+// cluster size for `groups` sample groups: the largest power of two <= 4 that keeps groups * K within the SMs and
 // leaves every CTA at least 32 channels and 2 hidden units
 static inline int se_gate_cluster_size(int groups, int C, int Cr, int num_sms) {
   int K = 1;
-  while (K < 8 && groups * (K * 2) <= num_sms && C % (K * 2) == 0 && C / (K * 2) >= 32 && Cr % (K * 2) == 0 && Cr / (K * 2) >= 2) K *= 2;
+  while (K < 4 && groups * (K * 2) <= num_sms && C % (K * 2) == 0 && C / (K * 2) >= 32 && Cr % (K * 2) == 0 && Cr / (K * 2) >= 2) K *= 2;
   return K;
 }
 
 template <bool kLin>
 static cudaError_t se_gate_cluster_launch(const SeGateParams& p, int num_sms, cudaStream_t stream, int force_k = 0) {
   const int groups = (p.N + kSeSpb - 1) / kSeSpb;
-  const int K = force_k > 0 ? force_k : se_gate_cluster_size(groups, p.C, p.Cr, num_sms);
+  static const int env_k = [] { const char* e = getenv("XEMO_SE_GATE_K"); return e ? atoi(e) : 0; }();   // A/B knob: cap on K
+  int K = force_k > 0 ? force_k : se_gate_cluster_size(groups, p.C, p.Cr, num_sms);
+  if (env_k > 0 && K > env_k) K = env_k;
   const size_t smem = size_t(kSeSpb) * ((kLin ? p.Cm : 0) + p.C + p.Cr + kSeGateThreads) * sizeof(float);
   if (smem > 48 * 1024 || p.C % K || p.Cr % K) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg = {};

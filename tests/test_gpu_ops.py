@@ -274,7 +274,7 @@ def test_full_height_data_gradient_matches_the_general_form_and_the_oracle(env, 
     assert np.abs(out["fullheight"] - out["general"]).max() / scale < 1e-3
 
 
-@pytest.mark.parametrize("n", [1, 3, 32, 64, 100, 256])                   # cluster sizes 8, 8, 8, 4, 2, 1
+@pytest.mark.parametrize("n", [1, 3, 32, 64, 100, 256])                   # cluster sizes 4, 4, 4, 4, 2, 1
 @pytest.mark.parametrize("dims", [(256, 64), (512, 128), (1024, 256), (2048, 512)])   # (C, Cm) of SENet50's four stages
 def test_se_gate_kernels_match_fp64_at_every_cluster_size(env, n, dims):
     """mcnExtraLayers SE gate (GlobalPooling -> Conv -> ReLU -> Conv -> Sigmoid): the plain form from s and the form

@@ -67,7 +67,7 @@ if __name__ == "__main__":
         for v in ("0", "28", "14", "7"):
             out["teacher senet50 XEMO_SE_LIN_MIN_HW=" + v] = with_env({"XEMO_SE_LIN_MIN_HW": v}, lambda: teacher_ms(n))
     if "gate" in which:     # (read once per process by the library: pass XEMO_SE_GATE_CLUSTER from the outside)
-        v = os.environ.get("XEMO_SE_GATE_CLUSTER", "1")
+        v = os.environ.get("XEMO_SE_GATE_CLUSTER", "1") + " XEMO_SE_GATE_K=" + os.environ.get("XEMO_SE_GATE_K", "0")
         out["teacher senet50 XEMO_SE_GATE_CLUSTER=" + v] = teacher_ms(n)
     if "costmodel" in which:
         v = os.environ.get("XEMO_CONV_COSTMODEL", "1")   # read once per process by the library: one value per run
