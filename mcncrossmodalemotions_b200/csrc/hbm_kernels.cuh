@@ -1009,52 +1009,85 @@ __global__ void relu_bwd_kernel(const T* __restrict__ y, const T* __restrict__ d
 //   gate    : a = sigmoid(W2 * relu(W1 * s + b1) + b2)              (one block per sample)
 //   excite  : y = relu(a[n][c] * u + shortcut)                      (vectorised pass)
 // ============================================================================================
-template <typename T>
+template <typename T, int F = 1>
 __global__ void se_squeeze_kernel(const T* __restrict__ u, int HW, int C, float* __restrict__ s) {
-  // grid: (ceil(C/8/LX), N); block LX x LY (= 1024 threads): x -> channel group, y -> pixel stride, four 16-byte
-  // loads in flight per thread.  LX = min(32, C/8) so that narrow tensors still fill the block.
-  const int LX = blockDim.x, LY = blockDim.y;
+  // grid: (ceil(C/8/LX), N); x -> channel group, y -> pixel stride.  The sum is defined over VLY = F * blockDim.y VIRTUAL
+  // pixel-stride lanes (lane v takes pixels v, v + VLY, ... in groups of four, then singly; the lanes are added in order):
+  // a thread owns the F lanes y, y + blockDim.y, ..., so that a block of 1024 / F threads produces bit-identical means
+  // -- the launcher picks F by grid size, and the same face must give the same logits in any batch.
+  // LX = min(32, C/8) so that narrow tensors still fill the block; LX * VLY <= 1024.
+  const int LX = blockDim.x, LYt = blockDim.y, VLY = LYt * F;
   const int n = blockIdx.y;
   const int c8 = blockIdx.x * LX + threadIdx.x;
   __shared__ float part[1024 * 9];
-  float acc[8];
+  float acc[F][8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int f = 0; f < F; ++f)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[f][k] = 0.f;
   if (c8 * 8 < C) {
     const T* base = u + size_t(n) * HW * C + c8 * 8;
-    int p = threadIdx.y;
-    for (; p + 3 * LY < HW; p += 4 * LY) {
+    auto quad = [&](int p, float (&a)[8]) {
       Vec8<T> v0, v1, v2, v3;
       v0.load(base + size_t(p) * C);
-      v1.load(base + size_t(p + LY) * C);
-      v2.load(base + size_t(p + 2 * LY) * C);
-      v3.load(base + size_t(p + 3 * LY) * C);
+      v1.load(base + size_t(p + VLY) * C);
+      v2.load(base + size_t(p + 2 * VLY) * C);
+      v3.load(base + size_t(p + 3 * VLY) * C);
       float f0[8], f1[8], f2[8], f3[8];
       v0.to_float(f0); v1.to_float(f1); v2.to_float(f2); v3.to_float(f3);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += (f0[k] + f1[k]) + (f2[k] + f3[k]);
-    }
-    for (; p < HW; p += LY) {
+      for (int k = 0; k < 8; ++k) a[k] += (f0[k] + f1[k]) + (f2[k] + f3[k]);
+    };
+    auto single = [&](int p, float (&a)[8]) {
       Vec8<T> v;
       v.load(base + size_t(p) * C);
       float f[8];
       v.to_float(f);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += f[k];
-    }
-  }
-  float* mine = part + (threadIdx.y * LX + threadIdx.x) * 9;
+      for (int k = 0; k < 8; ++k) a[k] += f[k];
+    };
+    int p0 = threadIdx.y;
+    if constexpr (F == 2) {
+      // both lanes' groups of four in one iteration: eight 16-byte loads in flight
+      int p1 = p0 + LYt;
+      for (; p1 + 3 * VLY < HW; p0 += 4 * VLY, p1 += 4 * VLY) {
+        Vec8<T> a0, a1, a2, a3, b0, b1, b2, b3;
+        a0.load(base + size_t(p0) * C);
+        a1.load(base + size_t(p0 + VLY) * C);
+        a2.load(base + size_t(p0 + 2 * VLY) * C);
+        a3.load(base + size_t(p0 + 3 * VLY) * C);
+        b0.load(base + size_t(p1) * C);
+        b1.load(base + size_t(p1 + VLY) * C);
+        b2.load(base + size_t(p1 + 2 * VLY) * C);
+        b3.load(base + size_t(p1 + 3 * VLY) * C);
+        float f0[8], f1[8], f2[8], f3[8];
+        a0.to_float(f0); a1.to_float(f1); a2.to_float(f2); a3.to_float(f3);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) mine[k] = acc[k];
+        for (int k = 0; k < 8; ++k) acc[0][k] += (f0[k] + f1[k]) + (f2[k] + f3[k]);
+        b0.to_float(f0); b1.to_float(f1); b2.to_float(f2); b3.to_float(f3);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[F - 1][k] += (f0[k] + f1[k]) + (f2[k] + f3[k]);
+      }
+      for (; p1 < HW; p1 += VLY) single(p1, acc[F - 1]);   // (lane y + blockDim.y has no group of four left)
+    }
+    for (; p0 + 3 * VLY < HW; p0 += 4 * VLY) quad(p0, acc[0]);
+    for (; p0 < HW; p0 += VLY) single(p0, acc[0]);
+  }
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    float* mine = part + ((threadIdx.y + f * LYt) * LX + threadIdx.x) * 9;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mine[k] = acc[f][k];
+  }
   __syncthreads();
-  // LX x 8 (channel-group, k) outputs, each summed over the LY pixel strides by one thread
+  // LX x 8 (channel-group, k) outputs, each summed over the VLY lanes by one thread
   const int t = threadIdx.y * LX + threadIdx.x;
   if (t < LX * 8) {
     const int cg = t >> 3, k = t & 7;
     const int c = (blockIdx.x * LX + cg) * 8 + k;
     if (c < C) {
       float tsum = 0.f;
-      for (int j = 0; j < LY; ++j) tsum += part[(j * LX + cg) * 9 + k];
+      for (int j = 0; j < VLY; ++j) tsum += part[(j * LX + cg) * 9 + k];
       s[size_t(n) * C + c] = tsum / float(HW);
     }
   }

@@ -53,7 +53,19 @@ __device__ __forceinline__ void st_cluster_f32(float* local, uint32_t rank, floa
 
 constexpr int kSeGateThreads = 1024;
 
-// dynamic smem (floats): kSeSpb * ((kLin ? Cm : 0) + C + Cr) + kSeSpb * kSeGateThreads
+// ranges of hidden units in the last phase's sum (see there) and thread groups that share one channel's ranges
+__host__ __device__ inline int se_gate_ranges(int C, int Cr) {
+  int pc = 1;
+  while (pc * 2 <= Cr / 8 && pc * 2 <= 4096 / C) pc *= 2;
+  return pc;
+}
+__host__ __device__ inline int se_gate_groups(int pc, int nout) {
+  int groups = 1;
+  while (groups * 2 <= pc && groups * 2 * nout <= kSeGateThreads) groups *= 2;
+  return groups;
+}
+
+// dynamic smem (floats): kSeSpb * ((kLin ? Cm : 0) + C + Cr) + (groups > 1 ? ranges * kSeSpb * C / K : 0)
 template <bool kLin, int CM64>
 static __global__ void __launch_bounds__(kSeGateThreads, 1) se_gate_cluster_kernel(SeGateParams p) {
   extern __shared__ __align__(16) float se_sm[];
@@ -63,7 +75,7 @@ static __global__ void __launch_bounds__(kSeGateThreads, 1) se_gate_cluster_kern
   float* mv = se_sm;                       // [kSeSpb][Cm]
   float* sv = mv + kSeSpb * Cm;            // [kSeSpb][C]
   float* hid = sv + kSeSpb * C;            // [kSeSpb][Cr]
-  float* red = hid + kSeSpb * Cr;          // [parts][kSeSpb][C / K] partial sums of the last phase
+  float* red = hid + kSeSpb * Cr;          // [ranges][kSeSpb][C / K] partial sums of the last phase
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int nwarps = kSeGateThreads / 32;
 
@@ -172,7 +184,7 @@ static __global__ void __launch_bounds__(kSeGateThreads, 1) se_gate_cluster_kern
 
   {
     // gate[c] = sigmoid(W2[c, :] . hidden + b2[c]) for this CTA's C / K channels: a thread per channel (coalesced
-    // rows of w2t); with fewer channels than threads the hidden range is split over `parts` thread groups
+    // rows of w2t); with fewer channels than threads the ranges of hidden units go to separate thread groups
     const int nout = C / K, c_lo = rank * nout;
     auto finish = [&](int c, const float (&t)[kSeSpb]) {
       float a = 0.f, b = 0.f;
@@ -192,47 +204,56 @@ static __global__ void __launch_bounds__(kSeGateThreads, 1) se_gate_cluster_kern
           }
         }
     };
-    if (nout >= kSeGateThreads) {
+    // The sum over the hidden units is DEFINED as b2 + p_0 + p_1 + ... over `pc` equal ranges of units (each summed in
+    // order from zero), pc a function of (C, Cr) only: whatever the cluster size -- it follows the batch -- a face gets
+    // bit-identical gates.  pc = min(Cr / 8, 4096 / C) rounded down to a power of two: every range keeps a batch of 8
+    // loads and the smallest slice (C / 4 channels, 1024 threads) still has a thread group per range.
+    const int pc = se_gate_ranges(C, Cr);
+    const int jper = (Cr + pc - 1) / pc;
+    auto range_sum = [&](int c, int part, float (&t)[kSeSpb]) {
+#pragma unroll
+      for (int q = 0; q < kSeSpb; ++q) t[q] = 0.f;
+      const int j_hi = min(Cr, (part + 1) * jper);
+#pragma unroll 8
+      for (int j = part * jper; j < j_hi; ++j) {
+        const float w = __ldg(p.w2t + size_t(j) * C + c);
+#pragma unroll
+        for (int q = 0; q < kSeSpb; ++q) t[q] = fmaf(w, hid[q * Cr + j], t[q]);
+      }
+    };
+    const int groups = se_gate_groups(pc, nout);
+    if (groups == 1) {
       for (int o = tid; o < nout; o += kSeGateThreads) {
         const int c = c_lo + o;
-        float t[kSeSpb];
+        float t[kSeSpb], r[kSeSpb];
 #pragma unroll
         for (int q = 0; q < kSeSpb; ++q) t[q] = p.b2 ? __ldg(p.b2 + c) : 0.f;
-#pragma unroll 8
-        for (int j = 0; j < Cr; ++j) {
-          const float w = __ldg(p.w2t + size_t(j) * C + c);
+        for (int part = 0; part < pc; ++part) {
+          range_sum(c, part, r);
 #pragma unroll
-          for (int q = 0; q < kSeSpb; ++q) t[q] = fmaf(w, hid[q * Cr + j], t[q]);
+          for (int q = 0; q < kSeSpb; ++q) t[q] += r[q];
         }
         finish(c, t);
       }
     } else {
-      int parts = kSeGateThreads / nout;
-      if (parts > Cr / 8) parts = Cr / 8 > 0 ? Cr / 8 : 1;   // at least 8 hidden units (one batch of loads) per part
-      const int part = tid / nout, o = tid - part * nout;
-      const int jper = (Cr + parts - 1) / parts;
+      const int grp = tid / nout, o = tid - grp * nout;
       const int c = c_lo + o;
-      if (part < parts) {
-        float t[kSeSpb];
+      const int per_group = pc / groups;
+      if (grp < groups) {
+        for (int part = grp * per_group; part < (grp + 1) * per_group; ++part) {
+          float r[kSeSpb];
+          range_sum(c, part, r);
 #pragma unroll
-        for (int q = 0; q < kSeSpb; ++q) t[q] = 0.f;
-        const int j_hi = min(Cr, (part + 1) * jper);
-#pragma unroll 8
-        for (int j = part * jper; j < j_hi; ++j) {
-          const float w = __ldg(p.w2t + size_t(j) * C + c);
-#pragma unroll
-          for (int q = 0; q < kSeSpb; ++q) t[q] = fmaf(w, hid[q * Cr + j], t[q]);
+          for (int q = 0; q < kSeSpb; ++q) red[(part * kSeSpb + q) * nout + o] = r[q];
         }
-#pragma unroll
-        for (int q = 0; q < kSeSpb; ++q) red[(part * kSeSpb + q) * nout + o] = t[q];
       }
       __syncthreads();
-      if (part == 0) {
+      if (grp == 0) {
         float t[kSeSpb];
 #pragma unroll
         for (int q = 0; q < kSeSpb; ++q) {
           t[q] = p.b2 ? __ldg(p.b2 + c) : 0.f;
-          for (int k = 0; k < parts; ++k) t[q] += red[(k * kSeSpb + q) * nout + o];
+          for (int k = 0; k < pc; ++k) t[q] += red[(k * kSeSpb + q) * nout + o];
         }
         finish(c, t);
       }
@@ -254,8 +275,11 @@ static cudaError_t se_gate_cluster_launch(const SeGateParams& p, int num_sms, cu
   static const int env_k = [] { const char* e = getenv("XEMO_SE_GATE_K"); return e ? atoi(e) : 0; }();   // A/B knob: cap on K
   int K = force_k > 0 ? force_k : se_gate_cluster_size(groups, p.C, p.Cr, num_sms);
   if (env_k > 0 && K > env_k) K = env_k;
-  const size_t smem = size_t(kSeSpb) * ((kLin ? p.Cm : 0) + p.C + p.Cr + kSeGateThreads) * sizeof(float);
-  if (smem > 48 * 1024 || p.C % K || p.Cr % K) return cudaErrorInvalidValue;
+  if (p.C % K || p.Cr % K) return cudaErrorInvalidValue;
+  const int pc = se_gate_ranges(p.C, p.Cr), nout = p.C / K;
+  const size_t red = se_gate_groups(pc, nout) > 1 ? size_t(pc) * kSeSpb * nout : 0;
+  const size_t smem = (size_t(kSeSpb) * ((kLin ? p.Cm : 0) + p.C + p.Cr) + red) * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(unsigned(groups * K));
   cfg.blockDim = dim3(kSeGateThreads);

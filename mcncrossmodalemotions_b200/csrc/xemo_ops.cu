@@ -740,14 +740,16 @@ extern "C" int xemo_op_se_squeeze(xemo_ctx* ctx, const void* u16, int N, int HW,
   int lx = 1;
   while (lx < 32 && lx * 2 <= C8) lx *= 2;   // min(32, largest power of two <= C/8)
   // pixel-stride lanes: 1024 / lx for the large maps; the 7 x 7 maps (49 pixels) would leave half of a 32-lane stride
-  // idle and pay a 1024-thread barrier for two loads per thread (1.4 TB/s in the launch list): 8 lanes there
-  // ... 512 threads once there is a block per SM (measured, teacher forward at 256 faces: 4.91 ms with
-  // 1024-thread blocks, 4.80 with 512, 4.90 with 256; at 32 faces 1.25 / 1.30 / 1.32 ms: few blocks want all the threads)
+  // idle and pay a 1024-thread barrier for two loads per thread (1.4 TB/s in the launch list): 8 lanes there.
+  // Once the grid has a block per SM, 512-thread blocks that own two lanes each (same summation order, bit-identical
+  // result) co-schedule better (measured, teacher forward at 256 faces: 4.91 ms with 1024-thread blocks, 4.80 with 512,
+  // 4.90 with 256; at 32 faces 1.25 / 1.30 / 1.32 ms: few blocks want all the threads).
   const int gx = (C8 + lx - 1) / lx;
-  const int threads = gx * N >= ctx->num_sms ? 512 : 1024;
-  const int ly = HW < 128 ? 8 : (threads / lx > 0 ? threads / lx : 1);
-  dim3 grid(gx, N), block(lx, ly);
-  se_squeeze_kernel<__half><<<grid, block, 0, ctx->stream>>>(static_cast<const __half*>(u16), HW, C, s);
+  const int ly = HW < 128 ? 8 : 1024 / lx;
+  const bool two = HW >= 128 && ly % 2 == 0 && gx * N >= ctx->num_sms;
+  dim3 grid(gx, N), block(lx, two ? ly / 2 : ly);
+  if (two) se_squeeze_kernel<__half, 2><<<grid, block, 0, ctx->stream>>>(static_cast<const __half*>(u16), HW, C, s);
+  else se_squeeze_kernel<__half, 1><<<grid, block, 0, ctx->stream>>>(static_cast<const __half*>(u16), HW, C, s);
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }

@@ -315,3 +315,39 @@ def test_se_gate_kernels_match_fp64_at_every_cluster_size(env, n, dims):
         gl = gate_of(s_lin)
         assert np.abs(sc.cpu().numpy() - gl * a3).max() < 5e-6
         assert np.abs(sh.cpu().numpy() - gl * b3).max() < 5e-6
+
+
+@pytest.mark.parametrize("dims", [(256, 64, 56 * 56), (512, 128, 28 * 28), (1024, 256, 14 * 14), (2048, 512, 49)])
+def test_se_squeeze_and_gate_do_not_depend_on_the_batch(env, dims):
+    """Block sizes (squeeze) and cluster sizes (gate) follow the batch; the summation orders do not: the first two faces of
+    a batch of 256 get bit-identical means and gates when they are run as a batch of 2, 32 or 100."""
+    torch, ctx, stream = env
+    Cc, Cm, HW = dims
+    Cr = Cc // 16
+    rng = np.random.default_rng(Cc)
+    with torch.cuda.stream(stream):
+        w1 = torch.from_numpy((rng.standard_normal((Cr, Cc)) / np.sqrt(Cc)).astype(np.float32)).cuda()
+        b1 = torch.from_numpy((0.1 * rng.standard_normal(Cr)).astype(np.float32)).cuda()
+        w2t = torch.from_numpy((rng.standard_normal((Cr, Cc)) / np.sqrt(Cr)).astype(np.float32)).cuda()
+        b2 = torch.from_numpy((0.1 * rng.standard_normal(Cc)).astype(np.float32)).cuda()
+        w3 = torch.from_numpy((rng.standard_normal((Cc, Cm)) / np.sqrt(Cm)).astype(np.float16)).cuda()
+        a3 = torch.from_numpy(rng.uniform(0.5, 1.5, Cc).astype(np.float32)).cuda()
+        b3 = torch.from_numpy((0.2 * rng.standard_normal(Cc)).astype(np.float32)).cuda()
+        u = torch.from_numpy(rng.standard_normal((256, HW, Cm)).astype(np.float16)).cuda()
+
+        def run(n):
+            m2 = torch.empty((n, Cm), device="cuda")
+            ctx.op_se_squeeze(_p(u), n, HW, Cm, _p(m2))
+            sc, sh = torch.empty((n, Cc), device="cuda"), torch.empty((n, Cc), device="cuda")
+            ctx.op_se_gate_lin(_p(m2), n, Cc, Cm, Cr, _p(w3), _p(a3), _p(b3), _p(w1), _p(b1), _p(w2t), _p(b2), _p(sc), _p(sh))
+            s = (sc + sh).contiguous()                   # any [n][C] fp32 vector serves as the plain gate's input
+            g = torch.empty((n, Cc), device="cuda")
+            ctx.op_se_gate(_p(s), n, Cc, Cr, _p(w1), _p(b1), _p(w2t), _p(b2), _p(g))
+            ctx.sync()
+            return [t[:2].cpu().numpy() for t in (m2, sc, sh, g)]
+
+        ref = run(256)
+        assert np.abs(ref[0] - u[:2].float().mean(1).cpu().numpy()).max() < 1e-5
+        for n in (2, 32, 100):
+            for a, b, what in zip(ref, run(n), ("squeeze", "nc_scale", "nc_shift", "gate")):
+                assert np.array_equal(a, b), (what, n)

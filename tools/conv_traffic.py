@@ -1,7 +1,8 @@
 """DRAM traffic of the tcgen05 convolution launches of ONE distillation step, from an ncu csv captured with
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:conv_ ...
-Writes profiles/r01_conv_traffic.json (bench.py reports its per-step total as roofline.traffic).
-    python tools/conv_traffic.py gpurun_out/conv_traffic.csv <conv_launches_per_step> <per_gpu_batch>"""
+Writes profiles/r02_conv_traffic.json (bench.py points at it from roofline.traffic_note; the run itself reports null).
+    python tools/conv_traffic.py gpurun_out/conv_traffic.csv <conv_launches_per_step, 0 = half of the capture (op_breakdown
+    runs two steps)> <per_gpu_batch> [out.json]"""
 import csv
 import json
 import sys
@@ -21,6 +22,8 @@ for r in rows[h + 1:]:
         launch[r[idc]] = {"kernel": r[ki].split("(")[0]}
         order.append(r[idc])
     launch[r[idc]][r[mi]] = float(r[vi].replace(",", "")) * scale.get(r[ui], 1)
+if per_step <= 0:
+    per_step = len(order) // 2
 ids = order[-per_step:]  # the last complete step in the capture
 tot_r = sum(launch[i].get("dram__bytes_read.sum", 0) for i in ids)
 tot_w = sum(launch[i].get("dram__bytes_write.sum", 0) for i in ids)
@@ -28,5 +31,5 @@ tot_t = sum(launch[i].get("gpu__time_duration.sum", 0) for i in ids)
 out = {"per_gpu_batch": batch, "conv_launches": len(ids), "dram_bytes_read": tot_r, "dram_bytes_write": tot_w,
        "dram_bytes": tot_r + tot_w, "ncu_serialised_seconds": tot_t,
        "note": "sum over the conv_fprop_kernel / conv_wgrad_kernel launches of one step (ncu, cold-cache, serialised)"}
-json.dump(out, open("profiles/r01_conv_traffic.json", "w"), indent=1)
+json.dump(out, open(sys.argv[4] if len(sys.argv) > 4 else "profiles/r02_conv_traffic.json", "w"), indent=1)
 print(json.dumps(out))

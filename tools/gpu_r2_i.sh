@@ -19,3 +19,5 @@ for f in ("bench_n1", "bench_ref", "bench_c2", "bench_c3", "bench_c5"):
 PY
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity-mode > gpurun_out/ncu_bench.log 2>&1; echo "launch list exit=$?"
 timeout 300 python tools/op_breakdown.py 256 > gpurun_out/op_breakdown.txt 2>&1; echo "op exit=$?"; tail -35 gpurun_out/op_breakdown.txt
+timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:conv_ --csv --log-file gpurun_out/conv_traffic.csv python tools/op_breakdown.py 256 > gpurun_out/ncu_traffic.log 2>&1; echo "traffic exit=$?"
+python tools/conv_traffic.py gpurun_out/conv_traffic.csv 0 256 gpurun_out/conv_traffic.json
