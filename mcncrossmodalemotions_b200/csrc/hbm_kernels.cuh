@@ -639,13 +639,13 @@ constexpr int kBnThreads = 256;
 struct BnGrid {
   int lanes, rows_par, slabs_x, slabs_y;
 };
-inline BnGrid bn_grid(size_t P, int C, int num_sms) {
+inline BnGrid bn_grid(size_t P, int C, int num_sms, int per_sm = 4) {
   BnGrid g;
   const int C8 = C >> 3;
   g.lanes = C8 < kBnThreads ? C8 : kBnThreads;
   g.rows_par = kBnThreads / g.lanes;
   g.slabs_y = (C8 + g.lanes - 1) / g.lanes;
-  size_t want = size_t(num_sms) * 4 / g.slabs_y;
+  size_t want = size_t(num_sms) * per_sm / g.slabs_y;
   if (want < 1) want = 1;
   const size_t max_slabs = (P + size_t(g.rows_par) * 4 - 1) / (size_t(g.rows_par) * 4);  // >= 4 rows per thread
   g.slabs_x = int(want < max_slabs ? want : (max_slabs < 1 ? 1 : max_slabs));

@@ -19,6 +19,14 @@ extern "C" int xemo_current_device(int* device) {
   return cudaGetDevice(device) == cudaSuccess ? XEMO_OK : XEMO_ERR_NO_DEVICE;
 }
 
+// grid-stride kernels: `waves` whole waves of the blocks that fit (XEMO_GRID_WAVES, default 1)
+static int grid_waves() {
+  static const int w = [] { const char* e = getenv("XEMO_GRID_WAVES"); const int v = e ? atoi(e) : 1; return v >= 1 && v <= 64 ? v : 1; }();
+  return w;
+}
+template <typename K>
+static int per_sm_of(K kernel, int threads = 256, size_t smem = 0) { return resident_blocks(kernel, threads, smem) * grid_waves(); }
+
 extern "C" int xemo_create(int device, void* cuda_stream, xemo_ctx** out) {
   if (!out) return XEMO_ERR_INVALID;
   *out = nullptr;
@@ -228,7 +236,7 @@ extern "C" int xemo_op_face_u8_rows_im2col(xemo_ctx* ctx, const uint8_t* faces, 
                                            const float* mean3, int S, int stride_w, int pad_l, int OW, void* dst16) {
   XEMO_REQUIRE(ctx, faces && mean3 && dst16 && S * 4 <= 32 && IH > 0 && IW > 0, "face_u8_rows_im2col: bad arguments");
   const size_t total = size_t(N) * OHt * OW;
-  face_u8_rows_im2col_kernel<<<grid_for(total, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
+  face_u8_rows_im2col_kernel<<<grid_for(total, 256, ctx->num_sms, 2 * per_sm_of(face_u8_rows_im2col_kernel)), 256, 0, ctx->stream>>>(
       faces, IH, IW, N, OHt, OWt, mean3, S, stride_w, pad_l, OW, static_cast<__half*>(dst16));
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
@@ -238,7 +246,7 @@ extern "C" int xemo_op_spec_s2d(xemo_ctx* ctx, const float* spec, int H, int W, 
                                 void* dst16) {
   XEMO_REQUIRE(ctx, spec && dst16, "spec_s2d: null pointer");
   const size_t total = size_t(N) * HP * OW;
-  spec_s2d_from_hwcn_kernel<<<grid_for(total, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
+  spec_s2d_from_hwcn_kernel<<<grid_for(total, 256, ctx->num_sms, 2 * per_sm_of(spec_s2d_from_hwcn_kernel)), 256, 0, ctx->stream>>>(
       spec, H, W, N, pad_t, pad_l, HP, OW, static_cast<__half*>(dst16));
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
@@ -526,14 +534,15 @@ static int maxpool_fwd_impl(xemo_ctx* ctx, const void* x16, int N, int H, int W,
   }
   const size_t total = size_t(N) * g.OH * g.OW * (C / 8);
   XEMO_REQUIRE(ctx, size_t(N) * g.OH * g.OW < (size_t(1) << 31), "maxpool_fwd: tensor too large for 32-bit pixel indices");
-  const int grid = fixed_channel_grid(total, C / 8, 256, ctx->num_sms, 8);
   const __half* xp = static_cast<const __half*>(x16);
   __half* yp = static_cast<__half*>(y16);
-#define XEMO_POOL_FWD(AFF, PHc, PWc) maxpool_fwd_kernel<__half, AFF, PHc, PWc><<<grid, 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax)
+#define XEMO_POOL_GRID(K) fixed_channel_grid(total, C / 8, 256, ctx->num_sms, per_sm_of(K))
+#define XEMO_POOL_FWD(AFF, PHc, PWc)                                                                                      \
+  maxpool_fwd_kernel<__half, AFF, PHc, PWc><<<XEMO_POOL_GRID((maxpool_fwd_kernel<__half, AFF, PHc, PWc>)), 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax)
 #define XEMO_POOL_FWD_H2(AFF, PHc, PWc)                                                                                   \
   do {                                                                                                                     \
-    if (nopad) maxpool_fwd_h2_kernel<AFF, PHc, PWc, true><<<grid, 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax, xwin);    \
-    else maxpool_fwd_h2_kernel<AFF, PHc, PWc, false><<<grid, 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax, xwin);         \
+    if (nopad) maxpool_fwd_h2_kernel<AFF, PHc, PWc, true><<<XEMO_POOL_GRID((maxpool_fwd_h2_kernel<AFF, PHc, PWc, true>)), 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax, xwin);    \
+    else maxpool_fwd_h2_kernel<AFF, PHc, PWc, false><<<XEMO_POOL_GRID((maxpool_fwd_h2_kernel<AFF, PHc, PWc, false>)), 256, 0, ctx->stream>>>(xp, g, a, b, yp, argmax, xwin);         \
   } while (0)
   const bool nopad = (pt == 0 && pl == 0 && (g.OH - 1) * sh + PH <= H && (g.OW - 1) * sw + PW <= W);
   XEMO_REQUIRE(ctx, !xwin || (PH == 3 && PW == 3) || (PH == 5 && PW == 3), "maxpool_fwd_win: only the 3x3 and 5x3 windows record the winner");
@@ -542,6 +551,7 @@ static int maxpool_fwd_impl(xemo_ctx* ctx, const void* x16, int N, int H, int W,
   else { if (a) XEMO_POOL_FWD(true, 0, 0); else XEMO_POOL_FWD(false, 0, 0); }
 #undef XEMO_POOL_FWD_H2
 #undef XEMO_POOL_FWD
+#undef XEMO_POOL_GRID
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }
@@ -571,15 +581,21 @@ static int maxpool_bwd_impl(xemo_ctx* ctx, const void* dy16, const uint8_t* argm
   }
   const size_t total = size_t(N) * H * W * (C / 8);
   XEMO_REQUIRE(ctx, size_t(N) * H * W < (size_t(1) << 31), "maxpool_bwd: tensor too large for 32-bit pixel indices");
-  const int grid = fixed_channel_grid(total, C / 8, 256, ctx->num_sms, 8);
   if (PH == 3 && PW == 3 && sh == 2 && sw == 2 && pt == 0 && pl == 0) {
     const size_t cells = size_t(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-    maxpool_bwd_3x3s2_h2_kernel<<<fixed_channel_grid(cells, C / 8, 256, ctx->num_sms, 8), 256, 0, ctx->stream>>>(
+    // (this one gathers through the arg-max bytes and writes 3x what it reads: it wants several waves -- measured at
+    // 1 / 2 / 4 / 8 / 16 waves of the 6 blocks that fit: 0.691 / 0.574 / 0.527 / 0.505 / 0.500 ms on the student's first
+    // pooling layer, where the BN / pooling-forward kernels are fastest at exactly one wave; XEMO_POOLBWD_WAVES)
+    static const int pool_waves = [] { const char* e = getenv("XEMO_POOLBWD_WAVES"); const int v = e ? atoi(e) : 8; return v >= 1 && v <= 64 ? v : 8; }();
+    const int per_sm = resident_blocks(maxpool_bwd_3x3s2_h2_kernel, 256) * pool_waves;
+    maxpool_bwd_3x3s2_h2_kernel<<<fixed_channel_grid(cells, C / 8, 256, ctx->num_sms, per_sm), 256, 0, ctx->stream>>>(
         static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
   } else if ((PH + sh - 1) / sh == 2 && (PW + sw - 1) / sw == 2)
-    maxpool_bwd_h2_kernel<2, 2><<<grid, 256, 0, ctx->stream>>>(static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
+    maxpool_bwd_h2_kernel<2, 2><<<fixed_channel_grid(total, C / 8, 256, ctx->num_sms, per_sm_of(maxpool_bwd_h2_kernel<2, 2>)), 256, 0, ctx->stream>>>(
+        static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
   else
-    maxpool_bwd_kernel<__half, 0, 0><<<grid, 256, 0, ctx->stream>>>(static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
+    maxpool_bwd_kernel<__half, 0, 0><<<fixed_channel_grid(total, C / 8, 256, ctx->num_sms, per_sm_of(maxpool_bwd_kernel<__half, 0, 0>)), 256, 0, ctx->stream>>>(
+        static_cast<const __half*>(dy16), argmax, g, static_cast<__half*>(dx16));
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
 }
@@ -650,7 +666,7 @@ extern "C" int xemo_op_bn_test(xemo_ctx* ctx, const float* moments, int C, const
 extern "C" int xemo_op_affine_act(xemo_ctx* ctx, const void* x16, size_t P, int C, const float* a, const float* b, int relu,
                                   void* y16) {
   XEMO_REQUIRE(ctx, x16 && y16 && C % 8 == 0, "affine_act: bad arguments");
-  affine_act_kernel<__half><<<fixed_channel_grid(P * (C / 8), C / 8, 256, ctx->num_sms, 8), 256, 0, ctx->stream>>>(
+  affine_act_kernel<__half><<<fixed_channel_grid(P * (C / 8), C / 8, 256, ctx->num_sms, per_sm_of(affine_act_kernel<__half>)), 256, 0, ctx->stream>>>(
       static_cast<const __half*>(x16), P, C, a, b, relu, static_cast<__half*>(y16));
   XEMO_LAUNCHED(ctx, 1);
   return XEMO_OK;
@@ -676,14 +692,16 @@ static int bn_bwd_impl(xemo_ctx* ctx, const __half* x, const __half* dy, size_t 
   else
     bn_bwd_reduce_kernel<__half, false><<<grid, kBnThreads, 0, ctx->stream>>>(x, dy, P, C, bg.lanes, bg.rows_par, moments, a, b, relu_mask, ws, nullptr, g0);
   XEMO_LAUNCHED(ctx, 1);
-  const int egrid = fixed_channel_grid(P * C8, C8, 256, ctx->num_sms, 8);
   const size_t cs_smem = dconv_bias ? size_t(C) * 4 : 0;
   if (test_mode) {
     XEMO_REQUIRE(ctx, !pg && !dconv_bias, "bn_bwd: test mode does not support the fused pool / bias-gradient variants");
+    const int egrid = fixed_channel_grid(P * C8, C8, 256, ctx->num_sms, per_sm_of(bn_bwd_test_kernel<__half>));
     bn_bwd_test_kernel<__half><<<egrid, 256, 0, ctx->stream>>>(x, dy, P, C, a, b, relu_mask, dx);
   } else if (pg) {
+    const int egrid = fixed_channel_grid(P * C8, C8, 256, ctx->num_sms, per_sm_of(bn_bwd_apply_kernel<__half, true>, 256, cs_smem));
     bn_bwd_apply_kernel<__half, true><<<egrid, 256, cs_smem, ctx->stream>>>(x, dy, P, C, moments, a, b, relu_mask, ws, dx, idx, *pg, dconv_bias, inv_grad_scale);
   } else {
+    const int egrid = fixed_channel_grid(P * C8, C8, 256, ctx->num_sms, per_sm_of(bn_bwd_apply_kernel<__half, false>, 256, cs_smem));
     bn_bwd_apply_kernel<__half, false><<<egrid, 256, cs_smem, ctx->stream>>>(x, dy, P, C, moments, a, b, relu_mask, ws, dx, nullptr, g0, dconv_bias, inv_grad_scale);
   }
   XEMO_LAUNCHED(ctx, 1);
@@ -813,7 +831,7 @@ extern "C" int xemo_op_se_excite(xemo_ctx* ctx, const void* u16, const float* ga
                                  int C, int relu, void* y16) {
   XEMO_REQUIRE(ctx, u16 && gate && y16 && C % 8 == 0, "se_excite: bad arguments");
   const size_t total8 = size_t(N) * HW * (C / 8);
-  se_excite_kernel<__half><<<grid_for(total8, 256, ctx->num_sms, 16), 256, 0, ctx->stream>>>(
+  se_excite_kernel<__half><<<grid_for(total8, 256, ctx->num_sms, 2 * per_sm_of(se_excite_kernel<__half>)), 256, 0, ctx->stream>>>(
       static_cast<const __half*>(u16), gate, static_cast<const __half*>(shortcut16), HW, C, total8, relu,
       static_cast<__half*>(y16));
   XEMO_LAUNCHED(ctx, 1);
@@ -872,7 +890,7 @@ extern "C" int xemo_op_stem_pool_bn_reduce(xemo_ctx* ctx, const void* xwin16, vo
   XEMO_REQUIRE(ctx, xwin16 && dpool16 && moments && a && b && acc && C % 8 == 0 && ld % 8 == 0 && ld >= C && P > 0,
                "stem_pool_bn_reduce: bad arguments");
   XEMO_CUDA(ctx, cudaMemsetAsync(acc, 0, size_t(2) * C * sizeof(double), ctx->stream));
-  const BnGrid bg = bn_grid(P, C, ctx->num_sms);
+  const BnGrid bg = bn_grid(P, C, ctx->num_sms, per_sm_of(stem_pool_bn_reduce_kernel, kBnThreads));
   dim3 grid(bg.slabs_x, bg.slabs_y);
   stem_pool_bn_reduce_kernel<<<grid, kBnThreads, 0, ctx->stream>>>(static_cast<const __half*>(xwin16), static_cast<__half*>(dpool16),
                                                                   P, C, ld, bg.lanes, bg.rows_par, moments, a, b, acc);
