@@ -350,10 +350,17 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int last_row = min(m0 + kConvBlockM, p.M) - 1;
         const int nimg = last_row / p.nc_hw - img0 + 1;   // <= kNcSlots (host check: nc_hw >= 43)
         float* ncs = epi_nc + group * (2 * kNcSlots * 256);
-        for (int i = tg; i < nimg * p.block_n; i += 128) {
-          const int sl = i / p.block_n, c = i - sl * p.block_n;
-          ncs[sl * 256 + c] = __ldg(p.nc_scale + size_t(img0 + sl) * p.Kout + n0 + c);
-          ncs[(kNcSlots + sl) * 256 + c] = __ldg(p.nc_shift + size_t(img0 + sl) * p.Kout + n0 + c);
+        // 16-byte loads, both vectors in flight before the stores: with two images and a 256-wide tile that is ONE
+        // round trip to L2 per tile (the scalar loop walked four dependent load -> store pairs per thread: 17 % of the
+        // kernel's stall samples, plus the barrier waits of everybody else; profiles/ncu/r02_full_fprop_nc56.txt)
+        const int q4 = p.block_n >> 2;
+        for (int i = tg; i < nimg * q4; i += 128) {
+          const int sl = i / q4, c = (i - sl * q4) * 4;
+          const size_t off = size_t(img0 + sl) * p.Kout + n0 + c;
+          const float4 vs = __ldg(reinterpret_cast<const float4*>(p.nc_scale + off));
+          const float4 vh = __ldg(reinterpret_cast<const float4*>(p.nc_shift + off));
+          *reinterpret_cast<float4*>(ncs + sl * 256 + c) = vs;
+          *reinterpret_cast<float4*>(ncs + (kNcSlots + sl) * 256 + c) = vh;
         }
         nc_slot = min(row, p.M - 1) / p.nc_hw - img0;
         epi_bar_sync(group);
