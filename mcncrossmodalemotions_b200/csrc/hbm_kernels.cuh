@@ -1080,16 +1080,21 @@ __global__ void se_squeeze_kernel(const T* __restrict__ u, int HW, int C, float*
     for (int k = 0; k < 8; ++k) mine[k] = acc[f][k];
   }
   __syncthreads();
-  // LX x 8 (channel-group, k) outputs, each summed over the VLY lanes by one thread
-  const int t = threadIdx.y * LX + threadIdx.x;
-  if (t < LX * 8) {
-    const int cg = t >> 3, k = t & 7;
+  // LX x 8 (channel-group, k) outputs, each summed over the VLY lanes by four threads (a quarter of the lanes each, in
+  // order), combined as (p0 + p1) + (p2 + p3): a fixed order for a given VLY, and a serial tail of VLY / 4 instead of VLY
+  const int nthreads = LX * LYt;
+  const int per = VLY >> 2;   // VLY is a multiple of 4 (1024 / LX or 8)
+  const unsigned lanes = __activemask();   // (whole warps, or the one partial warp of a tensor with fewer than 32 channels;
+                                           //  the trip count below is uniform within a warp: LX * 32 and nthreads are multiples of 8)
+  for (int t = threadIdx.y * LX + threadIdx.x; t < LX * 32; t += nthreads) {
+    const int o = t >> 2, quarter = t & 3;
+    const int cg = o >> 3, k = o & 7;
+    float ps = 0.f;
+    for (int j = quarter * per; j < (quarter + 1) * per; ++j) ps += part[(j * LX + cg) * 9 + k];
+    ps += __shfl_xor_sync(lanes, ps, 1);
+    ps += __shfl_xor_sync(lanes, ps, 2);
     const int c = (blockIdx.x * LX + cg) * 8 + k;
-    if (c < C) {
-      float tsum = 0.f;
-      for (int j = 0; j < VLY; ++j) tsum += part[(j * LX + cg) * 9 + k];
-      s[size_t(n) * C + c] = tsum / float(HW);
-    }
+    if (quarter == 0 && c < C) s[size_t(n) * C + c] = ps / float(HW);
   }
 }
 

@@ -757,14 +757,16 @@ extern "C" int xemo_op_se_squeeze(xemo_ctx* ctx, const void* u16, int N, int HW,
   const int C8 = C / 8;
   int lx = 1;
   while (lx < 32 && lx * 2 <= C8) lx *= 2;   // min(32, largest power of two <= C/8)
-  // pixel-stride lanes: 1024 / lx for the large maps; the 7 x 7 maps (49 pixels) would leave half of a 32-lane stride
-  // idle and pay a 1024-thread barrier for two loads per thread (1.4 TB/s in the launch list): 8 lanes there.
-  // Once the grid has a block per SM, 512-thread blocks that own two lanes each (same summation order, bit-identical
-  // result) co-schedule better (measured, teacher forward at 256 faces: 4.91 ms with 1024-thread blocks, 4.80 with 512,
+  // Virtual pixel-stride lanes (a function of the map and the channel count only, so that the mean of a face does not
+  // depend on the batch): 1024 / lx, but no more than HW / 8 -- a lane with fewer than ~8 pixels spends its time in the
+  // one-load-at-a-time tail (14 x 14 maps on 32 lanes: 0.037 ms per launch, on 16 lanes 0.027) -- and 8 for the 7 x 7 maps.
+  // A full 1024-lane block becomes 512 threads owning two lanes each once the grid has a block per SM (same summation
+  // order, bit-identical result; measured, teacher forward at 256 faces: 4.91 ms with 1024-thread blocks, 4.80 with 512,
   // 4.90 with 256; at 32 faces 1.25 / 1.30 / 1.32 ms: few blocks want all the threads).
   const int gx = (C8 + lx - 1) / lx;
-  const int ly = HW < 128 ? 8 : 1024 / lx;
-  const bool two = HW >= 128 && ly % 2 == 0 && gx * N >= ctx->num_sms;
+  int ly = 8;
+  while (ly * 2 <= 1024 / lx && ly * 2 <= HW / 8) ly *= 2;
+  const bool two = lx * ly == 1024 && gx * N >= ctx->num_sms;
   dim3 grid(gx, N), block(lx, two ? ly / 2 : ly);
   if (two) se_squeeze_kernel<__half, 2><<<grid, block, 0, ctx->stream>>>(static_cast<const __half*>(u16), HW, C, s);
   else se_squeeze_kernel<__half, 1><<<grid, block, 0, ctx->stream>>>(static_cast<const __half*>(u16), HW, C, s);

@@ -351,3 +351,19 @@ def test_se_squeeze_and_gate_do_not_depend_on_the_batch(env, dims):
         for n in (2, 32, 100):
             for a, b, what in zip(ref, run(n), ("squeeze", "nc_scale", "nc_shift", "gate")):
                 assert np.array_equal(a, b), (what, n)
+
+
+@pytest.mark.parametrize("shape", [(3, 49, 8), (2, 49, 16), (5, 200, 24), (4, 784, 40), (2, 3136, 64), (3, 130, 2048)])
+def test_se_squeeze_on_narrow_and_odd_tensors(env, shape):
+    """Global average pooling (mcnExtraLayers vl_nnglobalpool) on shapes outside SENet50's: fewer than 32 channels (one
+    partial warp per block), channel counts that are not powers of two, maps just above the 128-pixel switch."""
+    torch, ctx, stream = env
+    n, HW, Cc = shape
+    rng = np.random.default_rng(HW + Cc)
+    u = rng.standard_normal((n, HW, Cc)).astype(np.float16)
+    with torch.cuda.stream(stream):
+        ud = torch.from_numpy(u).cuda()
+        m = torch.full((n, Cc), -7.0, device="cuda")
+        ctx.op_se_squeeze(_p(ud), n, HW, Cc, _p(m))
+        ctx.sync()
+        assert np.abs(m.cpu().numpy() - u.astype(np.float64).mean(1)).max() < 2e-6
