@@ -398,18 +398,26 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // (kNC) this thread's image slot of the per-(image, channel) vectors
           const uint32_t nc_scale_u32 = kNC ? smem_u32(epi_nc + group * (2 * kNcSlots * 256) + nc_slot * 256) : 0u;
           const uint32_t nc_shift_u32 = kNC ? smem_u32(epi_nc + group * (2 * kNcSlots * 256) + (kNcSlots + nc_slot) * 256) : 0u;
-          auto process_fast = [&](const uint32_t (&v)[16], int jj, auto res_tag) {
-            constexpr bool kRes = decltype(res_tag)::value;
+          // the 16 columns' scale / shift vectors: fetched BEFORE the wait on the accumulator load they go with, so that the
+          // shared-memory latency hides behind it (ncu: the first FFMA after the eight LDS held ~10 % of the epilogue's
+          // stall samples on the HBM-bound layers, two epilogue warps per scheduler having nothing else to issue)
+          auto load_ss = [&](int jj, float4 (&sc)[4], float4 (&sh)[4]) {
             const uint32_t jb = uint32_t(q * cw + jj) * 4u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              sc[i] = lds_f4((kNC ? nc_scale_u32 : ss_scale_u32) + jb + i * 16);
+              sh[i] = lds_f4((kNC ? nc_shift_u32 : ss_shift_u32) + jb + i * 16);
+            }
+          };
+          auto process_fast = [&](const uint32_t (&v)[16], int jj, const float4 (&sc)[4], const float4 (&sh)[4], auto res_tag) {
+            constexpr bool kRes = decltype(res_tag)::value;
             float x[16];
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 sc = lds_f4((kNC ? nc_scale_u32 : ss_scale_u32) + jb + i * 4);
-              const float4 sh = lds_f4((kNC ? nc_shift_u32 : ss_shift_u32) + jb + i * 4);
-              x[i] = fmaf(__uint_as_float(v[i]), sc.x, sh.x);
-              x[i + 1] = fmaf(__uint_as_float(v[i + 1]), sc.y, sh.y);
-              x[i + 2] = fmaf(__uint_as_float(v[i + 2]), sc.z, sh.z);
-              x[i + 3] = fmaf(__uint_as_float(v[i + 3]), sc.w, sh.w);
+            for (int i = 0; i < 4; ++i) {
+              x[4 * i] = fmaf(__uint_as_float(v[4 * i]), sc[i].x, sh[i].x);
+              x[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), sc[i].y, sh[i].y);
+              x[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), sc[i].z, sh[i].z);
+              x[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), sc[i].w, sh[i].w);
             }
             const uint32_t c0 = (row_base + uint32_t(jj) * 2u) ^ row_xor, c1 = (row_base + uint32_t(jj) * 2u + 16u) ^ row_xor;
             if constexpr (kRes) {
@@ -431,15 +439,18 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             sts_u4(sbuf_u32 + c1, o[1]);
           };
           auto run_fast = [&](auto res_tag) {
+            float4 sc[4], sh[4];
             for (int jj = 0; jj < cw; jj += 32) {
+              load_ss(jj, sc, sh);
               tmem_ld_wait();
               const bool second = jj + 16 < cw;
               if (second) tmem_ld16(taddr + uint32_t(q * cw + jj + 16), vb);
-              process_fast(va, jj, res_tag);
+              process_fast(va, jj, sc, sh, res_tag);
               if (second) {
+                load_ss(jj + 16, sc, sh);
                 tmem_ld_wait();
                 if (jj + 32 < cw) tmem_ld16(taddr + uint32_t(q * cw + jj + 32), va);
-                process_fast(vb, jj + 16, res_tag);
+                process_fast(vb, jj + 16, sc, sh, res_tag);
               }
             }
           };
