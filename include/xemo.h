@@ -210,6 +210,14 @@ int xemo_debug_wgrad_plan(int N, int H, int W, int Cin, int ldy, int Kout, int R
 int xemo_debug_set_conv_pair_mode(int mode);
 int xemo_debug_conv_plan2(int N, int H, int W, int Cin, int Kout, int R, int S, int sh, int sw, int pt, int pb, int pl, int pr,
                           int num_sms, int* out13);
+/* Host-side planners of two memory-bound kernel families (no device needed; `-m "not gpu"` tests).
+ * xemo_debug_se_gate_plan: the SE gate's launch for N faces -- out[0] = cluster size K, out[1] = ranges of hidden units in
+ *   the last phase's sum (a function of C and Cr only), out[2] = thread groups per channel, out[3] = dynamic shared
+ *   memory in bytes, out[4] = grid size.  lin = 1: the form by linearity from mean_hw(t2) (Cm channels).
+ * xemo_debug_fixed_channel_grid: grid of a grid-stride kernel whose threads keep one channel group (C8 = C / 8 groups,
+ *   `threads` per block) when at most per_sm blocks per SM are resident. */
+int xemo_debug_se_gate_plan(int N, int C, int Cm, int Cr, int lin, int num_sms, int* out5);
+int xemo_debug_fixed_channel_grid(long long items, int C8, int threads, int num_sms, int per_sm);
 /* bias gradient: out[c] = scale * sum_p dy[p][c] */
 int xemo_op_colsum(xemo_ctx* ctx, const void* dy16, size_t P, int ld, int C, float scale, float* out);
 

@@ -83,6 +83,8 @@ SIGNATURES = {
     "xemo_debug_set_conv_pair_mode": (c_int, [c_int]),
     "xemo_debug_conv_plan2": (c_int, [c_int] * 14 + [P(c_int)]),
     "xemo_debug_wgrad_plan": (c_int, [c_int] * 15 + [P(c_int)]),
+    "xemo_debug_se_gate_plan": (c_int, [c_int] * 6 + [P(c_int)]),
+    "xemo_debug_fixed_channel_grid": (c_int, [C.c_longlong, c_int, c_int, c_int, c_int]),
     "xemo_op_colsum": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_float, c_void_p]),
     "xemo_op_maxpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p, c_void_p, c_void_p, c_void_p]),
     "xemo_op_maxpool_fwd_win": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),

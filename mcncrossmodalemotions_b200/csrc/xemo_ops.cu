@@ -774,6 +774,26 @@ extern "C" int xemo_op_se_squeeze(xemo_ctx* ctx, const void* u16, int N, int HW,
   return XEMO_OK;
 }
 
+extern "C" int xemo_debug_se_gate_plan(int N, int C, int Cm, int Cr, int lin, int num_sms, int* out5) {
+  if (!out5 || N < 1 || C < 1 || Cr < 1) return XEMO_ERR_INVALID;
+  const int groups = (N + kSeSpb - 1) / kSeSpb;
+  const int K = se_gate_cluster_size(groups, C, Cr, num_sms);
+  const int pc = se_gate_ranges(C, Cr), nout = C / K;
+  const int tg = se_gate_groups(pc, nout);
+  const size_t red = tg > 1 ? size_t(pc) * kSeSpb * nout : 0;
+  out5[0] = K;
+  out5[1] = pc;
+  out5[2] = tg;
+  out5[3] = int((size_t(kSeSpb) * ((lin ? Cm : 0) + C + Cr) + red) * sizeof(float));
+  out5[4] = groups * K;
+  return XEMO_OK;
+}
+
+extern "C" int xemo_debug_fixed_channel_grid(long long items, int C8, int threads, int num_sms, int per_sm) {
+  if (items < 0 || C8 < 1 || threads < 1 || num_sms < 1 || per_sm < 1) return -1;
+  return fixed_channel_grid(size_t(items), C8, threads, num_sms, per_sm);
+}
+
 extern "C" int xemo_op_se_gate(xemo_ctx* ctx, const float* s, int N, int C, int Cr, const float* w1, const float* b1,
                                const float* w2, const float* b2, float* gate) {
   XEMO_REQUIRE(ctx, s && w1 && w2 && gate && kSeSpb * (C + Cr) * 4 <= 48 * 1024 && C % 128 == 0, "se_gate: C must be a multiple of 128 and (C + Cr) <= 6144");

@@ -530,3 +530,56 @@ def test_loss_types_of_the_zoo():
         scale = 0.1 if lt == "euclidean" else 1.0
         np.testing.assert_allclose(dag.params["fc8f"], base.params["fc8f"] * scale, rtol=1e-6)
         np.testing.assert_array_equal(dag.params["fc7f"], base.params["fc7f"])
+
+
+def test_se_gate_launch_plan_follows_the_batch_but_not_the_summation_order():
+    """csrc/se_gate.cuh: the cluster size K follows the batch (1 at 256 faces, up to 4 at small batches, never more CTAs
+    than SMs, whole divisors of C and Cr); the ranges of hidden units that define the last phase's summation order depend
+    on (C, Cr) only; shared memory stays under the 48 KB default for SENet50's four stages in both forms."""
+    import ctypes as C
+
+    from mcncrossmodalemotions_b200 import _lib
+
+    lib = _lib.load_library()
+    out = (C.c_int * 5)()
+    stages = [(256, 64), (512, 128), (1024, 256), (2048, 512)]
+    for c, cm in stages:
+        cr = c // 16
+        ranges = set()
+        for n, want_k in [(256, 1), (128, 2), (100, 2), (64, 4), (32, 4), (3, 4), (1, 4)]:
+            for lin in (0, 1):
+                assert lib.xemo_debug_se_gate_plan(n, c, cm, cr, lin, 148, out) == 0
+                k, pc, tg, smem, grid = list(out)
+                assert k == want_k, (c, n, k)
+                assert grid == (n + 1) // 2 * k and grid <= 148
+                assert c % k == 0 and cr % k == 0 and c // k >= 32 and cr // k >= 2
+                assert smem <= 48 * 1024
+                assert pc >= 1 and cr % pc == 0 and cr // pc >= 8 and tg <= pc and (tg == 1 or tg * (c // k) <= 1024)
+                ranges.add(pc)
+        assert len(ranges) == 1, (c, ranges)            # the summation order does not know the batch
+    # 148 SMs: 75 groups (150 faces) no longer fit twice
+    assert lib.xemo_debug_se_gate_plan(150, 1024, 256, 64, 0, 148, out) == 0 and out[0] == 1
+    assert lib.xemo_debug_se_gate_plan(148, 1024, 256, 64, 0, 148, out) == 0 and out[0] == 2
+
+
+def test_fixed_channel_grids_are_whole_channel_multiples_and_never_exceed_the_resident_blocks():
+    """A grid-stride kernel whose threads keep their channel group needs grid * threads to be a multiple of C / 8; when the
+    grid is capped at the resident blocks it rounds DOWN (592 -> 591 on the 96-channel stem, not 594: two blocks in a
+    second wave cost 20 % of the kernel), small problems round up."""
+    import math
+
+    from mcncrossmodalemotions_b200 import _lib
+
+    lib = _lib.load_library()
+    g = lib.xemo_debug_fixed_channel_grid
+    assert g(10**9, 12, 256, 148, 4) == 591              # stem: 96 channels, 4 resident blocks per SM
+    assert g(10**9, 12, 256, 148, 3) == 444
+    assert g(10**9, 32, 256, 148, 3) == 444              # 256 channels: any grid works
+    assert g(10**9, 12, 256, 148, 48) == 7104
+    assert g(1000, 12, 256, 148, 8) == 6                 # 4 blocks of work, rounded up to a multiple of 3
+    assert g(0, 12, 256, 148, 8) == 3
+    for c8 in (1, 3, 8, 12, 48, 96, 512):
+        for per_sm in (1, 2, 3, 5, 8):
+            n = g(10**10, c8, 256, 148, per_sm)
+            assert (n * 256) % c8 == 0
+            assert n <= 148 * per_sm or n == c8 // math.gcd(c8, 256)       # (never below one channel multiple)
