@@ -193,8 +193,15 @@ class StudentNet(Net):
             raise ValueError("unrecognised regression loss: %s" % (loss_type,))
         super().__init__("vggvox", params, batch, width, 0, num_classes, ctx, device, stream)
         self.W, self.loss_type = width, loss_type
-        self._check(self.lib.xemo_net_set_loss(self.handle, LOSSES[loss_type], float(temperature), float(grad_scale)))
+        self.temperature, self.grad_scale = float(temperature), float(grad_scale)
+        self._check(self.lib.xemo_net_set_loss(self.handle, LOSSES[loss_type], self.temperature, self.grad_scale))
         self.hyper = dict(lr=1e-4, momentum=0.9, weight_decay=5e-4, batch_size=self.N)
+
+    def set_grad_scale(self, grad_scale):
+        """Loss scale of the fp16 activation-gradient chain (the filter / bias / BN reductions undo it in fp32).  It is baked
+        into the captured step: the next step re-captures (and restarts the epoch's per-class counters)."""
+        self.grad_scale = float(grad_scale)
+        self._check(self.lib.xemo_net_set_loss(self.handle, LOSSES[self.loss_type], self.temperature, self.grad_scale))
 
     def set_overlap(self, mode):
         """-1 auto (on for batch <= 64), 0 one stream, 1 forked branches inside the captured step"""

@@ -58,6 +58,41 @@ def save_checkpoint(exp_dir, epoch, program, stats):
              **{"m:" + k: v for k, v in momentum.items()}, stats=json.dumps(stats))
 
 
+class LossScaler:
+    """Dynamic loss scale for the fp16 activation-gradient chain (the reference trains in `single` and has no such knob).
+    A non-finite gradient -- detected on the device, where the guarded update has already skipped that step -- halves the
+    scale; `growth_interval` consecutive clean steps double it again, within [min_scale, the initial scale].  Under data
+    parallelism every rank sees the same flag (the guard scans the all-reduced gradient), so the ranks move in step."""
+
+    def __init__(self, initial=1024.0, growth_interval=2000, min_scale=1.0):
+        self.initial = self.scale = float(initial)
+        self.growth_interval, self.min_scale = int(growth_interval), float(min_scale)
+        self.clean = 0
+        self.overflows = 0
+
+    def update(self, overflow):
+        """Feed one step's flag; returns the scale to use from the next step on."""
+        if overflow:
+            self.overflows += 1
+            self.clean = 0
+            self.scale = max(self.scale / 2.0, self.min_scale)
+        else:
+            self.clean += 1
+            if self.clean >= self.growth_interval and self.scale < self.initial:
+                self.scale = min(self.scale * 2.0, self.initial)
+                self.clean = 0
+        return self.scale
+
+
+def apply_loss_scale(prog, scaler, overflow, log=print):
+    """One step of the policy on a StudentNet-like object (`grad_scale`, `set_grad_scale`)."""
+    new = scaler.update(overflow)
+    if new != prog.grad_scale:
+        log("loss scale %g -> %g (%s)" % (prog.grad_scale, new, "non-finite gradient, step skipped" if overflow else "clean run"))
+        prog.set_grad_scale(new)
+    return new
+
+
 def load_checkpoint(exp_dir, epoch):
     z = np.load(os.path.join(exp_dir, "net-epoch-%d.npz" % epoch), allow_pickle=False)
     params = {k[2:]: z[k] for k in z.files if k.startswith("p:")}
@@ -88,6 +123,7 @@ def cnn_train_dag(params, imdb, get_batch, *, learning_rate, batch_size=64, num_
     if mom is not None:
         prog.load_momentum(mom)
     comm = Comm.from_torch(prog.ctx) if world > 1 else None   # one process per GPU, torch.distributed only hands out the NCCL id
+    scaler = LossScaler(prog.grad_scale)
     for epoch in range(start, num_epochs):
         rng = np.random.default_rng([seed, epoch])   # per-epoch stream: a resumed run draws the same permutations
         lr = float(learning_rate[min(epoch, len(learning_rate) - 1)])
@@ -107,6 +143,9 @@ def cnn_train_dag(params, imdb, get_batch, *, learning_rate, batch_size=64, num_
             inputs = get_batch(imdb, idx)
             prog.train_step(inputs["data"], inputs[tkey], comm, weights=inputs.get("instanceWeights"))
             m = prog.metrics()   # objective / classerror of this batch; class counters accumulate
+            apply_loss_scale(prog, scaler, m["nonfinite_grad"], log)
+            if m["nonfinite_grad"]:
+                continue             # (the update was skipped on the device; its objective is not a number either)
             obj += m["objective"]; err += m["classerror"]; seen += len(idx)
         m = prog.metrics()
         tr = extract_stats(dict(objective=obj, classerror=err, correct=m["correct"], count=m["count"]), seen)

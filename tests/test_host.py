@@ -583,3 +583,38 @@ def test_fixed_channel_grids_are_whole_channel_multiples_and_never_exceed_the_re
             n = g(10**10, c8, 256, 148, per_sm)
             assert (n * 256) % c8 == 0
             assert n <= 148 * per_sm or n == c8 // math.gcd(c8, 256)       # (never below one channel multiple)
+
+
+def test_dynamic_loss_scale_policy():
+    """train.LossScaler / apply_loss_scale: halve on a non-finite gradient, grow back after a clean run, stay within
+    [1, initial]; the network is only touched when the scale changes."""
+    from mcncrossmodalemotions_b200.train import LossScaler, apply_loss_scale
+
+    class FakeNet:
+        def __init__(self):
+            self.grad_scale, self.calls = 1024.0, []
+
+        def set_grad_scale(self, s):
+            self.grad_scale = s
+            self.calls.append(s)
+
+    net, sc, lines = FakeNet(), LossScaler(1024.0, growth_interval=3), []
+    for _ in range(5):
+        apply_loss_scale(net, sc, False, lines.append)
+    assert net.calls == [] and sc.scale == 1024.0          # never above the initial scale
+    apply_loss_scale(net, sc, True, lines.append)
+    apply_loss_scale(net, sc, True, lines.append)
+    assert net.calls == [512.0, 256.0] and sc.overflows == 2
+    apply_loss_scale(net, sc, False, lines.append)
+    apply_loss_scale(net, sc, False, lines.append)
+    assert net.grad_scale == 256.0
+    apply_loss_scale(net, sc, False, lines.append)          # third clean step in a row
+    assert net.grad_scale == 512.0
+    apply_loss_scale(net, sc, True, lines.append)           # an overflow restarts the clean run
+    for _ in range(2):
+        apply_loss_scale(net, sc, False, lines.append)
+    assert net.grad_scale == 256.0
+    for _ in range(20):
+        apply_loss_scale(net, sc, True, lines.append)
+    assert net.grad_scale == 1.0 and sc.scale == 1.0         # floor
+    assert len(lines) == len(net.calls) and "non-finite" in lines[0]
