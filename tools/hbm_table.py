@@ -1,7 +1,10 @@
 """Achieved HBM GB/s of the memory-bound kernels of one distillation step: algorithmic bytes (tensor sizes read + written,
 fp16 activations, per-GPU batch 256, 512x300 spectrograms) over the per-launch duration of an ncu launch list
 (`--metrics gpu__time_duration.sum --clock-control none`: serialised, cold-cache).
-    python tools/hbm_table.py profiles/r01_launches_step_final.csv [peak_GBs] > profiles/r01_hbm_kernels.txt"""
+    python tools/hbm_table.py profiles/r02_launches_step.csv [peak_GBs] > profiles/r02_hbm_kernels.txt
+Round-2 kernel sequence: SE by linearity on the 56x56 / 28x28 stages (their squeeze reads the 3x3 output, C/4 channels; no
+excite pass), squeeze -> gate -> excite on the 14x14 / 7x7 stages; pooled tensors of the student's first layer carry a
+128-channel pitch.  (The round-1 sequence: git history of this file.)"""
 import csv
 import json
 import os
@@ -25,12 +28,13 @@ for r in rows[h + 1:]:
     seq.append((r[ki].split("(")[0].replace("void ", "").replace("xemo::", ""), us))
 starts = [i for i, (n, _) in enumerate(seq) if "face_u8" in n]
 st = starts[1] if len(starts) > 1 else starts[0]
-step = seq[st:st + 199]
+step = seq[st:st + 188]
 MB = 1e6
 act = lambda h_, w_, c: N * h_ * w_ * c * 2 / MB          # fp16 NHWC tensor of the batch, MB
 stage_hw = {2: 56, 3: 28, 4: 14, 5: 7}
 stage_c = {2: 256, 3: 512, 4: 1024, 5: 2048}
 stage_blocks = [2] * 3 + [3] * 4 + [4] * 6 + [5] * 3
+excite_blocks = [4] * 6 + [5] * 3
 student_bn = [(62, 36, 256), (30, 17, 384), (30, 17, 256), (30, 17, 256), (1, 8, 4096), (1, 1, 1024)]   # bn2..bn7 inputs
 out = []
 sq = ex = bs = br = ba = 0
@@ -42,16 +46,17 @@ for name, us in step:
         b, what = act(112, 112, 64) + act(56, 56, 64), "teacher pool1"
     elif name.startswith("se_squeeze"):
         s = stage_blocks[sq]; sq += 1
-        b, what = act(stage_hw[s], stage_hw[s], stage_c[s]), "SE squeeze, stage %d" % s
+        lin = s <= 3                                      # by linearity: the squeeze reads t2 (C / 4 channels)
+        b, what = act(stage_hw[s], stage_hw[s], stage_c[s] // (4 if lin else 1)), "SE squeeze, stage %d%s" % (s, " (of the 3x3 output)" if lin else "")
     elif name.startswith("se_excite"):
-        s = stage_blocks[ex]; ex += 1
+        s = excite_blocks[ex]; ex += 1
         b, what = 3 * act(stage_hw[s], stage_hw[s], stage_c[s]), "SE excite + shortcut + ReLU, stage %d" % s
     elif name.startswith("spec_s2d"):
         b, what = N * 512 * 300 * 4 / MB + act(257, 148, 16), "spectrogram -> space-to-depth"
     elif name.startswith("stem_autocorr"):
         b, what = act(257, 148, 16), "patch autocorrelation (mma.sync; compute-bound)"
     elif name.startswith("maxpool_fwd_h2_kernel<1, 3, 3, 1>") and us > 300:
-        b, what = act(254, 148, 96) + 2.5 * act(126, 73, 96), "student pool1: BN+ReLU folded, y + arg-max + winner"
+        b, what = act(254, 148, 96) + 2.5 * act(126, 73, 128), "student pool1: BN+ReLU folded, y + arg-max + winner (128-channel pitch)"
     elif name.startswith("maxpool_fwd_h2_kernel<1, 3, 3, 1>"):
         b, what = act(62, 36, 256) + 1.5 * act(30, 17, 256), "student pool2"
     elif name.startswith("bn_stats"):
@@ -64,9 +69,9 @@ for name, us in step:
         g = student_bn[::-1][ba]; ba += 1
         b, what = 3 * act(*g), "BN backward apply, %dx%dx%d" % g
     elif name.startswith("stem_pool_bn_reduce"):
-        b, what = 3 * act(126, 73, 96), "stem BN reductions + mask at the pooled resolution"
+        b, what = 3 * act(126, 73, 128), "stem BN reductions + mask at the pooled resolution"
     elif name.startswith("maxpool_bwd_3x3s2") and us > 300:
-        b, what = 1.5 * act(126, 73, 96) + act(254, 148, 96), "student pool1 backward"
+        b, what = 1.5 * act(126, 73, 128) + act(254, 148, 96), "student pool1 backward"
     elif name.startswith("maxpool_bwd_3x3s2"):
         b, what = 1.5 * act(30, 17, 256) + act(62, 36, 256), "student pool2 backward"
     elif name.startswith("sgd_momentum"):
